@@ -1,0 +1,56 @@
+"""ctypes loader for tests/native/libhostcheck.so (test harness around the product's host/device-portable code)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "native"), "-s"])
+        _lib = C.CDLL(os.path.join(_HERE, "native", "_build", "libhostcheck.so"))
+        _lib.hc_block_codes.restype = C.c_uint32
+        _lib.hc_hdr_words.restype = C.c_uint32
+    return _lib
+
+
+def code_lengths(freq, cap):
+    f = np.ascontiguousarray(freq, dtype=np.uint32)
+    w = np.zeros(len(f), dtype=np.uint8)
+    lib().hc_code_lengths(f.ctypes.data_as(C.c_void_p), len(f), cap, w.ctypes.data_as(C.c_void_p))
+    return w
+
+
+def block_codes(hist320):
+    L = lib()
+    h = np.ascontiguousarray(hist320, dtype=np.uint32)
+    lit = np.zeros(288, dtype=np.uint32)
+    dist = np.zeros(32, dtype=np.uint32)
+    hdr = np.zeros(L.hc_hdr_words(), dtype=np.uint32)
+    nbits = L.hc_block_codes(h.ctypes.data_as(C.c_void_p), lit.ctypes.data_as(C.c_void_p),
+                             dist.ctypes.data_as(C.c_void_p), hdr.ctypes.data_as(C.c_void_p))
+    return lit, dist, hdr, nbits
+
+
+def fixed_codes():
+    lit = np.zeros(288, dtype=np.uint32)
+    dist = np.zeros(32, dtype=np.uint32)
+    lib().hc_fixed_codes(lit.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p))
+    return lit, dist
+
+
+def length_code(n):
+    o = (C.c_uint32 * 3)()
+    lib().hc_length_code(n, o)
+    return tuple(o)
+
+
+def dist_code(d):
+    o = (C.c_uint32 * 3)()
+    lib().hc_dist_code(d, o)
+    return tuple(o)

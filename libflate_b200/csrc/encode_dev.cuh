@@ -1,0 +1,64 @@
+// encode_dev.cuh -- device-side view of one encode batch + stage timing helper.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace b2f {
+
+struct EncDev {
+    // inputs
+    const uint8_t *in;            // concatenated stream bytes (+ >= 64 B readable padding)
+    const ChunkDesc *chunks; uint32_t n_chunks;
+    const BlockDesc *blocks; uint32_t n_blocks;
+    const uint32_t *seg0, *pt0, *tile0, *grp0;       // per-chunk prefix arrays, n_chunks + 1 entries each
+    uint32_t n_segs, n_ptiles, n_tiles, n_grps;
+    uint32_t window, max_len;
+    // LZ77 stage
+    uint16_t *link;               // [N]  distance to previous same-hash position
+    uint32_t *md;                 // [N]  0 | len<<16 | dist  (candidate at every position)
+    uint16_t *exit_tab;           // [n_tiles * 258]
+    uint16_t *tile_entry;         // [n_tiles]
+    uint32_t *sym;                // [N]  tile-slotted symbol words
+    uint32_t *tile_nsym;          // [n_tiles]
+    // entropy stage
+    uint32_t *hist;               // [n_blocks * 320]
+    uint32_t *litcode;            // [n_blocks * 288]  width<<16 | reversed code
+    uint32_t *distcode;           // [n_blocks * 32]
+    uint32_t *hdr_words;          // [n_blocks * kHdrWords]
+    uint32_t *hdr_bits;           // [n_blocks]
+    uint32_t *tile_bits;          // [n_tiles]
+    uint64_t *tile_bitrel;        // [n_tiles]  bit offset inside the block's symbol area
+    uint64_t *blk_bits, *blk_bitoff, *blk_markpos;   // [n_blocks]
+    // streams
+    uint32_t n_streams;
+    const uint32_t *stream_blk0;  // [n_streams + 1]
+    const uint64_t *out_base;     // [n_streams] byte offset of the stream in out (16-aligned)
+    const uint32_t *hdr_len;      // [n_streams] container header bytes
+    uint64_t *stream_end_bits;    // [n_streams] end of the deflate bits, relative to out_base*8
+    uint32_t *out_words;          // output buffer viewed as u32 (zero-filled before the entropy stage)
+};
+
+struct StageTimer {
+    enum { kMax = 24 };
+    cudaEvent_t ev[kMax + 1];
+    const char *name[kMax];
+    int n = 0;
+    bool enabled = true, created = false;
+    void create() { if (!created) { for (int i = 0; i <= kMax; i++) cudaEventCreate(&ev[i]); created = true; } }
+    void destroy() { if (created) { for (int i = 0; i <= kMax; i++) cudaEventDestroy(ev[i]); created = false; } }
+    void reset() { n = 0; }
+    void mark(cudaStream_t st, const char *nm) { if (!enabled || !created || n >= kMax) return; cudaEventRecord(ev[n], st); name[n++] = nm; }
+    void finish(cudaStream_t st) { if (!enabled || !created) return; cudaEventRecord(ev[n], st); }
+    // after a stream synchronize
+    float stage_ms(int i) const { float ms = 0; if (i < n) cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); return ms; }
+    float total_ms() const { float ms = 0; if (n > 0) cudaEventElapsedTime(&ms, ev[0], ev[n]); return ms; }
+};
+
+cudaError_t enc_init_attributes();
+cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm);
+cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm);
+cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t *total, uint32_t *dst, cudaStream_t st);
+uint32_t enc_launch_count_lz();
+uint32_t enc_launch_count_entropy(bool has_tiles);
+
+}  // namespace b2f

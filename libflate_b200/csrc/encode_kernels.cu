@@ -1,0 +1,489 @@
+// encode_kernels.cu -- the DEFLATE encode hot path as hand-written sm_100a kernels.
+//
+// Pipeline (one launch each, all on the ctx stream; see DESIGN.md for bytes/unit and rooflines):
+//   K1 lz_chain      one warp per <=256 KiB segment: ordered hash chains out of shared memory   (E2/A2)
+//   K2 lz_match      CTA per 16 KiB tile, 48 KiB window staged in shared memory: prev + LCP     (E2/L1)
+//   K3 parse_exits   thread per 2 KiB tile: right-to-left exit DP of the greedy walk            (E2)
+//   K4 parse_stitch  thread per chunk: chain the tile entry points
+//   K5 parse_emit    thread per tile: walk, emit symbols, per-block histograms                  (S1/S2)
+//   K6 huff_build    one lane per DEFLATE block: code lengths, canonical codes, header bits     (H1-H3/S3/S4)
+//   K7 tile_bits     warp per tile: coded size of the tile
+//   K8 scan_tiles / scan_blocks: bit offsets of every tile / block / stream                     (B2, E1)
+//   K9 write_headers warp per block: BFINAL/BTYPE, dynamic header, EOB, sync marker             (B2)
+//   K10 bitpack      warp per tile: LSB-first packing in shared memory, coalesced store         (B1)
+// Reference behaviour: libflate_lz77/src/default.rs:59-183, src/deflate/encode.rs:261-426,
+// src/deflate/symbol.rs:95-183,321-386,486-540, src/huffman.rs:35-55,192-363, src/bit.rs:25-49.
+#include "common.cuh"
+#include "huff_build.cuh"
+#include "encode_dev.cuh"
+
+namespace b2f {
+
+// index of the chunk whose prefix range contains idx: prefix[c] <= idx < prefix[c+1]
+__device__ __forceinline__ uint32_t find_owner(const uint32_t *__restrict__ prefix, uint32_t n, uint32_t idx) {
+    uint32_t lo = 0, hi = n;                 // invariant: prefix[lo] <= idx < prefix[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// =============================================================================== K1 lz_chain
+// link[p] = distance to the nearest earlier position of the same chunk whose trigram has the same
+// 14-bit hash (0 = none within 32768).  Every position < end is "inserted" exactly once in
+// increasing order (default.rs:78, 92-97), so this ordered chain is parse independent.
+__global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
+    extern __shared__ uint32_t head[];       // 1 << kHashBits entries: last position + 1
+    const uint32_t lane = threadIdx.x;
+    const uint32_t seg = blockIdx.x;
+    const uint32_t c = find_owner(E.seg0, E.n_chunks, seg);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t n = cd.len;
+    const uint32_t end = (n > 3 ? n : 3) - 3;
+    const uint32_t s_start = (seg - E.seg0[c]) * kSeg;
+    const uint32_t s_end = min(s_start + kSeg, n);
+    const uint32_t lim = min(s_end, end);
+    const uint32_t ws = s_start > kLookback ? s_start - kLookback : 0;
+    for (uint32_t i = lane; i < (1u << kHashBits); i += 32) head[i] = 0;
+    __syncwarp();
+    const uint8_t *__restrict__ p = E.in + cd.off;
+    uint16_t *__restrict__ lk = E.link + cd.off;
+    for (uint32_t q = max(lim, s_start) + lane; q < s_end; q += 32) lk[q] = 0;   // tail without a trigram
+    for (uint32_t base = ws; base < lim; base += 32) {
+        const uint32_t pos = base + lane;
+        const bool valid = pos < lim;
+        uint32_t h = 0x80000000u | lane, old = 0;
+        if (valid) {
+            uint32_t t = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
+            h = (t * 0x9E3779B1u) >> (32 - kHashBits);
+            old = head[h];
+        }
+        const uint32_t m = __match_any_sync(0xFFFFFFFFu, h);
+        const uint32_t lower = m & ((1u << lane) - 1u);
+        const uint32_t prev1 = lower ? (base + (31 - __clz((int)lower)) + 1) : old;
+        if (valid) {
+            if (pos >= s_start) {
+                uint32_t d = prev1 ? pos + 1 - prev1 : 0;
+                if (d > kLookback) d = 0;
+                lk[pos] = (uint16_t)d;
+            }
+            if ((m >> lane) == 1u) head[h] = pos + 1;     // highest lane of the group publishes
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================== K2 lz_match
+__device__ __forceinline__ uint32_t ld32u(const uint8_t *s, uint32_t off) {     // unaligned 4-byte read from smem
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(s + (off & ~3u));
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+constexpr uint32_t kMatchSmem = kPTile + kLookback + 261 + 16 + 32;
+
+// md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
+// the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
+__global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
+    extern __shared__ __align__(16) uint8_t sb[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t pt = blockIdx.x;
+    const uint32_t c = find_owner(E.pt0, E.n_chunks, pt);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t n = cd.len;
+    const uint32_t end = (n > 3 ? n : 3) - 3;
+    const uint32_t ts = (pt - E.pt0[c]) * kPTile;
+    const uint32_t te = min(ts + kPTile, n);
+    const uint32_t lo = ts > kLookback ? ts - kLookback : 0;
+    const uint32_t hi = min(n, te + 261);
+    const uint64_t g_lo = cd.off + lo;
+    const uint64_t g_al = g_lo & ~15ull;
+    const uint32_t shift = (uint32_t)(g_lo - g_al);
+    const uint32_t nvec = (hi - lo + shift + 15) >> 4;
+    const uint4 *__restrict__ gsrc = reinterpret_cast<const uint4 *>(E.in + g_al);
+    uint4 *sdst = reinterpret_cast<uint4 *>(sb);
+    for (uint32_t i = tid; i < nvec; i += 512) sdst[i] = __ldg(gsrc + i);
+    __syncthreads();
+    const uint16_t *__restrict__ lk = E.link + cd.off;
+    uint32_t *__restrict__ md = E.md + cd.off;
+    const uint32_t sbase = shift - lo;        // smem index of chunk position x is x + sbase (mod 2^32 arithmetic)
+    for (uint32_t pos = ts + tid; pos < te; pos += 512) {
+        uint32_t out = 0;
+        if (pos < end) {
+            const uint32_t si = pos + sbase;
+            const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
+            uint32_t d = lk[pos], total = 0, j = pos;
+            bool found = false;
+            while (d) {
+                total += d;
+                if (total > E.window) break;
+                j -= d;
+                const uint32_t sj = j + sbase;
+                const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
+                if (tj == t) { found = true; break; }
+                d = lk[j];
+            }
+            if (found) {
+                const uint32_t a = si + 3, b = j + sbase + 3;
+                const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
+                uint32_t k = 0;
+                while (k < limit) {
+                    const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
+                    if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    k += 4;
+                }
+                if (k > limit) k = limit;
+                out = ((3 + k) << 16) | total;
+            }
+        }
+        md[pos] = out;
+    }
+}
+
+// =============================================================================== K3 parse_exits
+// Greedy walk i -> i + step(i), step = match length or 1.  For a tile [ts,te) and each of the <= 258
+// positions a previous tile can jump into, exit = (first position >= te reached) - te  (SURVEY App. C).
+constexpr uint32_t kRing = 260;
+__global__ void __launch_bounds__(64) k_parse_exits(EncDev E) {
+    __shared__ uint16_t ring[64 * kRing];
+    const uint32_t tile = blockIdx.x * 64 + threadIdx.x;
+    if (tile >= E.n_tiles) return;
+    const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t n = cd.len;
+    const uint32_t ts = (tile - E.tile0[c]) * kTile;
+    const uint32_t te = min(ts + kTile, n);
+    uint16_t *r = ring + threadIdx.x * kRing;
+    const uint32_t *__restrict__ m = E.md + cd.off;
+    uint16_t *__restrict__ xt = E.exit_tab + (uint64_t)tile * kExitW;
+    for (uint32_t i = te; i-- > ts;) {
+        const uint32_t v = m[i];
+        const uint32_t nx = i + (v ? (v >> 16) : 1u);
+        uint32_t ex;
+        if (nx >= te) ex = nx - te; else ex = r[(nx - ts) % kRing];
+        r[(i - ts) % kRing] = (uint16_t)ex;
+        if (i - ts < kExitW) xt[i - ts] = (uint16_t)ex;
+    }
+}
+
+// =============================================================================== K4 parse_stitch
+__global__ void __launch_bounds__(64) k_parse_stitch(EncDev E) {
+    const uint32_t c = blockIdx.x * 64 + threadIdx.x;
+    if (c >= E.n_chunks) return;
+    const uint32_t t0 = E.tile0[c], t1 = E.tile0[c + 1];
+    uint32_t p = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+        E.tile_entry[t] = (uint16_t)p;
+        if (t + 1 < t1) p = E.exit_tab[(uint64_t)t * kExitW + p];
+    }
+}
+
+// =============================================================================== K5 parse_emit
+__global__ void __launch_bounds__(64) k_parse_emit(EncDev E) {
+    __shared__ uint32_t sh[kHistStride];
+    const uint32_t grp = blockIdx.x;
+    const uint32_t c = find_owner(E.grp0, E.n_chunks, grp);
+    const ChunkDesc cd = E.chunks[c];
+    for (uint32_t i = threadIdx.x; i < kHistStride; i += 64) sh[i] = 0;
+    __syncthreads();
+    const uint32_t n = cd.len;
+    const uint32_t tk = (grp - E.grp0[c]) * kGrpTiles + threadIdx.x;      // tile index inside the chunk
+    const uint32_t ntile_c = E.tile0[c + 1] - E.tile0[c];
+    if (tk < ntile_c) {
+        const uint32_t tile = E.tile0[c] + tk;
+        const uint32_t ts = tk * kTile, te = min(ts + kTile, n);
+        const uint32_t *__restrict__ m = E.md + cd.off;
+        const uint8_t *__restrict__ p = E.in + cd.off;
+        uint32_t *__restrict__ so = E.sym + cd.off + ts;
+        uint32_t i = ts + E.tile_entry[tile], cnt = 0;
+        while (i < te) {
+            const uint32_t v = m[i];
+            const uint32_t b = p[i];
+            if (v) {
+                uint32_t lc, le, lx, dc, de, dx;
+                length_code(v >> 16, lc, le, lx);
+                dist_code(v & 0xFFFFu, dc, de, dx);
+                atomicAdd(&sh[lc], 1u);
+                atomicAdd(&sh[286 + dc], 1u);
+                so[cnt++] = kSymPtr | v;
+                i += v >> 16;
+            } else {
+                atomicAdd(&sh[b], 1u);
+                so[cnt++] = b;
+                i += 1;
+            }
+        }
+        E.tile_nsym[tile] = cnt;
+    }
+    __syncthreads();
+    uint32_t *__restrict__ gh = E.hist + (uint64_t)cd.block * kHistStride;
+    for (uint32_t i = threadIdx.x; i < 316; i += 64) if (sh[i]) atomicAdd(&gh[i], sh[i]);
+}
+
+// =============================================================================== K6 huff_build
+__global__ void __launch_bounds__(32) k_huff_build(EncDev E) {
+    __shared__ HuffWork W;
+    const uint32_t b = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    uint32_t *lit = E.litcode + (uint64_t)b * kLitStride;
+    uint32_t *dist = E.distcode + (uint64_t)b * kDistStride;
+    if (E.blocks[b].fixed) {
+        build_fixed_codes(lit, dist);
+        E.hdr_bits[b] = 0;
+    } else {
+        E.hdr_bits[b] = build_block_codes(E.hist + (uint64_t)b * kHistStride, lit, dist, E.hdr_words + (uint64_t)b * kHdrWords, W);
+    }
+}
+
+// =============================================================================== symbol -> bits
+__device__ __forceinline__ void sym_bits(uint32_t s, const uint32_t *__restrict__ lit, const uint32_t *__restrict__ dist, uint64_t &v, uint32_t &nb) {
+    if (s & kSymPtr) {
+        uint32_t lc, le, lx, dc, de, dx;
+        length_code((s >> 16) & 0x1FFu, lc, le, lx);
+        dist_code(s & 0xFFFFu, dc, de, dx);
+        const uint32_t cl = __ldg(lit + lc), cdist = __ldg(dist + dc);
+        const uint32_t wl = cl >> 16, wd = cdist >> 16;
+        v = (uint64_t)(cl & 0xFFFFu) | ((uint64_t)lx << wl) | ((uint64_t)(cdist & 0xFFFFu) << (wl + le)) | ((uint64_t)dx << (wl + le + wd));
+        nb = wl + le + wd + de;
+    } else {
+        const uint32_t cl = __ldg(lit + s);
+        v = cl & 0xFFFFu; nb = cl >> 16;
+    }
+}
+
+// =============================================================================== K7 tile_bits
+__global__ void __launch_bounds__(256) k_tile_bits(EncDev E) {
+    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile >= E.n_tiles) return;
+    const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t ts = (tile - E.tile0[c]) * kTile;
+    const uint32_t *__restrict__ so = E.sym + cd.off + ts;
+    const uint32_t *lit = E.litcode + (uint64_t)cd.block * kLitStride;
+    const uint32_t *dist = E.distcode + (uint64_t)cd.block * kDistStride;
+    const uint32_t nsym = E.tile_nsym[tile];
+    uint32_t sum = 0;
+    for (uint32_t k = lane; k < nsym; k += 32) { uint64_t v; uint32_t nb; sym_bits(so[k], lit, dist, v, nb); sum += nb; }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) E.tile_bits[tile] = sum;
+}
+
+// =============================================================================== K8a scan_tiles (CTA per block)
+__global__ void __launch_bounds__(256) k_scan_tiles(EncDev E) {
+    __shared__ uint64_t wsum[8];
+    __shared__ uint64_t carry_s;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const BlockDesc bd = E.blocks[b];
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < bd.ntiles; base += 256) {
+        const uint32_t k = base + tid;
+        const uint64_t x = k < bd.ntiles ? E.tile_bits[bd.tile0 + k] : 0;
+        uint64_t incl = x;
+        for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        uint64_t woff = 0;
+        for (uint32_t w = 0; w < wid; w++) woff += wsum[w];
+        const uint64_t carry = carry_s;
+        if (k < bd.ntiles) E.tile_bitrel[bd.tile0 + k] = carry + woff + incl - x;
+        __syncthreads();
+        if (tid == 255) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t eobw = E.litcode[(uint64_t)b * kLitStride + 256] >> 16;
+        E.blk_bits[b] = 3ull + E.hdr_bits[b] + carry_s + eobw;
+    }
+}
+
+// =============================================================================== K8b scan_blocks (thread per stream)
+__global__ void __launch_bounds__(64) k_scan_blocks(EncDev E) {
+    const uint32_t s = blockIdx.x * 64 + threadIdx.x;
+    if (s >= E.n_streams) return;
+    uint64_t pos = (uint64_t)E.hdr_len[s] * 8;
+    for (uint32_t b = E.stream_blk0[s]; b < E.stream_blk0[s + 1]; b++) {
+        E.blk_bitoff[b] = pos;
+        pos += E.blk_bits[b];
+        if (E.blocks[b].sync_after) {       // empty stored block, byte aligned (encode.rs:225-234)
+            pos += 3;
+            pos = (pos + 7) & ~7ull;
+            E.blk_markpos[b] = pos;
+            pos += 32;
+        }
+    }
+    E.stream_end_bits[s] = pos;
+}
+
+__device__ __forceinline__ void put_bits_global(uint32_t *__restrict__ out, uint64_t bitpos, uint32_t v, uint32_t nb) {
+    if (!nb) return;
+    const uint64_t wi = bitpos >> 5; const uint32_t sh = (uint32_t)bitpos & 31u;
+    atomicOr(out + wi, v << sh);
+    if (sh && sh + nb > 32) atomicOr(out + wi + 1, v >> (32 - sh));
+}
+
+// =============================================================================== K9 write_headers (warp per block)
+__global__ void __launch_bounds__(128) k_write_headers(EncDev E) {
+    const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (b >= E.n_blocks) return;
+    const BlockDesc bd = E.blocks[b];
+    const uint64_t abs0 = E.out_base[bd.stream] * 8 + E.blk_bitoff[b];
+    const uint32_t hb = E.hdr_bits[b];
+    if (lane == 0) {
+        const uint32_t btype = bd.fixed ? 1u : 2u;
+        put_bits_global(E.out_words, abs0, (bd.is_final ? 1u : 0u) | (btype << 1), 3);
+        const uint32_t eob = E.litcode[(uint64_t)b * kLitStride + 256];
+        put_bits_global(E.out_words, abs0 + E.blk_bits[b] - (eob >> 16), eob & 0xFFFFu, eob >> 16);
+        if (bd.sync_after) put_bits_global(E.out_words, E.out_base[bd.stream] * 8 + E.blk_markpos[b] + 16, 0xFFFFu, 16);
+    }
+    const uint32_t *hw = E.hdr_words + (uint64_t)b * kHdrWords;
+    for (uint32_t k = lane; k * 32 < hb; k += 32) {
+        const uint32_t nb = min(32u, hb - k * 32);
+        uint32_t v = hw[k];
+        if (nb < 32) v &= (1u << nb) - 1u;
+        put_bits_global(E.out_words, abs0 + 3 + (uint64_t)k * 32, v, nb);
+    }
+}
+
+// =============================================================================== K10 bitpack (warp per tile)
+constexpr uint32_t kPackWords = 1040;
+__global__ void __launch_bounds__(256) k_bitpack(EncDev E) {
+    extern __shared__ uint32_t pk[];
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * 8 + wid;
+    if (tile >= E.n_tiles) return;
+    const uint32_t nbits = E.tile_bits[tile];
+    if (!nbits) return;
+    const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t b = cd.block;
+    const uint32_t ts = (tile - E.tile0[c]) * kTile;
+    const uint32_t *__restrict__ so = E.sym + cd.off + ts;
+    const uint32_t *lit = E.litcode + (uint64_t)b * kLitStride;
+    const uint32_t *dist = E.distcode + (uint64_t)b * kDistStride;
+    const uint32_t nsym = E.tile_nsym[tile];
+    const uint64_t abs0 = E.out_base[E.blocks[b].stream] * 8 + E.blk_bitoff[b] + 3 + E.hdr_bits[b] + E.tile_bitrel[tile];
+    const uint64_t word0 = abs0 >> 5;
+    const uint32_t sh0 = (uint32_t)abs0 & 31u;
+    const uint32_t nwords = (sh0 + nbits + 31) >> 5;
+    uint32_t *buf = pk + wid * kPackWords;
+    for (uint32_t w = lane; w < nwords + 2; w += 32) buf[w] = 0;
+    __syncwarp();
+    uint32_t run = sh0;
+    for (uint32_t k0 = 0; k0 < nsym; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        uint64_t v = 0; uint32_t nb = 0;
+        if (k < nsym) sym_bits(so[k], lit, dist, v, nb);
+        uint32_t incl = nb;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+        if (nb) {
+            const uint32_t off = run + incl - nb;
+            const uint32_t wi = off >> 5, sh = off & 31u;
+            atomicOr(buf + wi, (uint32_t)(v << sh));
+            const uint64_t rem = v >> (32 - sh);
+            if ((uint32_t)rem) atomicOr(buf + wi + 1, (uint32_t)rem);
+            if ((uint32_t)(rem >> 32)) atomicOr(buf + wi + 2, (uint32_t)(rem >> 32));
+        }
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    __syncwarp();
+    uint32_t *__restrict__ out = E.out_words + word0;
+    for (uint32_t w = lane; w < nwords; w += 32) {
+        const uint32_t val = buf[w];
+        if (w == 0 || w == nwords - 1) { if (val) atomicOr(out + w, val); }
+        else out[w] = val;
+    }
+}
+
+// =============================================================================== symbol compaction (b2f_lz77_default)
+__global__ void __launch_bounds__(1024) k_scan_nsym_single(EncDev E, uint64_t *tile_symoff, uint64_t *total) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < E.n_tiles; base += 1024) {
+        const uint32_t k = base + tid;
+        const uint64_t x = k < E.n_tiles ? E.tile_nsym[k] : 0;
+        uint64_t incl = x;
+        for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        uint64_t woff = 0;
+        for (uint32_t w = 0; w < wid; w++) woff += wsum[w];
+        const uint64_t carry = carry_s;
+        if (k < E.n_tiles) tile_symoff[k] = carry + woff + incl - x;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *total = carry_s;
+}
+__global__ void __launch_bounds__(256) k_compact_syms(EncDev E, const uint64_t *tile_symoff, uint32_t *dst) {
+    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile >= E.n_tiles) return;
+    const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t ts = (tile - E.tile0[c]) * kTile;
+    const uint32_t *__restrict__ so = E.sym + cd.off + ts;
+    const uint32_t nsym = E.tile_nsym[tile];
+    uint32_t *d = dst + tile_symoff[tile];
+    for (uint32_t k = lane; k < nsym; k += 32) d[k] = so[k];
+}
+
+// =============================================================================== launchers
+#define B2F_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return e__; } while (0)
+
+cudaError_t enc_init_attributes() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_lz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << kHashBits) * 4));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_lz_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bitpack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kPackWords * 4));
+    return e;
+}
+
+cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm) {
+    if (E.n_chunks == 0) return cudaSuccess;
+    if (tm) tm->mark(st, "lz_chain");
+    k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 4, st>>>(E); B2F_LAUNCH_CHECK();
+    if (tm) tm->mark(st, "lz_match");
+    k_lz_match<<<E.n_ptiles, 512, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
+    if (tm) tm->mark(st, "parse_exits");
+    k_parse_exits<<<(E.n_tiles + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    if (tm) tm->mark(st, "parse_stitch");
+    k_parse_stitch<<<(E.n_chunks + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    if (tm) tm->mark(st, "parse_emit");
+    k_parse_emit<<<E.n_grps, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm) {
+    if (tm) tm->mark(st, "huff_build");
+    k_huff_build<<<E.n_blocks, 32, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    if (E.n_tiles) {
+        if (tm) tm->mark(st, "tile_bits");
+        k_tile_bits<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    }
+    if (tm) tm->mark(st, "scan");
+    k_scan_tiles<<<E.n_blocks, 256, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    k_scan_blocks<<<(E.n_streams + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    if (tm) tm->mark(st, "write_headers");
+    k_write_headers<<<(E.n_blocks + 3) / 4, 128, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    if (E.n_tiles) {
+        if (tm) tm->mark(st, "bitpack");
+        k_bitpack<<<(E.n_tiles + 7) / 8, 256, 8 * kPackWords * 4, st>>>(E); B2F_LAUNCH_CHECK();
+    }
+    return cudaSuccess;
+}
+cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t *total, uint32_t *dst, cudaStream_t st) {
+    k_scan_nsym_single<<<1, 1024, 0, st>>>(E, tile_symoff, total); B2F_LAUNCH_CHECK();
+    k_compact_syms<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E, tile_symoff, dst); B2F_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+uint32_t enc_launch_count_lz() { return 5; }
+uint32_t enc_launch_count_entropy(bool has_tiles) { return has_tiles ? 6 : 4; }
+
+}  // namespace b2f

@@ -54,3 +54,16 @@ def dist_code(d):
     o = (C.c_uint32 * 3)()
     lib().hc_dist_code(d, o)
     return tuple(o)
+
+
+def inflate(data, cap=None):
+    """product inflate core on the host: returns (status, out bytes, consumed, end_bit)"""
+    data = bytes(data)
+    if cap is None:
+        cap = max(1 << 16, len(data) * 1100 + 1024)
+    out = C.create_string_buffer(cap + 64)
+    res = (C.c_int64 * 4)()
+    buf = C.create_string_buffer(data, len(data) + 64)      # padded like device buffers
+    lib().hc_inflate(buf, C.c_uint64(len(data)), out, C.c_uint64(cap), res)
+    n = min(res[1], cap)
+    return res[0], out.raw[:n], res[2], res[3]

@@ -27,3 +27,29 @@ void hc_dist_code(uint32_t dist, uint32_t *out3) { dist_code(dist, out3[0], out3
 uint32_t hc_hdr_words(void) { return kHdrWords; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ inflate core on the host
+#include "../../libflate_b200/csrc/inflate_core.cuh"
+namespace {
+struct HostOut {
+    uint8_t *o; uint64_t capacity;
+    uint64_t cap() const { return capacity; }
+    void lit(uint64_t pos, uint8_t b) { o[pos] = b; }
+    void copy(uint64_t pos, uint32_t len, uint32_t dist) { for (uint32_t k = 0; k < len; k++) o[pos + k] = o[pos + k - dist]; }
+    void raw(uint64_t pos, const uint8_t *src, uint64_t n) { memcpy(o + pos, src, n); }
+};
+struct NoSync { void operator()() const {} };
+}
+extern "C" {
+// raw DEFLATE stream decode with the product's core. res[0]=status res[1]=out_len res[2]=consumed res[3]=end_bit
+void hc_inflate(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, int64_t *res) {
+    static InflateTables T;
+    BitIn b; bi_init(b, in, n, 0);
+    HostOut o = { out, cap };
+    InflateResult R;
+    inflate_blocks(b, T, o, 0, 0, 0xFFFFFFFFu, 0, 1, NoSync(), R);
+    res[0] = R.status; res[1] = (int64_t)R.out_len; res[2] = (int64_t)R.consumed; res[3] = (int64_t)R.end_bit;
+}
+uint32_t hc_len_base(uint32_t k) { return len_base(k) | (len_extra(k) << 16); }
+uint32_t hc_dist_base(uint32_t k) { return dist_base(k) | (dist_extra(k) << 16); }
+}

@@ -167,7 +167,7 @@ typedef struct b2f_stats {
     float last_device_ms;         /* whole device section of the last call */
 } b2f_stats;
 int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out);
-const char *b2f_stage_name(int is_decode, uint32_t stage);
+const char *b2f_stage_name(b2f_ctx *ctx, uint32_t stage);   /* name of stage i of the last call */
 void *b2f_ctx_stream(b2f_ctx *ctx);   /* cudaStream_t the ctx launches on */
 
 #ifdef __cplusplus

@@ -1,0 +1,36 @@
+"""Builds libb2f.so (the CUDA hot path + C ABI) in-tree with nvcc for sm_100a."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libb2f.so")
+SOURCES = ["b2f_api.cu", "encode_kernels.cu", "decode_kernels.cu", "checksum_kernels.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-cudart", "static"]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
+           [os.path.join(HERE, "..", "include", "b2f.h")]
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _newest(deps):
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for s in srcs:
+        o = os.path.join(CSRC, os.path.basename(s).replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        subprocess.check_call(cmd)
+        objs.append(o)
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-shared", "-o", SO] + objs)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,989 @@
+// b2f_api.cu -- C ABI (include/b2f.h): context, segmentation plan, container framing and the host
+// orchestration of the encode / decode / checksum kernels.  Host code here is bookkeeping only
+// (sizes, offsets, 10-20 byte headers/trailers); every byte of LZ77 / Huffman / bit-packing / inflate /
+// checksum work is done by the CUDA kernels.  There is no CPU fallback: without a device the context cannot
+// be created and every entry point needs a context.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/b2f.h"
+#include "common.cuh"
+#include "encode_dev.cuh"
+#include "decode_dev.cuh"
+#include "checksum_dev.cuh"
+#include "inflate_core.cuh"
+
+using namespace b2f;
+
+// ------------------------------------------------------------------------------------------ context
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_COUNT };
+
+struct b2f_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf buf[NB_COUNT];
+    PinBuf pin_meta, pin_res, pin_ck, pin_win;
+    StageTimer tm;
+    std::string err;
+    b2f_stats stats;
+    const char *stage_names[16];
+    bool last_is_decode = false;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return B2F_ERR_CUDA; } } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" const char *b2f_version(void) { return "libb2f 0.1 (sm_100a)"; }
+
+extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
+    if (!out) return B2F_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        g_create_err = e != cudaSuccess ? cudaGetErrorString(e) : "no such CUDA device";
+        return B2F_ERR_CUDA;                   // no CPU fallback by design
+    }
+    b2f_ctx *ctx = new b2f_ctx();
+    ctx->device = device;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        enc_init_attributes() != cudaSuccess || dec_init_attributes() != cudaSuccess || checksum_init_tables() != cudaSuccess) {
+        g_create_err = cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return B2F_ERR_CUDA;
+    }
+    ctx->tm.create();
+    *out = ctx;
+    return B2F_OK;
+}
+extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->buf) b.release();
+    ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release();
+    ctx->tm.destroy();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char *b2f_last_error(const b2f_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" void *b2f_ctx_stream(b2f_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out) { if (!ctx || !out) return B2F_ERR_INVALID_ARG; *out = ctx->stats; return B2F_OK; }
+extern "C" const char *b2f_stage_name(b2f_ctx *ctx, uint32_t i) { return (ctx && i < 16 && ctx->stage_names[i]) ? ctx->stage_names[i] : ""; }
+
+extern "C" void b2f_encode_opts_default(b2f_encode_opts *o) {
+    memset(o, 0, sizeof *o);
+    o->block_size = 1u << 20; o->window_size = 32768; o->max_length = 258; o->mode = B2F_MODE_DYNAMIC; o->gzip_os = 3;
+}
+
+static void collect_stats(b2f_ctx *ctx, bool is_decode) {
+    ctx->last_is_decode = is_decode;
+    uint32_t n = (uint32_t)std::min(ctx->tm.n, 16);
+    ctx->stats.last_n_stages = n;
+    for (uint32_t i = 0; i < 16; i++) { ctx->stats.last_kernel_ms[i] = i < n ? ctx->tm.stage_ms((int)i) : 0.f; ctx->stage_names[i] = i < n ? ctx->tm.name[i] : nullptr; }
+    ctx->stats.last_device_ms = ctx->tm.total_ms();
+}
+
+// ------------------------------------------------------------------------------------------ E1: plan
+namespace {
+struct PlanOut {
+    std::vector<uint64_t> chunk_ends;      // stream-relative
+    std::vector<uint64_t> block_ends;
+    std::vector<uint32_t> block_chunks;
+    std::vector<uint8_t> block_after_flush;   // block was closed by an explicit flush() (candidate for the zlib sync marker)
+};
+// Block::write / CompressBuf::append / DefaultLz77Encoder::encode bookkeeping (encode.rs:277-286,405-425; default.rs:60-68)
+void plan_stream(const int64_t *sched, size_t n_sched, uint64_t in_len, uint64_t block_size, uint32_t window, PlanOut &P) {
+    const uint64_t chunk_thresh = (uint64_t)window * 8;
+    uint64_t lz = 0, orig = 0, pos = 0; uint32_t chunks_in_block = 0;
+    auto end_chunk = [&]() { P.chunk_ends.push_back(pos); chunks_in_block++; lz = 0; };
+    auto flush_block = [&](bool after_flush) {
+        if (lz > 0) end_chunk();
+        P.block_ends.push_back(pos); P.block_chunks.push_back(chunks_in_block); P.block_after_flush.push_back(after_flush ? 1 : 0);
+        chunks_in_block = 0; orig = 0;
+    };
+    int64_t one = (int64_t)in_len;
+    if (!sched) { sched = &one; n_sched = in_len ? 1 : 0; }
+    for (size_t k = 0; k < n_sched; k++) {
+        if (sched[k] < 0) { flush_block(true); continue; }
+        uint64_t w = (uint64_t)sched[k]; if (pos + w > in_len) w = in_len - pos;
+        pos += w; orig += w; lz += w;
+        if (lz >= chunk_thresh) end_chunk();
+        while (orig >= block_size) flush_block(false);
+    }
+    flush_block(false);                    // finish(): always one more block, possibly empty (encode.rs:296-303)
+}
+}  // namespace
+
+extern "C" int b2f_plan_from_writes(const int64_t *sched, size_t n_sched, uint64_t in_len, uint64_t block_size, uint32_t window_size,
+                                    uint64_t *chunk_ends, size_t *n_chunks, uint64_t *block_ends, uint32_t *block_chunks,
+                                    uint8_t *block_after_flush, size_t *n_blocks) {
+    if (block_size == 0 || window_size == 0) return B2F_ERR_INVALID_ARG;
+    PlanOut P;
+    plan_stream(sched, n_sched, in_len, block_size, window_size > 32768 ? 32768 : window_size, P);
+    if (n_chunks) *n_chunks = P.chunk_ends.size();
+    if (n_blocks) *n_blocks = P.block_ends.size();
+    if (chunk_ends) memcpy(chunk_ends, P.chunk_ends.data(), P.chunk_ends.size() * 8);
+    if (block_ends) memcpy(block_ends, P.block_ends.data(), P.block_ends.size() * 8);
+    if (block_chunks) memcpy(block_chunks, P.block_chunks.data(), P.block_chunks.size() * 4);
+    if (block_after_flush) memcpy(block_after_flush, P.block_after_flush.data(), P.block_after_flush.size());
+    return B2F_OK;
+}
+
+// ------------------------------------------------------------------------------------------ framing (G1)
+namespace {
+uint32_t host_crc32(const uint8_t *p, size_t n) {   // only for the <= ~64 KiB gzip header CRC16 (gzip.rs:356-367), not a data path
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) { c ^= p[i]; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; }
+    return ~c;
+}
+void gzip_header(const b2f_encode_opts &o, bool with_hcrc, std::vector<uint8_t> &h) {   // Header::write_to (gzip.rs:368-389)
+    uint8_t flags = 0;
+    if (o.gzip_is_text) flags |= 1;
+    if (with_hcrc && o.gzip_is_verified) flags |= 2;
+    if (o.gzip_has_extra) flags |= 4;
+    if (o.gzip_filename) flags |= 8;
+    if (o.gzip_comment) flags |= 16;
+    const uint8_t b[10] = { 31, 139, 8, flags, (uint8_t)o.gzip_mtime, (uint8_t)(o.gzip_mtime >> 8), (uint8_t)(o.gzip_mtime >> 16),
+                            (uint8_t)(o.gzip_mtime >> 24), 0 /* XFL: CompressionLevel::Unknown */, o.gzip_os };
+    h.insert(h.end(), b, b + 10);
+    if (o.gzip_has_extra) { h.push_back((uint8_t)o.gzip_extra_len); h.push_back((uint8_t)(o.gzip_extra_len >> 8)); h.insert(h.end(), o.gzip_extra, o.gzip_extra + o.gzip_extra_len); }
+    if (o.gzip_filename) h.insert(h.end(), (const uint8_t *)o.gzip_filename, (const uint8_t *)o.gzip_filename + strlen(o.gzip_filename) + 1);
+    if (o.gzip_comment) h.insert(h.end(), (const uint8_t *)o.gzip_comment, (const uint8_t *)o.gzip_comment + strlen(o.gzip_comment) + 1);
+    if (with_hcrc && o.gzip_is_verified) {
+        std::vector<uint8_t> t; gzip_header(o, false, t);
+        uint32_t c = host_crc32(t.data(), t.size());
+        h.push_back((uint8_t)c); h.push_back((uint8_t)(c >> 8));
+    }
+}
+void zlib_header(const b2f_encode_opts &o, std::vector<uint8_t> &h) {                   // zlib.rs:212-220, 267-279
+    uint32_t ws = o.window_size > 32768 ? 32768 : o.window_size;
+    uint8_t cinfo = ws > 16384 ? 7 : ws > 8192 ? 6 : ws > 4096 ? 5 : ws > 2048 ? 4 : ws > 1024 ? 3 : ws > 512 ? 2 : ws > 256 ? 1 : 0;
+    uint8_t level = o.mode == B2F_MODE_STORED ? 0 : 2;
+    uint8_t cmf = (uint8_t)((cinfo << 4) | 8), flg = (uint8_t)(level << 6);
+    uint16_t check = (uint16_t)(((uint16_t)cmf << 8) + flg);
+    if (check % 31 != 0) flg = (uint8_t)(flg + (31 - check % 31));
+    h.push_back(cmf); h.push_back(flg);
+}
+void make_header(int fmt, const b2f_encode_opts &o, std::vector<uint8_t> &h) {
+    h.clear();
+    if (fmt == B2F_FMT_GZIP) gzip_header(o, true, h);
+    else if (fmt == B2F_FMT_ZLIB) zlib_header(o, h);
+}
+size_t trailer_len(int fmt) { return fmt == B2F_FMT_GZIP ? 8 : fmt == B2F_FMT_ZLIB ? 4 : 0; }
+}  // namespace
+
+extern "C" size_t b2f_header_len(int fmt, const b2f_encode_opts *opts) {
+    b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
+    std::vector<uint8_t> h; make_header(fmt, *opts, h); return h.size();
+}
+extern "C" size_t b2f_encode_bound(size_t in_len, size_t n_sched, const b2f_encode_opts *opts) {
+    b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
+    size_t bs = opts->block_size ? (size_t)opts->block_size : 1;
+    if (opts->mode == B2F_MODE_STORED && bs > 0xFFFF) bs = 0xFFFF;
+    size_t nblocks = n_sched + in_len / bs + 2;
+    size_t hdr = 32 + (opts->gzip_has_extra ? opts->gzip_extra_len + 2 : 0) + (opts->gzip_filename ? strlen(opts->gzip_filename) + 1 : 0) +
+                 (opts->gzip_comment ? strlen(opts->gzip_comment) + 1 : 0);
+    return hdr + in_len + in_len / 2 + nblocks * 640 + 64;
+}
+
+// ------------------------------------------------------------------------------------------ checksums on device data
+namespace {
+// d_base + off[s], len[s] for n buffers that are already on the device; results to host arrays.
+int run_checksums(b2f_ctx *ctx, const uint8_t *d_base, const std::vector<uint64_t> &off, const std::vector<uint64_t> &len,
+                  bool do_crc, bool do_adler, const uint32_t *init, std::vector<uint32_t> &crc, std::vector<uint32_t> &adler) {
+    const size_t n = off.size();
+    crc.assign(n, 0); adler.assign(n, 1);
+    if (!n) return B2F_OK;
+    std::vector<uint64_t> piece0(n + 1, 0);
+    for (size_t s = 0; s < n; s++) piece0[s + 1] = piece0[s] + (len[s] + kChecksumPiece - 1) / kChecksumPiece;
+    // layout in NB_CK: off | len | piece0 | acc_a | acc_b | acc_crc | init | out_crc | out_adler
+    size_t o_off = 0, o_len = o_off + n * 8, o_p0 = o_len + n * 8, o_a = o_p0 + (n + 1) * 8, o_b = o_a + n * 8, o_c = o_b + n * 8,
+           o_init = o_c + n * 4, o_oc = o_init + n * 4, o_oa = o_oc + n * 4, total = align_up(o_oa + n * 4, 16);
+    CK(ctx->buf[NB_CK].ensure(total));
+    CK(ctx->pin_ck.ensure(total));
+    uint8_t *hm = ctx->pin_ck.as<uint8_t>();
+    memset(hm, 0, total);
+    memcpy(hm + o_off, off.data(), n * 8); memcpy(hm + o_len, len.data(), n * 8); memcpy(hm + o_p0, piece0.data(), (n + 1) * 8);
+    if (init) memcpy(hm + o_init, init, n * 4);
+    uint8_t *dm = ctx->buf[NB_CK].as<uint8_t>();
+    CK(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, ctx->stream));
+    ChecksumDev C;
+    C.in = d_base; C.off = (const uint64_t *)(dm + o_off); C.len = (const uint64_t *)(dm + o_len); C.piece0 = (const uint64_t *)(dm + o_p0);
+    C.n_pieces = piece0[n]; C.n_streams = (uint32_t)n;
+    C.acc_a = (uint64_t *)(dm + o_a); C.acc_b = (uint64_t *)(dm + o_b); C.acc_crc = (uint32_t *)(dm + o_c);
+    C.init_crc = (init && do_crc) ? (const uint32_t *)(dm + o_init) : nullptr;
+    C.init_adler = (init && do_adler) ? (const uint32_t *)(dm + o_init) : nullptr;
+    C.out_crc = (uint32_t *)(dm + o_oc); C.out_adler = (uint32_t *)(dm + o_oa);
+    ctx->tm.mark(ctx->stream, "checksum");
+    CK(checksum_launch(C, do_crc, do_adler, ctx->stream));
+    ctx->stats.kernel_launches += (C.n_pieces ? 1 : 0) + 1;
+    CK(ctx->pin_res.ensure(n * 8));
+    uint32_t *hr = ctx->pin_res.as<uint32_t>();
+    CK(cudaMemcpyAsync(hr, dm + o_oc, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->tm.finish(ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t s = 0; s < n; s++) { crc[s] = hr[s]; adler[s] = hr[n + s]; }
+    return B2F_OK;
+}
+
+int checksum_batch_host(b2f_ctx *ctx, size_t n, const uint8_t *const *buf, const size_t *len, const uint32_t *init, uint32_t *out, bool is_crc) {
+    if (!ctx || (n && (!buf || !len || !out))) return B2F_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    std::vector<uint64_t> off(n), ln(n); size_t total = 0;
+    for (size_t s = 0; s < n; s++) { off[s] = total; ln[s] = len[s]; total += align_up(len[s], 16); }
+    CK(ctx->buf[NB_IN].ensure(total + 256));
+    uint8_t *d = ctx->buf[NB_IN].as<uint8_t>();
+    for (size_t s = 0; s < n; s++) if (len[s]) CK(cudaMemcpyAsync(d + off[s], buf[s], len[s], cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint32_t> crc, adler;
+    int rc = run_checksums(ctx, d, off, ln, is_crc, !is_crc, init, crc, adler);
+    if (rc) return rc;
+    for (size_t s = 0; s < n; s++) out[s] = is_crc ? crc[s] : adler[s];
+    collect_stats(ctx, false);
+    return B2F_OK;
+}
+}  // namespace
+
+extern "C" int b2f_adler32_batch(b2f_ctx *ctx, size_t n, const uint8_t *const *buf, const size_t *len, const uint32_t *init, uint32_t *out) {
+    return checksum_batch_host(ctx, n, buf, len, init, out, false);
+}
+extern "C" int b2f_crc32_batch(b2f_ctx *ctx, size_t n, const uint8_t *const *buf, const size_t *len, const uint32_t *init, uint32_t *out) {
+    return checksum_batch_host(ctx, n, buf, len, init, out, true);
+}
+
+// ------------------------------------------------------------------------------------------ encode core
+namespace {
+struct EncPlan {
+    std::vector<ChunkDesc> chunks;
+    std::vector<BlockDesc> blocks;
+    std::vector<uint32_t> seg0, pt0, tile0, grp0;      // per chunk prefixes (+1)
+    std::vector<uint32_t> stream_blk0;                  // per stream (+1)
+    uint64_t total_in = 0;
+};
+
+// Fills plan for streams laid out at in_off[] in the device input.
+int build_plan(b2f_ctx *ctx, const b2f_encode_opts &o, size_t n_streams, const uint64_t *in_off, const size_t *in_len,
+               const int64_t *const *sched, const size_t *n_sched, int fmt, EncPlan &P) {
+    const uint32_t window = o.window_size > 32768 ? 32768 : o.window_size;
+    P.stream_blk0.assign(1, 0);
+    P.seg0.assign(1, 0); P.pt0.assign(1, 0); P.tile0.assign(1, 0); P.grp0.assign(1, 0);
+    for (size_t s = 0; s < n_streams; s++) {
+        PlanOut po;
+        plan_stream(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s], o.block_size, window, po);
+        uint64_t cstart = 0; size_t ci = 0;
+        for (size_t b = 0; b < po.block_ends.size(); b++) {
+            BlockDesc bd; memset(&bd, 0, sizeof bd);
+            bd.stream = (uint32_t)s; bd.chunk0 = (uint32_t)P.chunks.size(); bd.nchunks = po.block_chunks[b];
+            bd.tile0 = P.tile0.back();
+            bd.is_final = b + 1 == po.block_ends.size();
+            bd.sync_after = (fmt == B2F_FMT_ZLIB && o.zlib_flush_sync && po.block_after_flush[b]) ? 1 : 0;
+            bd.fixed = o.mode == B2F_MODE_FIXED;
+            for (uint32_t k = 0; k < bd.nchunks; k++, ci++) {
+                uint64_t cend = po.chunk_ends[ci];
+                uint64_t len = cend - cstart;
+                if (len >= (1ull << 31)) { ctx->err = "LZ77 chunk larger than 2 GiB is not supported"; return B2F_ERR_INVALID_ARG; }
+                ChunkDesc cd; cd.off = in_off[s] + cstart; cd.len = (uint32_t)len; cd.block = (uint32_t)P.blocks.size();
+                P.chunks.push_back(cd);
+                uint32_t nt = (uint32_t)((len + kTile - 1) / kTile);
+                P.seg0.push_back(P.seg0.back() + (uint32_t)((len + kSeg - 1) / kSeg));
+                P.pt0.push_back(P.pt0.back() + (uint32_t)((len + kPTile - 1) / kPTile));
+                P.tile0.push_back(P.tile0.back() + nt);
+                P.grp0.push_back(P.grp0.back() + (nt + kGrpTiles - 1) / kGrpTiles);
+                cstart = cend;
+            }
+            bd.ntiles = P.tile0.back() - bd.tile0;
+            P.blocks.push_back(bd);
+        }
+        P.stream_blk0.push_back((uint32_t)P.blocks.size());
+        P.total_in += in_len[s];
+    }
+    return B2F_OK;
+}
+
+template <class T> T *carve(uint8_t *&p, size_t count) { T *r = reinterpret_cast<T *>(p); p += align_up(count * sizeof(T), 256); return r; }
+template <class T> size_t carve_size(size_t count) { return align_up(count * sizeof(T), 256); }
+
+// Framing kernel: container header bytes + trailer (checksums are already on the device).
+__global__ void k_write_framing(uint8_t *out, const uint64_t *out_base, const uint64_t *stream_end_bits, const uint8_t *hdr, uint32_t hdr_len,
+                                int fmt, const uint32_t *crc, const uint32_t *adler, const uint64_t *in_len, uint64_t *out_len, uint32_t n) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint8_t *o = out + out_base[s];
+    for (uint32_t i = 0; i < hdr_len; i++) o[i] = hdr[i];
+    uint64_t end = (stream_end_bits[s] + 7) >> 3;
+    if (fmt == B2F_FMT_GZIP) {          // Trailer::write_to (gzip.rs:114-121): CRC32 LE, ISIZE LE (mod 2^32)
+        uint32_t c = crc[s], z = (uint32_t)in_len[s];
+        for (int k = 0; k < 4; k++) o[end + k] = (uint8_t)(c >> (8 * k));
+        for (int k = 0; k < 4; k++) o[end + 4 + k] = (uint8_t)(z >> (8 * k));
+        end += 8;
+    } else if (fmt == B2F_FMT_ZLIB) {   // zlib.rs:630-638: Adler-32 big endian
+        uint32_t a = adler[s];
+        for (int k = 0; k < 4; k++) o[end + k] = (uint8_t)(a >> (8 * (3 - k)));
+        end += 4;
+    }
+    out_len[s] = end;
+}
+
+struct EncodeJob {
+    // device-resident inputs
+    const uint8_t *d_in; std::vector<uint64_t> in_off; std::vector<uint64_t> in_len;
+    // results
+    std::vector<uint64_t> out_base; std::vector<uint64_t> out_len;   // in ctx->buf[NB_OUT]
+};
+
+// Runs the whole device pipeline for compressed modes.  On return the encoded streams sit in ctx->buf[NB_OUT] at job.out_base[s].
+int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_streams, const int64_t *const *sched, const size_t *n_sched, EncodeJob &job) {
+    job.out_base.clear(); job.out_len.clear();
+    if (n_streams == 0) return B2F_OK;
+    EncPlan P;
+    std::vector<size_t> lens(n_streams);
+    for (size_t s = 0; s < n_streams; s++) lens[s] = (size_t)job.in_len[s];
+    int rc = build_plan(ctx, o, n_streams, job.in_off.data(), lens.data(), sched, n_sched, fmt, P);
+    if (rc) return rc;
+    std::vector<uint8_t> hdr; make_header(fmt, o, hdr);
+    const size_t tl = trailer_len(fmt);
+    // output slots
+    job.out_base.resize(n_streams); job.out_len.assign(n_streams, 0);
+    uint64_t out_total = 0;
+    for (size_t s = 0; s < n_streams; s++) {
+        job.out_base[s] = out_total;
+        size_t nb = P.stream_blk0[s + 1] - P.stream_blk0[s];
+        out_total += align_up(hdr.size() + (size_t)job.in_len[s] + (size_t)job.in_len[s] / 2 + nb * 640 + tl + 64, 256);
+    }
+    const uint32_t n_chunks = (uint32_t)P.chunks.size(), n_blocks = (uint32_t)P.blocks.size(), n_tiles = P.tile0.back();
+    // span of the device input touched by chunks (scratch arrays are indexed by global input offset)
+    uint64_t in_span = 0;
+    for (size_t s = 0; s < n_streams; s++) in_span = std::max<uint64_t>(in_span, job.in_off[s] + job.in_len[s]);
+
+    CK(ctx->buf[NB_LINK].ensure(in_span * 2 + 256));
+    CK(ctx->buf[NB_MD].ensure(in_span * 4 + 256));
+    CK(ctx->buf[NB_SYM].ensure(in_span * 4 + 256));
+    CK(ctx->buf[NB_EXIT].ensure((size_t)n_tiles * kExitW * 2 + 256));
+    size_t tile_bytes = carve_size<uint16_t>(n_tiles) + 2 * carve_size<uint32_t>(n_tiles) + carve_size<uint64_t>(n_tiles);
+    CK(ctx->buf[NB_TILE].ensure(tile_bytes + 256));
+    size_t blk_bytes = carve_size<uint32_t>((size_t)n_blocks * kHistStride) + carve_size<uint32_t>((size_t)n_blocks * kLitStride) +
+                       carve_size<uint32_t>((size_t)n_blocks * kDistStride) + carve_size<uint32_t>((size_t)n_blocks * kHdrWords) +
+                       carve_size<uint32_t>(n_blocks) + 3 * carve_size<uint64_t>(n_blocks);
+    CK(ctx->buf[NB_BLK].ensure(blk_bytes + 256));
+    CK(ctx->buf[NB_OUT].ensure(out_total + 256));
+    // descriptors: chunks | blocks | 4 prefixes | stream_blk0 | out_base | hdr_len | in_len | hdr bytes  (one H2D copy)
+    size_t d_total = carve_size<ChunkDesc>(n_chunks) + carve_size<BlockDesc>(n_blocks) + 4 * carve_size<uint32_t>(n_chunks + 1) +
+                     carve_size<uint32_t>(n_streams + 1) + carve_size<uint64_t>(n_streams) + carve_size<uint32_t>(n_streams) +
+                     carve_size<uint64_t>(n_streams) + carve_size<uint8_t>(hdr.size() + 1) + 16 * 256;
+    size_t misc_total = 2 * carve_size<uint64_t>(n_streams) + 256;     // stream_end_bits | out_len
+    CK(ctx->buf[NB_DESC].ensure(d_total + 256));
+    CK(ctx->buf[NB_MISC].ensure(misc_total));
+    CK(ctx->pin_meta.ensure(d_total + 256));
+    uint8_t *hp = ctx->pin_meta.as<uint8_t>(), *hp0 = hp;
+    uint8_t *dp = ctx->buf[NB_DESC].as<uint8_t>(), *dp0 = dp;
+    auto put = [&](const void *src, size_t bytes) -> uint8_t * { memcpy(hp, src, bytes); uint8_t *d = dp0 + (hp - hp0); hp += align_up(bytes ? bytes : 1, 256); return d; };
+    std::vector<uint32_t> hdr_len(n_streams, (uint32_t)hdr.size());
+    EncDev E; memset(&E, 0, sizeof E);
+    E.in = job.d_in;
+    E.chunks = (const ChunkDesc *)put(P.chunks.data(), n_chunks * sizeof(ChunkDesc)); E.n_chunks = n_chunks;
+    E.blocks = (const BlockDesc *)put(P.blocks.data(), n_blocks * sizeof(BlockDesc)); E.n_blocks = n_blocks;
+    E.seg0 = (const uint32_t *)put(P.seg0.data(), (n_chunks + 1) * 4); E.pt0 = (const uint32_t *)put(P.pt0.data(), (n_chunks + 1) * 4);
+    E.tile0 = (const uint32_t *)put(P.tile0.data(), (n_chunks + 1) * 4); E.grp0 = (const uint32_t *)put(P.grp0.data(), (n_chunks + 1) * 4);
+    E.n_segs = P.seg0.back(); E.n_ptiles = P.pt0.back(); E.n_tiles = n_tiles; E.n_grps = P.grp0.back();
+    E.window = o.window_size > 32768 ? 32768 : o.window_size; E.max_len = o.max_length > 258 ? 258 : o.max_length;
+    E.n_streams = (uint32_t)n_streams;
+    E.stream_blk0 = (const uint32_t *)put(P.stream_blk0.data(), (n_streams + 1) * 4);
+    E.out_base = (const uint64_t *)put(job.out_base.data(), n_streams * 8);
+    E.hdr_len = (const uint32_t *)put(hdr_len.data(), n_streams * 4);
+    const uint64_t *d_in_len = (const uint64_t *)put(job.in_len.data(), n_streams * 8);
+    const uint8_t *d_hdr = put(hdr.data(), hdr.size());
+    CK(cudaMemcpyAsync(dp0, hp0, (size_t)(hp - hp0), cudaMemcpyHostToDevice, ctx->stream));
+    E.link = ctx->buf[NB_LINK].as<uint16_t>(); E.md = ctx->buf[NB_MD].as<uint32_t>(); E.sym = ctx->buf[NB_SYM].as<uint32_t>();
+    E.exit_tab = ctx->buf[NB_EXIT].as<uint16_t>();
+    uint8_t *tp = ctx->buf[NB_TILE].as<uint8_t>();
+    E.tile_entry = carve<uint16_t>(tp, n_tiles); E.tile_nsym = carve<uint32_t>(tp, n_tiles); E.tile_bits = carve<uint32_t>(tp, n_tiles); E.tile_bitrel = carve<uint64_t>(tp, n_tiles);
+    uint8_t *bp = ctx->buf[NB_BLK].as<uint8_t>();
+    E.hist = carve<uint32_t>(bp, (size_t)n_blocks * kHistStride);
+    const size_t hist_bytes = (size_t)n_blocks * kHistStride * 4;
+    E.litcode = carve<uint32_t>(bp, (size_t)n_blocks * kLitStride); E.distcode = carve<uint32_t>(bp, (size_t)n_blocks * kDistStride);
+    E.hdr_words = carve<uint32_t>(bp, (size_t)n_blocks * kHdrWords); E.hdr_bits = carve<uint32_t>(bp, n_blocks);
+    E.blk_bits = carve<uint64_t>(bp, n_blocks); E.blk_bitoff = carve<uint64_t>(bp, n_blocks); E.blk_markpos = carve<uint64_t>(bp, n_blocks);
+    uint8_t *mp = ctx->buf[NB_MISC].as<uint8_t>();
+    E.stream_end_bits = carve<uint64_t>(mp, n_streams);
+    uint64_t *d_out_len = carve<uint64_t>(mp, n_streams);
+    E.out_words = ctx->buf[NB_OUT].as<uint32_t>();
+
+    ctx->tm.mark(ctx->stream, "clear");
+    CK(cudaMemsetAsync(E.hist, 0, hist_bytes, ctx->stream));
+    CK(cudaMemsetAsync(ctx->buf[NB_OUT].p, 0, out_total, ctx->stream));
+    CK(enc_launch_lz(E, ctx->stream, &ctx->tm));
+    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz();
+    CK(enc_launch_entropy(E, ctx->stream, &ctx->tm));
+    ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0);
+    // checksums over the inputs (C1/C2) -> trailers
+    const uint32_t *d_crc = nullptr, *d_adler = nullptr;
+    if (fmt == B2F_FMT_GZIP || fmt == B2F_FMT_ZLIB) {
+        std::vector<uint64_t> piece0(n_streams + 1, 0);
+        for (size_t s = 0; s < n_streams; s++) piece0[s + 1] = piece0[s] + (job.in_len[s] + kChecksumPiece - 1) / kChecksumPiece;
+        size_t n = n_streams;
+        size_t o_off = 0, o_len = o_off + n * 8, o_p0 = o_len + n * 8, o_a = o_p0 + (n + 1) * 8, o_b = o_a + n * 8, o_c = o_b + n * 8,
+               o_oc = o_c + n * 4, o_oa = o_oc + n * 4, total = align_up(o_oa + n * 4, 16);
+        CK(ctx->buf[NB_CK].ensure(total));
+        CK(ctx->pin_ck.ensure(total));
+        uint8_t *hm = ctx->pin_ck.as<uint8_t>(); memset(hm, 0, total);
+        memcpy(hm + o_off, job.in_off.data(), n * 8); memcpy(hm + o_len, job.in_len.data(), n * 8); memcpy(hm + o_p0, piece0.data(), (n + 1) * 8);
+        uint8_t *dm = ctx->buf[NB_CK].as<uint8_t>();
+        CK(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, ctx->stream));
+        ChecksumDev C; memset(&C, 0, sizeof C);
+        C.in = job.d_in; C.off = (const uint64_t *)(dm + o_off); C.len = (const uint64_t *)(dm + o_len); C.piece0 = (const uint64_t *)(dm + o_p0);
+        C.n_pieces = piece0[n]; C.n_streams = (uint32_t)n;
+        C.acc_a = (uint64_t *)(dm + o_a); C.acc_b = (uint64_t *)(dm + o_b); C.acc_crc = (uint32_t *)(dm + o_c);
+        C.out_crc = (uint32_t *)(dm + o_oc); C.out_adler = (uint32_t *)(dm + o_oa);
+        ctx->tm.mark(ctx->stream, "checksum");
+        CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->stream));
+        ctx->stats.kernel_launches += (C.n_pieces ? 1 : 0) + 1;
+        d_crc = C.out_crc; d_adler = C.out_adler;
+    }
+    ctx->tm.mark(ctx->stream, "framing");
+    k_write_framing<<<(unsigned)((n_streams + 63) / 64), 64, 0, ctx->stream>>>(ctx->buf[NB_OUT].as<uint8_t>(), E.out_base, E.stream_end_bits, d_hdr,
+                                                                             (uint32_t)hdr.size(), fmt, d_crc, d_adler, d_in_len, d_out_len, (uint32_t)n_streams);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    ctx->tm.finish(ctx->stream);
+    CK(ctx->pin_res.ensure(n_streams * 8 + 64));
+    uint64_t *h_out_len = ctx->pin_res.as<uint64_t>();
+    CK(cudaMemcpyAsync(h_out_len, d_out_len, n_streams * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t s = 0; s < n_streams; s++) job.out_len[s] = h_out_len[s];
+    return B2F_OK;
+}
+
+// Stored mode (EncodeOptions::no_compression, RawBuf encode.rs:354-383): framing + memcpy only, plus the device checksum.
+void stored_stream(int fmt, const b2f_encode_opts &o, const uint8_t *in, size_t n, const int64_t *sched, size_t n_sched,
+                   uint32_t crc, uint32_t adler, std::vector<uint8_t> &out) {
+    make_header(fmt, o, out);
+    size_t bs = (size_t)o.block_size; if (bs > 0xFFFF) bs = 0xFFFF;
+    size_t buf_start = 0, pos = 0;                     // RawBuf holds in[buf_start, pos)
+    auto flush = [&](bool fin) {
+        size_t size = std::min<size_t>(pos - buf_start, 0xFFFF);
+        out.push_back(fin ? 1 : 0);                    // BFINAL + BTYPE=00, then BitWriter::flush pads the byte
+        out.push_back((uint8_t)size); out.push_back((uint8_t)(size >> 8));
+        uint16_t ns = (uint16_t)~size; out.push_back((uint8_t)ns); out.push_back((uint8_t)(ns >> 8));
+        out.insert(out.end(), in + buf_start, in + buf_start + size);
+        buf_start += size;
+    };
+    int64_t one = (int64_t)n;
+    if (!sched) { sched = &one; n_sched = n ? 1 : 0; }
+    for (size_t k = 0; k < n_sched; k++) {
+        if (sched[k] < 0) {
+            flush(false);
+            if (fmt == B2F_FMT_ZLIB && o.zlib_flush_sync) { const uint8_t m[5] = { 0, 0, 0, 255, 255 }; out.insert(out.end(), m, m + 5); }
+            continue;
+        }
+        size_t w = (size_t)sched[k]; if (pos + w > n) w = n - pos;
+        pos += w;
+        while (pos - buf_start >= bs) flush(false);
+    }
+    flush(true);
+    if (fmt == B2F_FMT_GZIP) { for (int k = 0; k < 4; k++) out.push_back((uint8_t)(crc >> (8 * k))); uint32_t z = (uint32_t)n; for (int k = 0; k < 4; k++) out.push_back((uint8_t)(z >> (8 * k))); }
+    else if (fmt == B2F_FMT_ZLIB) { for (int k = 3; k >= 0; k--) out.push_back((uint8_t)(adler >> (8 * k))); }
+}
+}  // namespace
+
+static int validate_opts(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o) {
+    if (fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP) { ctx->err = "bad format"; return B2F_ERR_INVALID_ARG; }
+    if (o.block_size == 0 || o.window_size == 0 || o.max_length < 3 || o.mode < 0 || o.mode > 2) { ctx->err = "bad encode options"; return B2F_ERR_INVALID_ARG; }
+    return B2F_OK;
+}
+
+extern "C" int b2f_encode_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts *opts, size_t n_streams,
+                                 const uint8_t *d_in, const uint64_t *in_off, const size_t *in_len,
+                                 const int64_t *const *sched, const size_t *n_sched,
+                                 uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, int *status) {
+    if (!ctx) return B2F_ERR_INVALID_ARG;
+    b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
+    int rc = validate_opts(ctx, fmt, *opts); if (rc) return rc;
+    if (opts->mode == B2F_MODE_STORED) { ctx->err = "stored mode has no device-resident variant (framing only)"; return B2F_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    EncodeJob job; job.d_in = d_in;
+    job.in_off.assign(in_off, in_off + n_streams); job.in_len.resize(n_streams);
+    for (size_t s = 0; s < n_streams; s++) job.in_len[s] = in_len[s];
+    rc = encode_on_device(ctx, fmt, *opts, n_streams, sched, n_sched, job);
+    if (rc) return rc;
+    for (size_t s = 0; s < n_streams; s++) {
+        out_len[s] = (size_t)job.out_len[s];
+        if (job.out_len[s] > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
+        status[s] = B2F_OK;
+        CK(cudaMemcpyAsync(d_out + out_off[s], ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s], job.out_len[s], cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_stats(ctx, false);
+    return B2F_OK;
+}
+
+extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *opts, size_t n_streams,
+                                const uint8_t *const *in, const size_t *in_len,
+                                const int64_t *const *sched, const size_t *n_sched,
+                                uint8_t *const *out, const size_t *out_cap, size_t *out_len, int *status) {
+    if (!ctx) return B2F_ERR_INVALID_ARG;
+    b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
+    int rc = validate_opts(ctx, fmt, *opts); if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    // stage inputs: stream s at a 256-aligned offset
+    EncodeJob job; job.in_off.resize(n_streams); job.in_len.resize(n_streams);
+    uint64_t total = 0;
+    for (size_t s = 0; s < n_streams; s++) { job.in_off[s] = total; job.in_len[s] = in_len[s]; total += align_up(in_len[s], 256); }
+    CK(ctx->buf[NB_IN].ensure(total + 512));
+    uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>();
+    ctx->tm.mark(ctx->stream, "h2d");
+    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(cudaMemcpyAsync(d_in + job.in_off[s], in[s], in_len[s], cudaMemcpyHostToDevice, ctx->stream));
+    job.d_in = d_in;
+    if (opts->mode == B2F_MODE_STORED) {
+        std::vector<uint32_t> crc, adler;
+        rc = run_checksums(ctx, d_in, job.in_off, job.in_len, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
+        if (rc) return rc;
+        for (size_t s = 0; s < n_streams; s++) {
+            std::vector<uint8_t> o;
+            stored_stream(fmt, *opts, in[s], in_len[s], sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, crc[s], adler[s], o);
+            out_len[s] = o.size();
+            if (o.size() > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
+            memcpy(out[s], o.data(), o.size()); status[s] = B2F_OK;
+        }
+        collect_stats(ctx, false);
+        return B2F_OK;
+    }
+    rc = encode_on_device(ctx, fmt, *opts, n_streams, sched, n_sched, job);
+    if (rc) return rc;
+    collect_stats(ctx, false);
+    for (size_t s = 0; s < n_streams; s++) {
+        out_len[s] = (size_t)job.out_len[s];
+        if (job.out_len[s] > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
+        status[s] = B2F_OK;
+        CK(cudaMemcpyAsync(out[s], ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s], job.out_len[s], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2F_OK;
+}
+
+// ------------------------------------------------------------------------------------------ E2: Lz77Encode backend
+extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, uint32_t window_size, uint32_t max_length, uint32_t *codes, size_t *n_codes) {
+    if (!ctx || !n_codes || (len && (!buf || !codes))) return B2F_ERR_INVALID_ARG;
+    if (window_size == 0 || max_length < 3) return B2F_ERR_INVALID_ARG;
+    *n_codes = 0;
+    if (len == 0) return B2F_OK;
+    if (len >= (1ull << 31)) return B2F_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    CK(ctx->buf[NB_IN].ensure(len + 512));
+    uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>();
+    CK(cudaMemcpyAsync(d_in, buf, len, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t n_tiles = (uint32_t)((len + kTile - 1) / kTile);
+    ChunkDesc cd; cd.off = 0; cd.len = (uint32_t)len; cd.block = 0;
+    uint32_t pref[8] = { 0, (uint32_t)((len + kSeg - 1) / kSeg), 0, (uint32_t)((len + kPTile - 1) / kPTile), 0, n_tiles, 0, (n_tiles + kGrpTiles - 1) / kGrpTiles };
+    CK(ctx->buf[NB_LINK].ensure(len * 2 + 256)); CK(ctx->buf[NB_MD].ensure(len * 4 + 256)); CK(ctx->buf[NB_SYM].ensure(len * 4 + 256));
+    CK(ctx->buf[NB_EXIT].ensure((size_t)n_tiles * kExitW * 2 + 256));
+    size_t tile_bytes = carve_size<uint16_t>(n_tiles) + carve_size<uint32_t>(n_tiles) + carve_size<uint64_t>(n_tiles) + 512;
+    CK(ctx->buf[NB_TILE].ensure(tile_bytes));
+    CK(ctx->buf[NB_BLK].ensure(kHistStride * 4 + 256));
+    CK(ctx->buf[NB_DESC].ensure(1024));
+    CK(ctx->buf[NB_OUT].ensure(len * 4 + 256));          // compacted codes
+    CK(ctx->pin_meta.ensure(1024));
+    uint8_t *hp = ctx->pin_meta.as<uint8_t>();
+    memcpy(hp, &cd, sizeof cd); memcpy(hp + 256, pref, sizeof pref);
+    uint8_t *dp = ctx->buf[NB_DESC].as<uint8_t>();
+    CK(cudaMemcpyAsync(dp, hp, 512, cudaMemcpyHostToDevice, ctx->stream));
+    EncDev E; memset(&E, 0, sizeof E);
+    E.in = d_in; E.chunks = (const ChunkDesc *)dp; E.n_chunks = 1;
+    const uint32_t *dpref = (const uint32_t *)(dp + 256);
+    E.seg0 = dpref; E.pt0 = dpref + 2; E.tile0 = dpref + 4; E.grp0 = dpref + 6;
+    E.n_segs = pref[1]; E.n_ptiles = pref[3]; E.n_tiles = n_tiles; E.n_grps = pref[7];
+    E.window = window_size > 32768 ? 32768 : window_size; E.max_len = max_length > 258 ? 258 : max_length;
+    E.link = ctx->buf[NB_LINK].as<uint16_t>(); E.md = ctx->buf[NB_MD].as<uint32_t>(); E.sym = ctx->buf[NB_SYM].as<uint32_t>();
+    E.exit_tab = ctx->buf[NB_EXIT].as<uint16_t>();
+    uint8_t *tp = ctx->buf[NB_TILE].as<uint8_t>();
+    E.tile_entry = carve<uint16_t>(tp, n_tiles); E.tile_nsym = carve<uint32_t>(tp, n_tiles);
+    uint64_t *tile_symoff = carve<uint64_t>(tp, n_tiles);
+    uint64_t *d_total = reinterpret_cast<uint64_t *>(tp);
+    E.hist = ctx->buf[NB_BLK].as<uint32_t>();
+    CK(cudaMemsetAsync(E.hist, 0, kHistStride * 4, ctx->stream));
+    CK(enc_launch_lz(E, ctx->stream, &ctx->tm));
+    uint32_t *d_codes = ctx->buf[NB_OUT].as<uint32_t>();
+    CK(enc_launch_compact(E, tile_symoff, d_total, d_codes, ctx->stream));
+    ctx->stats.kernel_launches += enc_launch_count_lz() + 2;
+    ctx->tm.finish(ctx->stream);
+    CK(ctx->pin_res.ensure(64));
+    uint64_t *h_total = ctx->pin_res.as<uint64_t>();
+    CK(cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_codes = (size_t)*h_total;
+    CK(cudaMemcpyAsync(codes, d_codes, *n_codes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_stats(ctx, false);
+    return B2F_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decode
+namespace {
+struct HostReader { const uint8_t *p; size_t n, pos; };
+bool rd_exact(HostReader &r, uint8_t *dst, size_t k) { if (r.n - r.pos < k) { r.pos = r.n; return false; } memcpy(dst, r.p + r.pos, k); r.pos += k; return true; }
+
+// gzip::Header::read_from (gzip.rs:390-446) incl. libflate's CRC16 convention; returns B2F status
+int parse_gzip_header(HostReader &r) {
+    uint8_t b[10];
+    if (!rd_exact(r, b, 10)) return B2F_ERR_UNEXPECTED_EOF;
+    if (b[0] != 31 || b[1] != 139) return B2F_ERR_INVALID_DATA;
+    if (b[2] != 8) return B2F_ERR_INVALID_DATA;
+    const uint8_t flags = b[3];
+    std::vector<uint8_t> re;                     // the header as libflate re-serialises it for the CRC16 (is_text is never restored)
+    const uint8_t xfl = b[8] == 4 ? 4 : b[8] == 2 ? 2 : 0;
+    const uint8_t h[10] = { 31, 139, 8, (uint8_t)(flags & (4 | 8 | 16)), b[4], b[5], b[6], b[7], xfl, b[9] };
+    re.insert(re.end(), h, h + 10);
+    if (flags & 4) {
+        uint8_t l2[2];
+        if (!rd_exact(r, l2, 2)) return B2F_ERR_UNEXPECTED_EOF;
+        size_t limit = (size_t)(l2[0] | (l2[1] << 8));
+        size_t total_pos = re.size(); re.push_back(0); re.push_back(0); size_t total = 0;
+        while (limit > 0) {
+            uint8_t sf[4];
+            if (limit < 4 || r.n - r.pos < 4) { r.pos = std::min(r.n, r.pos + limit); return B2F_ERR_UNEXPECTED_EOF; }
+            rd_exact(r, sf, 4); limit -= 4;
+            size_t dl = (size_t)(sf[2] | (sf[3] << 8));
+            if (dl > limit || r.n - r.pos < dl) { r.pos = std::min(r.n, r.pos + std::min(dl, limit)); return B2F_ERR_UNEXPECTED_EOF; }
+            re.insert(re.end(), sf, sf + 4); re.insert(re.end(), r.p + r.pos, r.p + r.pos + dl); r.pos += dl; limit -= dl; total += 4 + dl;
+        }
+        re[total_pos] = (uint8_t)total; re[total_pos + 1] = (uint8_t)(total >> 8);
+    }
+    for (int f = 8; f <= 16; f <<= 1) if (flags & f) {
+        for (;;) { uint8_t c; if (!rd_exact(r, &c, 1)) return B2F_ERR_UNEXPECTED_EOF; re.push_back(c); if (!c) break; }
+    }
+    if (flags & 2) {
+        uint8_t c2[2];
+        if (!rd_exact(r, c2, 2)) return B2F_ERR_UNEXPECTED_EOF;
+        uint16_t crc = (uint16_t)(c2[0] | (c2[1] << 8)), expected = (uint16_t)host_crc32(re.data(), re.size());
+        if (crc != expected) return B2F_ERR_INVALID_DATA;
+    }
+    return B2F_OK;
+}
+int parse_zlib_header(HostReader &r) {          // zlib::Header::read_from (zlib.rs:221-266)
+    uint8_t b[2];
+    if (!rd_exact(r, b, 2)) return B2F_ERR_UNEXPECTED_EOF;
+    if (((((uint32_t)b[0]) << 8) + b[1]) % 31 != 0) return B2F_ERR_INVALID_DATA;
+    if ((b[0] & 15) != 8) return B2F_ERR_INVALID_DATA;
+    if ((b[0] >> 4) > 7) return B2F_ERR_INVALID_DATA;
+    if (b[1] & 0x20) { uint8_t d[4]; if (!rd_exact(r, d, 4)) return B2F_ERR_UNEXPECTED_EOF; return B2F_ERR_INVALID_DATA; }
+    return B2F_OK;
+}
+int map_inf_status(int s) { return s == kInfOk ? B2F_OK : s == kInfInvalid ? B2F_ERR_INVALID_DATA : s == kInfEof ? B2F_ERR_UNEXPECTED_EOF : B2F_ERR_OUTPUT_TOO_SMALL; }
+
+struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_off; uint64_t out_cap; };
+
+// Decodes one "round": members[] are raw DEFLATE streams inside d_in; outputs to d_out.  Results to host vectors.
+int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::vector<Member> &mem,
+                  std::vector<int> &st, std::vector<uint64_t> &olen, std::vector<uint64_t> &cons) {
+    const size_t n = mem.size();
+    st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0);
+    if (!n) return B2F_OK;
+    size_t o_io = 0, o_il = o_io + n * 8, o_oo = o_il + n * 8, o_oc = o_oo + n * 8, in_total = o_oc + n * 8;
+    size_t o_st = align_up(in_total, 16), o_ol = o_st + align_up(n * 4, 16), o_cs = o_ol + n * 8, total = o_cs + n * 8;
+    CK(ctx->buf[NB_DEC_META].ensure(total + 64));
+    CK(ctx->pin_meta.ensure(total + 64));
+    uint8_t *hm = ctx->pin_meta.as<uint8_t>();
+    uint64_t *a = (uint64_t *)hm;
+    for (size_t i = 0; i < n; i++) { a[i] = mem[i].def_off; a[n + i] = mem[i].def_len; a[2 * n + i] = mem[i].out_off; a[3 * n + i] = mem[i].out_cap; }
+    uint8_t *dm = ctx->buf[NB_DEC_META].as<uint8_t>();
+    CK(cudaMemcpyAsync(dm, hm, in_total, cudaMemcpyHostToDevice, ctx->stream));
+    DecDev D;
+    D.in = d_in; D.in_off = (const uint64_t *)(dm + o_io); D.in_len = (const uint64_t *)(dm + o_il);
+    D.out = d_out; D.out_off = (const uint64_t *)(dm + o_oo); D.out_cap = (const uint64_t *)(dm + o_oc); D.n = (uint32_t)n;
+    D.status = (int32_t *)(dm + o_st); D.out_len = (uint64_t *)(dm + o_ol); D.consumed = (uint64_t *)(dm + o_cs);
+    ctx->tm.mark(ctx->stream, "inflate");
+    CK(dec_launch_serial(D, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    ctx->tm.mark(ctx->stream, "results");
+    CK(ctx->pin_res.ensure(total + 64));
+    uint8_t *hr = ctx->pin_res.as<uint8_t>();
+    CK(cudaMemcpyAsync(hr + o_st, dm + o_st, total - o_st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; i++) { st[i] = ((int32_t *)(hr + o_st))[i]; olen[i] = ((uint64_t *)(hr + o_ol))[i]; cons[i] = ((uint64_t *)(hr + o_cs))[i]; }
+    return B2F_OK;
+}
+
+// warp per request: copies len[i] bytes from src + soff[i] to dst + doff[i]
+__global__ void k_gather_windows(const uint8_t *src, const uint64_t *soff, const uint64_t *len, const uint64_t *doff, uint8_t *dst, uint32_t n) {
+    uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint8_t *s = src + soff[i]; uint8_t *d = dst + doff[i];
+    for (uint64_t k = lane; k < len[i]; k += 32) d[k] = s[k];
+}
+
+// Access to the few container bytes the host needs (headers, trailers).  Host inputs are read in place; device-resident
+// inputs are fetched as small windows with ONE gather kernel + ONE copy per round.
+struct InputAccess {
+    b2f_ctx *ctx; const uint8_t *const *h_in; const uint8_t *d_in; const uint64_t *in_off; const size_t *in_len;
+    int fetch(const std::vector<size_t> &streams, const std::vector<size_t> &pos, size_t want, std::vector<std::vector<uint8_t>> &out) {
+        const size_t n = streams.size();
+        out.assign(n, std::vector<uint8_t>());
+        if (!n) return B2F_OK;
+        std::vector<uint64_t> meta(3 * n); uint64_t total = 0;
+        for (size_t i = 0; i < n; i++) {
+            size_t s = streams[i];
+            size_t avail = in_len[s] > pos[i] ? in_len[s] - pos[i] : 0, k = std::min(avail, want);
+            if (h_in) { out[i].assign(h_in[s] + pos[i], h_in[s] + pos[i] + k); continue; }
+            meta[i] = in_off[s] + pos[i]; meta[n + i] = k; meta[2 * n + i] = total; total += k;
+        }
+        if (h_in || total == 0) return B2F_OK;
+        CK(ctx->buf[NB_DEC_META].ensure(3 * n * 8 + total + 256));
+        CK(ctx->pin_win.ensure(3 * n * 8 + total + 256));
+        uint8_t *hw = ctx->pin_win.as<uint8_t>(); uint8_t *dw = ctx->buf[NB_DEC_META].as<uint8_t>();
+        memcpy(hw, meta.data(), 3 * n * 8);
+        CK(cudaMemcpyAsync(dw, hw, 3 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const uint64_t *dm = (const uint64_t *)dw;
+        k_gather_windows<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(d_in, dm, dm + n, dm + 2 * n, dw + 3 * n * 8, (uint32_t)n);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+        CK(cudaMemcpyAsync(hw + 3 * n * 8, dw + 3 * n * 8, total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < n; i++) out[i].assign(hw + 3 * n * 8 + meta[2 * n + i], hw + 3 * n * 8 + meta[2 * n + i] + meta[n + i]);
+        return B2F_OK;
+    }
+};
+
+// Shared decode driver: container framing on the host (a few bytes per stream), DEFLATE + checksums on the device.
+int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const uint8_t *d_in, const uint64_t *in_off, const size_t *in_len,
+                uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status) {
+    std::vector<size_t> pos(n_streams, 0);            // reader position per stream
+    std::vector<uint64_t> produced(n_streams, 0);
+    std::vector<char> done(n_streams, 0);
+    for (size_t s = 0; s < n_streams; s++) { status[s] = B2F_OK; out_len[s] = 0; in_consumed[s] = 0; }
+    bool first = true;
+    for (;;) {
+        // ---- container headers
+        std::vector<size_t> act;
+        for (size_t s = 0; s < n_streams; s++) if (!done[s]) act.push_back(s);
+        if (act.empty()) break;
+        if (fmt != B2F_FMT_DEFLATE) {
+            std::vector<size_t> todo = act, apos;
+            size_t want = 4096;
+            while (!todo.empty()) {
+                apos.clear(); for (size_t s : todo) apos.push_back(pos[s]);
+                std::vector<std::vector<uint8_t>> win;
+                int rc = IA.fetch(todo, apos, want, win); if (rc) return rc;
+                std::vector<size_t> again;
+                for (size_t i = 0; i < todo.size(); i++) {
+                    size_t s = todo[i];
+                    HostReader r = { win[i].data(), win[i].size(), 0 };
+                    int hrc = fmt == B2F_FMT_ZLIB ? parse_zlib_header(r) : parse_gzip_header(r);
+                    if (hrc == B2F_ERR_UNEXPECTED_EOF && pos[s] + win[i].size() < in_len[s]) { again.push_back(s); continue; }   // window too small
+                    if (hrc != B2F_OK) {
+                        done[s] = 1; in_consumed[s] = pos[s] + r.pos;
+                        // MultiDecoder: EOF while reading the NEXT header ends the stream cleanly (gzip.rs:1148-1156)
+                        if (!(!first && hrc == B2F_ERR_UNEXPECTED_EOF)) status[s] = hrc;
+                        continue;
+                    }
+                    pos[s] += r.pos;
+                }
+                todo.swap(again);
+                want = want < (1u << 20) ? (1u << 20) : (size_t)-1;
+            }
+        }
+        std::vector<Member> mem;
+        for (size_t s : act) {
+            if (done[s]) continue;
+            Member m = { s, in_off[s] + pos[s], in_len[s] - pos[s], out_off[s] + produced[s], out_cap[s] > produced[s] ? out_cap[s] - produced[s] : 0 };
+            mem.push_back(m);
+        }
+        if (mem.empty()) break;
+        std::vector<int> st; std::vector<uint64_t> olen, cons;
+        int rc = inflate_round(ctx, d_in, d_out, mem, st, olen, cons);
+        if (rc) return rc;
+        // ---- trailers + checksums of what was produced in this round
+        std::vector<uint64_t> ck_off, ck_len; std::vector<size_t> ck_idx, ck_streams, ck_pos;
+        for (size_t i = 0; i < mem.size(); i++) {
+            size_t s = mem[i].stream;
+            uint64_t wrote = std::min<uint64_t>(olen[i], mem[i].out_cap);
+            pos[s] += cons[i];
+            produced[s] += olen[i]; out_len[s] = produced[s]; in_consumed[s] = pos[s];
+            if (st[i] != kInfOk) { status[s] = map_inf_status(st[i]); done[s] = 1; continue; }
+            if (fmt == B2F_FMT_DEFLATE) { done[s] = 1; continue; }
+            ck_off.push_back(mem[i].out_off); ck_len.push_back(wrote); ck_idx.push_back(i); ck_streams.push_back(s); ck_pos.push_back(pos[s]);
+        }
+        if (!ck_idx.empty()) {
+            std::vector<uint32_t> crc, adler;
+            rc = run_checksums(ctx, d_out, ck_off, ck_len, fmt != B2F_FMT_ZLIB, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
+            if (rc) return rc;
+            std::vector<std::vector<uint8_t>> tw;
+            rc = IA.fetch(ck_streams, ck_pos, 8, tw); if (rc) return rc;
+            for (size_t j = 0; j < ck_idx.size(); j++) {
+                size_t s = ck_streams[j];
+                HostReader r = { tw[j].data(), tw[j].size(), 0 };
+                if (fmt == B2F_FMT_ZLIB) {               // zlib.rs:377-409
+                    uint8_t t[4];
+                    if (!rd_exact(r, t, 4)) status[s] = B2F_ERR_UNEXPECTED_EOF;
+                    else { uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3]; if (want != adler[j]) status[s] = B2F_ERR_INVALID_DATA; }
+                    done[s] = 1;
+                } else {                                 // gzip.rs:1018-1047: CRC32 checked, ISIZE read but not checked
+                    uint8_t t[8];
+                    if (!rd_exact(r, t, 4) || !rd_exact(r, t + 4, 4)) { status[s] = B2F_ERR_UNEXPECTED_EOF; done[s] = 1; }
+                    else {
+                        uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+                        if (want != crc[j]) { status[s] = B2F_ERR_INVALID_DATA; done[s] = 1; }
+                        else if (fmt == B2F_FMT_GZIP) done[s] = 1;
+                    }
+                }
+                pos[s] += r.pos; in_consumed[s] = pos[s];
+            }
+        }
+        first = false;
+        if (fmt != B2F_FMT_GZIP_MULTI) break;
+    }
+    return B2F_OK;
+}
+}  // namespace
+
+extern "C" int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams, const uint8_t *const *in, const size_t *in_len,
+                                uint8_t *const *out, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status) {
+    if (!ctx || fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP_MULTI) return B2F_ERR_INVALID_ARG;
+    if (n_streams == 0) return B2F_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    std::vector<uint64_t> in_off(n_streams), out_off(n_streams); uint64_t tin = 0, tout = 0;
+    for (size_t s = 0; s < n_streams; s++) { in_off[s] = tin; tin += align_up(in_len[s] + 16, 256); out_off[s] = tout; tout += align_up(out_cap[s] + 16, 256); }
+    CK(ctx->buf[NB_IN].ensure(tin + 512));
+    CK(ctx->buf[NB_DEC_OUT].ensure(tout + 512));
+    uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>(), *d_out = ctx->buf[NB_DEC_OUT].as<uint8_t>();
+    ctx->tm.mark(ctx->stream, "h2d");
+    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(cudaMemcpyAsync(d_in + in_off[s], in[s], in_len[s], cudaMemcpyHostToDevice, ctx->stream));
+    InputAccess IA = { ctx, in, d_in, in_off.data(), in_len };
+    int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status);
+    if (rc) return rc;
+    collect_stats(ctx, true);
+    for (size_t s = 0; s < n_streams; s++) {
+        size_t w = std::min(out_len[s], out_cap[s]);
+        if (w) CK(cudaMemcpyAsync(out[s], d_out + out_off[s], w, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2F_OK;
+}
+
+extern "C" int b2f_decode_device(b2f_ctx *ctx, int fmt, size_t n_streams, const uint8_t *d_in, const uint64_t *in_off, const size_t *in_len,
+                                 uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status) {
+    if (!ctx || fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP_MULTI) return B2F_ERR_INVALID_ARG;
+    if (n_streams == 0) return B2F_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    InputAccess IA = { ctx, nullptr, d_in, in_off, in_len };
+    int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off, in_len, d_out, out_off, out_cap, out_len, in_consumed, status);
+    if (rc) return rc;
+    collect_stats(ctx, true);
+    return B2F_OK;
+}
+
+// ------------------------------------------------------------------------------------------ streaming handles
+struct b2f_encoder { b2f_ctx *ctx; int fmt; b2f_encode_opts opts; std::vector<uint8_t> data; std::vector<int64_t> sched; std::vector<uint8_t> out; bool finished; std::string name, comment; std::vector<uint8_t> extra; };
+struct b2f_decoder { b2f_ctx *ctx; int fmt; std::vector<uint8_t> in; std::vector<uint8_t> out; size_t rd; size_t consumed; int status; bool decoded; };
+
+extern "C" int b2f_encoder_new(b2f_ctx *ctx, int fmt, const b2f_encode_opts *opts, b2f_encoder **out) {
+    if (!ctx || !out) return B2F_ERR_INVALID_ARG;
+    b2f_encoder *e = new b2f_encoder();
+    e->ctx = ctx; e->fmt = fmt; e->finished = false;
+    if (opts) e->opts = *opts; else b2f_encode_opts_default(&e->opts);
+    if (e->opts.gzip_filename) { e->name = e->opts.gzip_filename; e->opts.gzip_filename = e->name.c_str(); }
+    if (e->opts.gzip_comment) { e->comment = e->opts.gzip_comment; e->opts.gzip_comment = e->comment.c_str(); }
+    if (e->opts.gzip_has_extra) { e->extra.assign(e->opts.gzip_extra, e->opts.gzip_extra + e->opts.gzip_extra_len); e->opts.gzip_extra = e->extra.data(); }
+    int rc = validate_opts(ctx, fmt, e->opts);
+    if (rc) { delete e; return rc; }
+    *out = e; return B2F_OK;
+}
+extern "C" int b2f_encoder_write(b2f_encoder *e, const uint8_t *buf, size_t len) {
+    if (!e || e->finished) return B2F_ERR_INVALID_ARG;
+    e->data.insert(e->data.end(), buf, buf + len); e->sched.push_back((int64_t)len); return B2F_OK;
+}
+extern "C" int b2f_encoder_flush(b2f_encoder *e) { if (!e || e->finished) return B2F_ERR_INVALID_ARG; e->sched.push_back(B2F_SCHED_FLUSH); return B2F_OK; }
+extern "C" int b2f_encoder_finish(b2f_encoder *e, const uint8_t **out, size_t *out_len) {
+    if (!e || !out || !out_len) return B2F_ERR_INVALID_ARG;
+    if (!e->finished) {
+        size_t cap = b2f_encode_bound(e->data.size(), e->sched.size(), &e->opts);
+        e->out.resize(cap);
+        const uint8_t *in = e->data.data(); size_t n = e->data.size(); const int64_t *sc = e->sched.data(); size_t ns = e->sched.size();
+        static const int64_t none = 0;
+        if (!ns) { sc = &none; }                         // zero writes: an explicit empty schedule (not "one write_all")
+        uint8_t *op = e->out.data(); size_t ol = 0; int st = 0;
+        size_t ns_eff = ns;
+        int rc = b2f_encode_batch(e->ctx, e->fmt, &e->opts, 1, &in, &n, &sc, &ns_eff, &op, &cap, &ol, &st);
+        if (rc) return rc;
+        if (st) return st;
+        e->out.resize(ol); e->finished = true;
+    }
+    *out = e->out.data(); *out_len = e->out.size();
+    return B2F_OK;
+}
+extern "C" void b2f_encoder_free(b2f_encoder *e) { delete e; }
+
+extern "C" int b2f_decoder_new(b2f_ctx *ctx, int fmt, const uint8_t *in, size_t in_len, b2f_decoder **out) {
+    if (!ctx || !out) return B2F_ERR_INVALID_ARG;
+    b2f_decoder *d = new b2f_decoder();
+    d->ctx = ctx; d->fmt = fmt; d->in.assign(in, in + in_len); d->rd = 0; d->consumed = 0; d->status = 0; d->decoded = false;
+    *out = d; return B2F_OK;
+}
+static int decoder_run(b2f_decoder *d) {
+    size_t cap = std::max<size_t>(1 << 16, d->in.size() * 8 + 4096);
+    for (;;) {
+        d->out.resize(cap);
+        const uint8_t *in = d->in.data(); size_t n = d->in.size(); uint8_t *op = d->out.data(); size_t ol = 0, ic = 0; int st = 0;
+        int rc = b2f_decode_batch(d->ctx, d->fmt, 1, &in, &n, &op, &cap, &ol, &ic, &st);
+        if (rc) return rc;
+        if (st == B2F_ERR_OUTPUT_TOO_SMALL) { cap = std::max(cap * 2, ol + 64); continue; }
+        d->out.resize(std::min(ol, cap)); d->consumed = ic; d->status = st; d->decoded = true;
+        return B2F_OK;
+    }
+}
+extern "C" int64_t b2f_decoder_read(b2f_decoder *d, uint8_t *buf, size_t len) {
+    if (!d) return B2F_ERR_INVALID_ARG;
+    if (!d->decoded) { int rc = decoder_run(d); if (rc) return rc; }
+    // Decoder::read: data decoded before an error is NOT handed out by read() (it stays in unread_decoded_data()); the error is returned.
+    if (d->status != B2F_OK) return d->status;
+    size_t k = std::min(len, d->out.size() - d->rd);
+    memcpy(buf, d->out.data() + d->rd, k); d->rd += k;
+    return (int64_t)k;
+}
+extern "C" size_t b2f_decoder_unread(const b2f_decoder *d, const uint8_t **ptr) { if (!d || !d->decoded) return 0; if (ptr) *ptr = d->out.data() + d->rd; return d->out.size() - d->rd; }
+extern "C" size_t b2f_decoder_consumed(const b2f_decoder *d) { return d ? d->consumed : 0; }
+extern "C" void b2f_decoder_free(b2f_decoder *d) { delete d; }

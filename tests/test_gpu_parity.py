@@ -1,0 +1,306 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every test goes through the C ABI of libb2f.so and
+compares with the CPU oracle (bit-exact) or with the reference's committed golden vectors."""
+import json
+import os
+import random
+import zlib as pyzlib
+import gzip as pygzip
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "goldens.json")))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from libflate_b200 import native
+    c = native.Context(0)
+    yield c
+    c.close()
+
+
+def _text(rng, n, nwords=300):
+    words = [bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz_") for _ in range(rng.randint(2, 9))) for _ in range(nwords)]
+    b = bytearray()
+    while len(b) < n:
+        b += rng.choice(words) + b"\n"
+    return bytes(b[:n])
+
+
+def _cases(rng):
+    return {
+        "empty": b"", "one": b"a", "two": b"ab", "three": b"abc", "four": b"abcd", "aaaaa": b"aaaaa",
+        "hello": b"Hello World!", "text3k": _text(rng, 3000), "text70k": _text(rng, 70000),
+        "rand5k": bytes(rng.getrandbits(8) for _ in range(5000)), "zeros100k": b"\x00" * 100000,
+        "w32767": _text(rng, 32767), "w32768": _text(rng, 32768), "w32769": _text(rng, 32769),
+        "text300k": _text(rng, 300000), "counter1m": bytes(i & 255 for i in range(1 << 20)),
+        "lowent": bytes(rng.getrandbits(8) >> 6 for _ in range(200000)),
+        "periodic": (b"abcdefghij" * 30000)[:262144 + 77],
+    }
+
+
+# ------------------------------------------------------------------------------------------ C1 / C2
+def test_checksum_kats(ctx):                                   # src/checksum.rs:45-56
+    g = G["checksum_kat"]
+    assert ctx.crc32([g["input"].encode()]) == [g["crc32"]]
+    assert ctx.adler32([g["input"].encode()]) == [g["adler32"]]
+
+
+def test_checksums_match_oracle_and_zlib(ctx):
+    rng = random.Random(1)
+    datas = [b"", b"a", bytes(rng.getrandbits(8) for _ in range(511)), bytes(rng.getrandbits(8) for _ in range(512)),
+             bytes(rng.getrandbits(8) for _ in range(513)), _text(rng, 100003), b"\xff" * 1000000, _text(rng, 3 << 20)]
+    assert ctx.crc32(datas) == [orc.crc32(d) for d in datas] == [pyzlib.crc32(d) for d in datas]
+    assert ctx.adler32(datas) == [orc.adler32(d) for d in datas] == [pyzlib.adler32(d) for d in datas]
+    # chaining through init values (Crc32::update called repeatedly)
+    a, b = datas[5][:4321], datas[5][4321:]
+    assert ctx.crc32([b], init=[pyzlib.crc32(a)]) == [pyzlib.crc32(datas[5])]
+    assert ctx.adler32([b], init=[pyzlib.adler32(a)]) == [pyzlib.adler32(datas[5])]
+
+
+# ------------------------------------------------------------------------------------------ E2: LZ77 codes
+def test_lz77_issue21(ctx):                                    # src/lz77.rs:16-31
+    assert list(ctx.lz77_default(b"aaaaa")) == [97, 0x80000000 | (4 << 16) | 1]
+
+
+def test_lz77_codes_match_oracle(ctx):
+    rng = random.Random(2)
+    for name, d in _cases(rng).items():
+        got, want = ctx.lz77_default(d), orc.lz77_default(d)
+        assert len(got) == len(want), name
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (name, int(bad[0]), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
+
+
+def test_lz77_window_and_max_length_options(ctx):              # libflate_lz77/src/default.rs:222-239
+    rng = random.Random(3)
+    d = _text(rng, 120000, nwords=40)
+    for window, max_len in ((1024, 258), (32768, 16), (4096, 3), (300, 100)):
+        got, want = ctx.lz77_default(d, window, max_len), orc.lz77_default(d, window, max_len)
+        assert np.array_equal(got, want), (window, max_len)
+
+
+def test_lz77_multi_segment_chunk(ctx):                        # one chunk > 256 KiB: several chain segments + many tiles
+    rng = random.Random(4)
+    d = _text(rng, 3 * 262144 + 12345, nwords=2000)
+    assert np.array_equal(ctx.lz77_default(d), orc.lz77_default(d))
+
+
+# ------------------------------------------------------------------------------------------ encode goldens
+def test_encode_goldens(ctx):
+    from libflate_b200 import native as nv
+    g = G["deflate_hello_dynamic"]
+    assert list(ctx.encode(nv.FMT_DEFLATE, g["plain"].encode())) == g["bytes"]         # src/deflate/encode.rs:152-154
+    g = G["zlib_hello_default"]
+    assert list(ctx.encode(nv.FMT_ZLIB, g["plain"].encode())) == g["bytes"]            # src/zlib.rs:547-549
+    g = G["deflate_hello_stored"]
+    assert list(ctx.encode(nv.FMT_DEFLATE, g["plain"].encode(), mode=nv.MODE_STORED)) == g["bytes"]
+    g = G["zlib_raw_encode"]
+    assert list(ctx.encode(nv.FMT_ZLIB, g["plain"].encode(), mode=nv.MODE_STORED)) == g["bytes"]
+    g = G["gzip_stored_mtime123"]
+    assert list(ctx.encode(nv.FMT_GZIP, g["plain"].encode(), mode=nv.MODE_STORED, mtime=123)) == g["bytes"]
+    for key, sync in (("zlib_issue27_none", False), ("zlib_issue27_sync", True)):     # src/zlib.rs:840-902
+        g = G[key]
+        writes = [w.encode() for w in g["writes"]]
+        sched = ([len(w) for w in writes] + [nv.FLUSH]) * 2
+        assert list(ctx.encode(nv.FMT_ZLIB, b"".join(writes) * 2, sched, zlib_flush_sync=sync)) == g["bytes"]
+
+
+def test_issue52_size_bound(ctx):                              # src/deflate/encode.rs:435-457
+    from libflate_b200 import native as nv
+    data = open(os.path.join(HERE, "golden", "issue52_input.bin"), "rb").read()
+    for lim in (16031, 16032):
+        enc = ctx.encode(nv.FMT_DEFLATE, data[:lim])
+        assert len(enc) < lim and enc == orc.encode(orc.FMT_DEFLATE, data[:lim])
+
+
+# ------------------------------------------------------------------------------------------ encode == oracle
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_encode_matches_oracle_single_write(ctx, fmt):
+    rng = random.Random(10 + fmt)
+    cases = _cases(rng)
+    names = list(cases)
+    got = ctx.encode_batch(fmt, [cases[k] for k in names], mtime=77)
+    for k, enc in zip(names, got):
+        want = orc.encode(fmt, cases[k], mtime=77)
+        assert enc == want, (k, len(enc), len(want), next((i for i in range(min(len(enc), len(want))) if enc[i] != want[i]), -1))
+
+
+def test_encode_matches_oracle_schedules(ctx):
+    rng = random.Random(20)
+    d = _text(rng, 2500000, nwords=3000)
+    scheds = {
+        "8k": [8192] * (len(d) // 8192 + 1), "7": None, "1m": [1 << 20] * 3, "odd": [100000, 1, 0, 262143, 1, 999999, 5000000],
+        "flushes": [1000, -1, -1, 300000, -1, 1200000, -1], "big_first": [2000000, 10, -1, 600000],
+    }
+    scheds["7"] = [70001] * (len(d) // 70001 + 1)
+    for fmt in (0, 1, 2):
+        names = list(scheds)
+        got = ctx.encode_batch(fmt, [d] * len(names), [scheds[k] for k in names], mtime=5)
+        for k, enc in zip(names, got):
+            want = orc.encode(fmt, d, scheds[k], mtime=5)
+            assert enc == want, (fmt, k, len(enc), len(want))
+    enc = ctx.encode(1, d, scheds["flushes"], zlib_flush_sync=True)
+    assert enc == orc.encode(1, d, scheds["flushes"], zlib_flush_sync=True)
+    assert pyzlib.decompress(enc) == d
+
+
+def test_encode_options_match_oracle(ctx):
+    rng = random.Random(30)
+    d = _text(rng, 400000, nwords=100)
+    for kw in (dict(mode=1), dict(block_size=50000), dict(window_size=1024), dict(max_length=10), dict(window_size=2000, max_length=40, block_size=7777),
+               dict(mode=2, block_size=1000), dict(mode=2)):
+        for fmt in (0, 1, 2):
+            for sched in (None, [30000] * 14, [5, -1, 100000, -1]):
+                enc = ctx.encode(fmt, d, sched, **kw)
+                assert enc == orc.encode(fmt, d, sched, **kw), (kw, fmt, sched and sched[:3])
+
+
+def test_gzip_header_fields(ctx):                              # src/gzip.rs:126-288, 343-389
+    kw = dict(mtime=123456, os_=11, is_text=True, is_verified=True, extra=bytes([0, 0x42, 3, 0]) + b"abc", filename=b"foo.txt", comment=b"hi")
+    enc = ctx.encode(2, b"hello world hello world", **kw)
+    assert enc == orc.encode(2, b"hello world hello world", **kw)
+
+
+# ------------------------------------------------------------------------------------------ decode
+def test_decode_goldens(ctx):
+    from libflate_b200 import native as nv
+    st, out, used, _ = ctx.decode(nv.FMT_DEFLATE, bytes(G["deflate_fixed_hello"]["bytes"]))        # src/deflate/decode.rs:28-33
+    assert st == 0 and out == b"Hello World!" and used == 14
+    st, out, _, _ = ctx.decode(nv.FMT_ZLIB, bytes(G["zlib_decode_works"]["bytes"]))                 # src/zlib.rs:708-730
+    assert st == 0 and out == b"Hello World!"
+    one = orc.encode(orc.FMT_GZIP, b"Hello World!")                                                  # src/gzip.rs:1217-1226
+    st, out, used, _ = ctx.decode(nv.FMT_GZIP, one * 2)
+    assert st == 0 and out == b"Hello World!" and used == len(one)
+    st, out, used, _ = ctx.decode(nv.FMT_GZIP_MULTI, one * 2)
+    assert st == 0 and out == b"Hello World!Hello World!" and used == 2 * len(one)
+    st, out, _, _ = ctx.decode(nv.FMT_GZIP, open(os.path.join(HERE, "golden", "offset.gz"), "rb").read())   # src/non_blocking/gzip.rs:178-183
+    assert st == 0 and out == open(os.path.join(HERE, "golden", "offset.bin"), "rb").read()
+
+
+def test_decode_error_goldens(ctx):
+    from libflate_b200 import native as nv
+    for name in sorted(os.listdir(os.path.join(HERE, "golden"))):                                    # src/zlib.rs:799-837
+        if name.startswith("issue16_crash-"):
+            st, _, _, _ = ctx.decode(nv.FMT_ZLIB, open(os.path.join(HERE, "golden", name), "rb").read())
+            assert st == nv.ERR_INVALID_DATA
+    st, _, _, _ = ctx.decode(nv.FMT_DEFLATE, bytes(G["deflate_it_works_too_long"]["encoded"]))      # src/deflate/decode.rs:194-212
+    assert st == nv.ERR_INVALID_DATA
+    st, _, _, _ = ctx.decode(nv.FMT_DEFLATE, bytes(G["deflate_issue64"]["encoded"]))                # :216-220
+    assert st != 0
+    for k in (1, 2, 3):                                                                              # src/gzip.rs:1230-1247
+        st, _, _, _ = ctx.decode(nv.FMT_GZIP, bytes(G[f"gzip_issue15_{k}"]["encoded"]))
+        assert st != 0
+    st, out, _, _ = ctx.decode(nv.FMT_ZLIB, bytes(G["zlib_issue71"]["encoded"]))                     # src/zlib.rs:917-934
+    assert st != 0 and list(out) == G["zlib_issue71"]["partial"]
+    st, _, _, _ = ctx.decode(nv.FMT_ZLIB, bytes([0, 0]))                                             # src/zlib.rs:938-943
+    assert st == nv.ERR_INVALID_DATA
+
+
+def test_decode_matches_oracle_valid_and_corrupt(ctx):
+    rng = random.Random(40)
+    d = _text(rng, 200000)
+    streams, fmts = [], []
+    for fmt in (0, 1, 2):
+        enc = orc.encode(fmt, d, [8192] * 30)
+        streams += [enc, enc[: len(enc) // 2], enc[:7], enc[:-1], enc + b"tail"]
+        fmts += [fmt] * 5
+        for _ in range(40):
+            b = bytearray(enc)
+            i = rng.randrange(len(b)); b[i] ^= 1 << rng.randrange(8)
+            streams.append(bytes(b)); fmts.append(fmt)
+    for lvl in (0, 1, 6, 9):
+        streams.append(pyzlib.compress(d, lvl)); fmts.append(1)
+    streams.append(pygzip.compress(d, 6, mtime=0)); fmts.append(2)
+    for fmt in (0, 1, 2):
+        idx = [i for i, f in enumerate(fmts) if f == fmt]
+        res = ctx.decode_batch(fmt, [streams[i] for i in idx])
+        for i, (st, out, used, _) in zip(idx, res):
+            rc, want, wused, msg = orc.decode(fmt, streams[i])
+            assert st == rc, (fmt, i, st, rc, msg)
+            assert out == want, (fmt, i, len(out), len(want), msg)
+            if rc == 0:
+                assert used == wused
+
+
+def test_decode_output_too_small(ctx):
+    d = b"abcabcabc" * 5000
+    enc = orc.encode(orc.FMT_ZLIB, d)
+    st, out, _, need = ctx.decode(1, enc, cap=1000)
+    assert st == -3 and out == d[:1000] and need == len(d)
+
+
+# ------------------------------------------------------------------------------------------ streaming handles (Read/Write surface)
+def test_streaming_encoder_decoder_handles(ctx):
+    from libflate_b200.deflate import Encoder, Decoder
+    from libflate_b200 import gzip as bgzip, zlib as bzlib
+    rng = random.Random(50)
+    d = _text(rng, 300000)
+    e = Encoder(ctx)                                                                                 # src/deflate/encode.rs:132-258
+    for k in range(0, len(d), 50000):
+        assert e.write(d[k: k + 50000]) == len(d[k: k + 50000])
+    e.flush()
+    enc = e.finish()
+    assert enc == orc.encode(0, d, [50000] * 6 + [-1])
+    dec = Decoder(ctx, enc)                                                                          # src/deflate/decode.rs:8-165
+    got = bytearray()
+    while True:
+        chunk = dec.read(7777)
+        if not chunk:
+            break
+        got += chunk
+    assert bytes(got) == d
+    ge = bgzip.Encoder(ctx, mtime=9)
+    ge.write_all(d)
+    genc = ge.finish()
+    assert genc == orc.encode(2, d, [len(d)], mtime=9)
+    assert bgzip.Decoder(ctx, genc).read_to_end() == d
+    assert bgzip.MultiDecoder(ctx, genc * 3).read_to_end() == d * 3
+    ze = bzlib.Encoder(ctx)
+    ze.write_all(d)
+    zenc = ze.finish()
+    assert pyzlib.decompress(zenc) == d and bzlib.Decoder(ctx, zenc).read_to_end() == d
+    # error surface: io::ErrorKind::InvalidData -> exception, partial data via unread_decoded_data()
+    bad = bzlib.Decoder(ctx, bytes(G["zlib_issue71"]["encoded"]))
+    with pytest.raises(Exception):
+        bad.read_to_end()
+    assert list(bad.unread_decoded_data()) == G["zlib_issue71"]["partial"]
+
+
+# ------------------------------------------------------------------------------------------ BASELINE-shaped cases (reduced sizes; full sizes in bench.py)
+def test_config2_shape_many_streams_raw_deflate(ctx):
+    from libflate_b200 import titles
+    datas = [titles.segment(1000 + i, 1 << 20).ljust(1 << 20, b"\n") for i in range(6)]
+    encs = ctx.encode_batch(0, datas)
+    for i, (d, e) in enumerate(zip(datas, encs)):
+        if i < 2:
+            assert e == orc.encode(0, d)
+        assert pyzlib.decompress(e, -15) == d
+    res = ctx.decode_batch(0, encs)
+    assert all(st == 0 and out == d for (st, out, _, _), d in zip(res, datas))
+
+
+def test_config3_shape_gzip_roundtrip_schedule_a(ctx):
+    from libflate_b200 import titles
+    d = titles.generate(5 * (1 << 20) + 12345, seed=42, workers=1).tobytes()
+    sched = [8192] * (len(d) // 8192 + 1)
+    enc = ctx.encode(2, d, sched, mtime=0)
+    assert enc == orc.encode(2, d, sched, mtime=0)
+    st, out, used, _ = ctx.decode(2, enc)
+    assert st == 0 and out == d and used == len(enc)
+    assert pygzip.decompress(enc) == d
+
+
+def test_config4_shape_zlib_streams(ctx):
+    from libflate_b200 import titles
+    datas = [titles.segment(2000 + i, 1 << 18) for i in range(16)]
+    encs = ctx.encode_batch(1, datas)
+    for d, e in zip(datas, encs):
+        assert e == orc.encode(1, d)
+        assert e[-4:] == pyzlib.adler32(d).to_bytes(4, "big")

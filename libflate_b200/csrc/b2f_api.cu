@@ -526,6 +526,14 @@ void stored_stream(int fmt, const b2f_encode_opts &o, const uint8_t *in, size_t 
 }
 }  // namespace
 
+// bytes of in[] that the schedule actually writes (a schedule may stop short of in_len; those bytes are never written)
+static size_t effective_len(const int64_t *sched, size_t n_sched, size_t in_len) {
+    if (!sched) return in_len;
+    size_t pos = 0;
+    for (size_t k = 0; k < n_sched && pos < in_len; k++) if (sched[k] > 0) pos += std::min<size_t>((size_t)sched[k], in_len - pos);
+    return pos;
+}
+
 static int validate_opts(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o) {
     if (fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP) { ctx->err = "bad format"; return B2F_ERR_INVALID_ARG; }
     if (o.block_size == 0 || o.window_size == 0 || o.max_length < 3 || o.mode < 0 || o.mode > 2) { ctx->err = "bad encode options"; return B2F_ERR_INVALID_ARG; }
@@ -544,7 +552,7 @@ extern "C" int b2f_encode_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts *o
     ctx->tm.reset();
     EncodeJob job; job.d_in = d_in;
     job.in_off.assign(in_off, in_off + n_streams); job.in_len.resize(n_streams);
-    for (size_t s = 0; s < n_streams; s++) job.in_len[s] = in_len[s];
+    for (size_t s = 0; s < n_streams; s++) job.in_len[s] = effective_len(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s]);
     rc = encode_on_device(ctx, fmt, *opts, n_streams, sched, n_sched, job);
     if (rc) return rc;
     for (size_t s = 0; s < n_streams; s++) {
@@ -570,11 +578,15 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
     // stage inputs: stream s at a 256-aligned offset
     EncodeJob job; job.in_off.resize(n_streams); job.in_len.resize(n_streams);
     uint64_t total = 0;
-    for (size_t s = 0; s < n_streams; s++) { job.in_off[s] = total; job.in_len[s] = in_len[s]; total += align_up(in_len[s], 256); }
+    for (size_t s = 0; s < n_streams; s++) {
+        job.in_off[s] = total;
+        job.in_len[s] = effective_len(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s]);
+        total += align_up(job.in_len[s], 256);
+    }
     CK(ctx->buf[NB_IN].ensure(total + 512));
     uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>();
     ctx->tm.mark(ctx->stream, "h2d");
-    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(cudaMemcpyAsync(d_in + job.in_off[s], in[s], in_len[s], cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t s = 0; s < n_streams; s++) if (job.in_len[s]) CK(cudaMemcpyAsync(d_in + job.in_off[s], in[s], job.in_len[s], cudaMemcpyHostToDevice, ctx->stream));
     job.d_in = d_in;
     if (opts->mode == B2F_MODE_STORED) {
         std::vector<uint32_t> crc, adler;
@@ -582,7 +594,7 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         if (rc) return rc;
         for (size_t s = 0; s < n_streams; s++) {
             std::vector<uint8_t> o;
-            stored_stream(fmt, *opts, in[s], in_len[s], sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, crc[s], adler[s], o);
+            stored_stream(fmt, *opts, in[s], (size_t)job.in_len[s], sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, crc[s], adler[s], o);
             out_len[s] = o.size();
             if (o.size() > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
             memcpy(out[s], o.data(), o.size()); status[s] = B2F_OK;

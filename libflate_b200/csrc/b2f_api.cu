@@ -52,13 +52,13 @@ struct PinBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_COUNT };
+enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_DEC_CAND, NB_DEC_BLK, NB_DEC_SER, NB_COUNT };
 
 struct b2f_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevBuf buf[NB_COUNT];
-    PinBuf pin_meta, pin_res, pin_ck, pin_win;
+    PinBuf pin_meta, pin_res, pin_ck, pin_win, pin_cand, pin_blk, pin_ser;
     StageTimer tm;
     std::string err;
     b2f_stats stats;
@@ -101,7 +101,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->buf) b.release();
-    ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release();
+    ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release(); ctx->pin_cand.release(); ctx->pin_blk.release(); ctx->pin_ser.release();
     ctx->tm.destroy();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -727,34 +727,177 @@ int map_inf_status(int s) { return s == kInfOk ? B2F_OK : s == kInfInvalid ? B2F
 
 struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_off; uint64_t out_cap; };
 
+// Packs several host arrays into one pinned staging area + one H2D copy; returns device pointers.
+struct Packer {
+    PinBuf &pin; DevBuf &dev; size_t off = 0; std::vector<std::pair<const void *, size_t>> items; std::vector<size_t> offs;
+    Packer(PinBuf &p, DevBuf &d) : pin(p), dev(d) {}
+    size_t add(const void *src, size_t bytes) { size_t o = off; items.push_back({ src, bytes }); offs.push_back(o); off += align_up(bytes ? bytes : 1, 256); return o; }
+    size_t reserve(size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1, 256); return o; }     // device-only region
+    cudaError_t commit(cudaStream_t st) {
+        cudaError_t e = dev.ensure(off + 256); if (e != cudaSuccess) return e;
+        e = pin.ensure(off + 256); if (e != cudaSuccess) return e;
+        size_t hi = 0;
+        for (size_t i = 0; i < items.size(); i++) { if (items[i].second) memcpy(pin.as<uint8_t>() + offs[i], items[i].first, items[i].second); hi = std::max(hi, offs[i] + items[i].second); }
+        if (hi) e = cudaMemcpyAsync(dev.p, pin.p, hi, cudaMemcpyHostToDevice, st);
+        return e;
+    }
+    template <class T> T *ptr(size_t o) const { return reinterpret_cast<T *>(dev.as<uint8_t>() + o); }
+};
+
+constexpr uint64_t kParallelMinBytes = 128 * 1024;    // smaller streams are decoded in order by one warp each
+
 // Decodes one "round": members[] are raw DEFLATE streams inside d_in; outputs to d_out.  Results to host vectors.
+//  - large members: block-boundary finder -> probe every candidate -> verify the chain of block ends from bit 0 ->
+//    decode all blocks of the chain in parallel (one warp per block, 64 KiB window in shared memory);
+//  - small members, and any member whose chain is not clean (non-dynamic blocks, cross-block back-references,
+//    errors, too-small output): in-order kernel, which reproduces libflate's error kinds and partial output.
 int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::vector<Member> &mem,
                   std::vector<int> &st, std::vector<uint64_t> &olen, std::vector<uint64_t> &cons) {
     const size_t n = mem.size();
     st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0);
     if (!n) return B2F_OK;
-    size_t o_io = 0, o_il = o_io + n * 8, o_oo = o_il + n * 8, o_oc = o_oo + n * 8, in_total = o_oc + n * 8;
-    size_t o_st = align_up(in_total, 16), o_ol = o_st + align_up(n * 4, 16), o_cs = o_ol + n * 8, total = o_cs + n * 8;
-    CK(ctx->buf[NB_DEC_META].ensure(total + 64));
-    CK(ctx->pin_meta.ensure(total + 64));
-    uint8_t *hm = ctx->pin_meta.as<uint8_t>();
-    uint64_t *a = (uint64_t *)hm;
-    for (size_t i = 0; i < n; i++) { a[i] = mem[i].def_off; a[n + i] = mem[i].def_len; a[2 * n + i] = mem[i].out_off; a[3 * n + i] = mem[i].out_cap; }
-    uint8_t *dm = ctx->buf[NB_DEC_META].as<uint8_t>();
-    CK(cudaMemcpyAsync(dm, hm, in_total, cudaMemcpyHostToDevice, ctx->stream));
-    DecDev D;
-    D.in = d_in; D.in_off = (const uint64_t *)(dm + o_io); D.in_len = (const uint64_t *)(dm + o_il);
-    D.out = d_out; D.out_off = (const uint64_t *)(dm + o_oo); D.out_cap = (const uint64_t *)(dm + o_oc); D.n = (uint32_t)n;
-    D.status = (int32_t *)(dm + o_st); D.out_len = (uint64_t *)(dm + o_ol); D.consumed = (uint64_t *)(dm + o_cs);
+    std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_cap(n), out_end(n);
+    for (size_t i = 0; i < n; i++) { in_off[i] = mem[i].def_off; in_len[i] = mem[i].def_len; out_off[i] = mem[i].out_off; out_cap[i] = mem[i].out_cap; out_end[i] = mem[i].out_off + mem[i].out_cap; }
+    std::vector<uint32_t> big;
+    for (size_t i = 0; i < n; i++) if (in_len[i] >= kParallelMinBytes) big.push_back((uint32_t)i);
+    std::vector<uint32_t> serial;                          // member indices for the in-order kernel
+    std::vector<char> is_par(n, 0);
+    // ---- phase A: members + finder
+    Packer PA(ctx->pin_meta, ctx->buf[NB_DEC_META]);
+    const size_t a_io = PA.add(in_off.data(), n * 8), a_il = PA.add(in_len.data(), n * 8), a_oo = PA.add(out_off.data(), n * 8),
+                 a_oc = PA.add(out_cap.data(), n * 8), a_oe = PA.add(out_end.data(), n * 8);
+    std::vector<uint32_t> seg0(big.size() + 1, 0);
+    uint64_t big_bytes = 0;
+    for (size_t k = 0; k < big.size(); k++) { seg0[k + 1] = seg0[k] + (uint32_t)((in_len[big[k]] + 1023) / 1024); big_bytes += in_len[big[k]]; }
+    const size_t a_sel = PA.add(big.data(), big.size() * 4), a_seg = PA.add(seg0.data(), seg0.size() * 4);
+    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(1u << 22, big_bytes / 512 + 4096);
+    const size_t a_cm = PA.reserve((size_t)cand_cap * 4), a_cb = PA.reserve((size_t)cand_cap * 8), a_cc = PA.reserve(64);
+    CK(PA.commit(ctx->stream));
+    std::vector<uint32_t> c_member; std::vector<uint64_t> c_bit;
+    if (!big.empty()) {
+        FindDev F;
+        F.in = d_in; F.in_off = PA.ptr<uint64_t>(a_io); F.in_len = PA.ptr<uint64_t>(a_il);
+        F.members = PA.ptr<uint32_t>(a_sel); F.seg0 = PA.ptr<uint32_t>(a_seg); F.n_sel = (uint32_t)big.size(); F.n_segs = seg0.back();
+        F.cand_member = PA.ptr<uint32_t>(a_cm); F.cand_bit = PA.ptr<uint64_t>(a_cb); F.cand_count = PA.ptr<uint32_t>(a_cc); F.cand_cap = cand_cap;
+        CK(cudaMemsetAsync(F.cand_count, 0, 4, ctx->stream));
+        ctx->tm.mark(ctx->stream, "find_blocks");
+        CK(dec_launch_find(F, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        ctx->tm.mark(ctx->stream, "sync");
+        CK(ctx->pin_res.ensure(64));
+        uint32_t *h_cnt = ctx->pin_res.as<uint32_t>();
+        CK(cudaMemcpyAsync(h_cnt, F.cand_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint32_t nc = *h_cnt;
+        if (nc > cand_cap) { for (uint32_t m : big) serial.push_back(m); big.clear(); nc = 0; }    // absurd candidate count: do not trust
+        if (nc) {
+            CK(ctx->pin_cand.ensure((size_t)nc * 12 + 64));
+            uint8_t *hc = ctx->pin_cand.as<uint8_t>();
+            CK(cudaMemcpyAsync(hc, F.cand_member, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hc + align_up((size_t)nc * 4, 8), F.cand_bit, (size_t)nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            c_member.assign((uint32_t *)hc, (uint32_t *)hc + nc);
+            const uint64_t *hb = (const uint64_t *)(hc + align_up((size_t)nc * 4, 8));
+            c_bit.assign(hb, hb + nc);
+        }
+    }
+    // ---- phase B: probe all candidates (plus bit 0 of every big member)
+    std::vector<std::pair<uint32_t, uint64_t>> cands;      // (member, bit) sorted
+    for (size_t i = 0; i < c_member.size(); i++) cands.push_back({ c_member[i], c_bit[i] });
+    for (uint32_t m : big) cands.push_back({ m, 0 });
+    std::sort(cands.begin(), cands.end());
+    cands.erase(std::unique(cands.begin(), cands.end()), cands.end());
+    const size_t ncand = cands.size();
+    std::vector<int32_t> p_status; std::vector<uint64_t> p_end, p_len; std::vector<uint32_t> p_flags;
+    if (ncand) {
+        std::vector<uint32_t> bm(ncand); std::vector<uint64_t> bb(ncand), bs(ncand);
+        for (size_t i = 0; i < ncand; i++) {
+            bm[i] = cands[i].first; bb[i] = cands[i].second;
+            size_t j = i + 8;                               // a true block contains no true boundary; allow a few false positives inside
+            bs[i] = (j < ncand && cands[j].first == bm[i]) ? cands[j].second : ~0ull;
+        }
+        Packer PB(ctx->pin_cand, ctx->buf[NB_DEC_CAND]);
+        const size_t b_m = PB.add(bm.data(), ncand * 4), b_b = PB.add(bb.data(), ncand * 8), b_s = PB.add(bs.data(), ncand * 8);
+        const size_t b_st = PB.reserve(ncand * 4), b_en = PB.reserve(ncand * 8), b_ln = PB.reserve(ncand * 8), b_fl = PB.reserve(ncand * 4);
+        CK(PB.commit(ctx->stream));
+        BlockDev B; memset(&B, 0, sizeof B);
+        B.in = d_in; B.in_off = PA.ptr<uint64_t>(a_io); B.in_len = PA.ptr<uint64_t>(a_il); B.n_blocks = (uint32_t)ncand;
+        B.blk_member = PB.ptr<uint32_t>(b_m); B.blk_bit = PB.ptr<uint64_t>(b_b); B.blk_stop = PB.ptr<uint64_t>(b_s);
+        B.p_status = PB.ptr<int32_t>(b_st); B.p_end_bit = PB.ptr<uint64_t>(b_en); B.p_out_len = PB.ptr<uint64_t>(b_ln); B.p_flags = PB.ptr<uint32_t>(b_fl);
+        ctx->tm.mark(ctx->stream, "probe_blocks");
+        CK(dec_launch_probe(B, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        ctx->tm.mark(ctx->stream, "sync");
+        const size_t res_bytes = PB.off - b_st;
+        CK(ctx->pin_res.ensure(res_bytes + 64));
+        uint8_t *hr = ctx->pin_res.as<uint8_t>();
+        CK(cudaMemcpyAsync(hr, PB.ptr<uint8_t>(b_st), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        p_status.assign((int32_t *)hr, (int32_t *)hr + ncand);
+        p_end.assign((uint64_t *)(hr + (b_en - b_st)), (uint64_t *)(hr + (b_en - b_st)) + ncand);
+        p_len.assign((uint64_t *)(hr + (b_ln - b_st)), (uint64_t *)(hr + (b_ln - b_st)) + ncand);
+        p_flags.assign((uint32_t *)(hr + (b_fl - b_st)), (uint32_t *)(hr + (b_fl - b_st)) + ncand);
+    }
+    // ---- phase C: chain walk from bit 0 of every big member
+    std::vector<uint32_t> k_member; std::vector<uint64_t> k_bit, k_out, k_len;
+    for (uint32_t m : big) {
+        uint64_t pos = 0, out = 0; bool ok = true, fin = false;
+        const size_t first_blk = k_member.size();
+        while (!fin) {
+            auto it = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, pos));
+            if (it == cands.end() || it->first != m || it->second != pos) { ok = false; break; }
+            const size_t ci = (size_t)(it - cands.begin());
+            if (p_status[ci] != kInfOk || (p_flags[ci] & 2u)) { ok = false; break; }
+            k_member.push_back(m); k_bit.push_back(pos); k_out.push_back(out_off[m] + out); k_len.push_back(p_len[ci]);
+            out += p_len[ci]; pos = p_end[ci]; fin = (p_flags[ci] & 1u) != 0;
+        }
+        if (ok && out > out_cap[m]) ok = false;
+        if (!ok) { k_member.resize(first_blk); k_bit.resize(first_blk); k_out.resize(first_blk); k_len.resize(first_blk); serial.push_back(m); continue; }
+        is_par[m] = 1; st[m] = kInfOk; olen[m] = out; cons[m] = (pos + 7) >> 3;
+    }
+    for (size_t i = 0; i < n; i++) if (in_len[i] < kParallelMinBytes) serial.push_back((uint32_t)i);
+    // ---- pass 2 + in-order kernel
+    const size_t nblk = k_member.size(), nser = serial.size();
+    Packer PC(ctx->pin_blk, ctx->buf[NB_DEC_BLK]);
+    const size_t c_m = PC.add(k_member.data(), nblk * 4), c_b = PC.add(k_bit.data(), nblk * 8), c_o = PC.add(k_out.data(), nblk * 8);
+    const size_t c_st = PC.reserve(nblk * 4), c_ln = PC.reserve(nblk * 8);
+    std::vector<uint64_t> s_io(nser), s_il(nser), s_oo(nser), s_oc(nser);
+    for (size_t k = 0; k < nser; k++) { uint32_t m = serial[k]; s_io[k] = in_off[m]; s_il[k] = in_len[m]; s_oo[k] = out_off[m]; s_oc[k] = out_cap[m]; }
+    const size_t s_a = PC.add(s_io.data(), nser * 8), s_b = PC.add(s_il.data(), nser * 8), s_c = PC.add(s_oo.data(), nser * 8), s_d = PC.add(s_oc.data(), nser * 8);
+    const size_t s_st = PC.reserve(nser * 4), s_ol = PC.reserve(nser * 8), s_cs = PC.reserve(nser * 8);
+    CK(PC.commit(ctx->stream));
     ctx->tm.mark(ctx->stream, "inflate");
-    CK(dec_launch_serial(D, ctx->stream));
-    ctx->stats.kernel_launches += 1;
+    if (nblk) {
+        BlockDev B; memset(&B, 0, sizeof B);
+        B.in = d_in; B.in_off = PA.ptr<uint64_t>(a_io); B.in_len = PA.ptr<uint64_t>(a_il); B.n_blocks = (uint32_t)nblk;
+        B.blk_member = PC.ptr<uint32_t>(c_m); B.blk_bit = PC.ptr<uint64_t>(c_b); B.blk_out = PC.ptr<uint64_t>(c_o);
+        B.out = d_out; B.mem_out_off = PA.ptr<uint64_t>(a_oo); B.mem_out_end = PA.ptr<uint64_t>(a_oe);
+        B.d_status = PC.ptr<int32_t>(c_st); B.d_out_len = PC.ptr<uint64_t>(c_ln);
+        CK(dec_launch_blocks(B, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    if (nser) {
+        DecDev D;
+        D.in = d_in; D.in_off = PC.ptr<uint64_t>(s_a); D.in_len = PC.ptr<uint64_t>(s_b);
+        D.out = d_out; D.out_off = PC.ptr<uint64_t>(s_c); D.out_cap = PC.ptr<uint64_t>(s_d); D.n = (uint32_t)nser;
+        D.status = PC.ptr<int32_t>(s_st); D.out_len = PC.ptr<uint64_t>(s_ol); D.consumed = PC.ptr<uint64_t>(s_cs);
+        CK(dec_launch_serial(D, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
     ctx->tm.mark(ctx->stream, "results");
-    CK(ctx->pin_res.ensure(total + 64));
+    const size_t res_bytes = PC.off - c_st;
+    CK(ctx->pin_res.ensure(res_bytes + 64));
     uint8_t *hr = ctx->pin_res.as<uint8_t>();
-    CK(cudaMemcpyAsync(hr + o_st, dm + o_st, total - o_st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hr, PC.ptr<uint8_t>(c_st), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (size_t i = 0; i < n; i++) { st[i] = ((int32_t *)(hr + o_st))[i]; olen[i] = ((uint64_t *)(hr + o_ol))[i]; cons[i] = ((uint64_t *)(hr + o_cs))[i]; }
+    for (size_t k = 0; k < nblk; k++) {
+        const int32_t ds = ((int32_t *)hr)[k]; const uint64_t dl = ((uint64_t *)(hr + (c_ln - c_st)))[k];
+        if (ds != kInfOk || dl != k_len[k]) { ctx->err = "internal: block-parallel decode disagrees with its probe"; return B2F_ERR_CUDA; }
+    }
+    for (size_t k = 0; k < nser; k++) {
+        uint32_t m = serial[k];
+        st[m] = ((int32_t *)(hr + (s_st - c_st)))[k]; olen[m] = ((uint64_t *)(hr + (s_ol - c_st)))[k]; cons[m] = ((uint64_t *)(hr + (s_cs - c_st)))[k];
+    }
     return B2F_OK;
 }
 

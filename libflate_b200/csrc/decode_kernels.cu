@@ -1,57 +1,217 @@
 // decode_kernels.cu -- DEFLATE decode hot path (sm_100a).
-//   k_inflate_streams : one warp per stream, blocks in order.  Every lane runs the scalar decode of
-//                       inflate_core.cuh uniformly (broadcast loads, decode tables in shared memory);
-//                       LZ77 copies and stored-block copies are spread over the 32 lanes.
+//   k_find_blocks      every bit offset of a stream is tested for a plausible dynamic-block header
+//                      (CTA-local two-level compaction: 17-bit precheck -> code-length-code Kraft test -> full validation)
+//   k_probe_blocks     warp per candidate: Huffman-decodes ONE block without producing output -> end bit, size, flags
+//   k_inflate_blocks   warp per verified block: full decode, 64 KiB output window in shared memory, coalesced flushes
+//   k_inflate_streams  warp per stream, blocks in order (small streams, foreign streams with cross-block references,
+//                      streams with stored/fixed blocks, and every error path -- it reproduces the reference's error
+//                      kinds and partial output exactly)
+// Every lane of a warp runs the scalar decode of inflate_core.cuh uniformly (broadcast loads, shared-memory tables);
+// LZ77 copies and flushes are spread over the 32 lanes.
 // Reference behaviour: src/deflate/decode.rs:81-165, src/deflate/symbol.rs:193-243,387-484,
 // src/huffman.rs:96-179, libflate_lz77/src/lib.rs:164-194.
 #include "common.cuh"
 #include "inflate_core.cuh"
+#include "finder_core.cuh"
 #include "decode_dev.cuh"
 
 namespace b2f {
 
 struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 
-// Output policy: literals by lane 0, copies striped over the warp.  __syncwarp() orders the warp's earlier
-// global stores before the reads of a copy (CUDA guarantees memory ordering among the participating lanes).
-struct WarpOut {
-    uint8_t *o; uint64_t capacity; uint32_t lane;
+constexpr uint32_t kRingBytes = 65536, kRingMask = kRingBytes - 1;
+
+// Output policy: the last 64 KiB of output live in a shared-memory ring (index = absolute output offset mod 64 Ki);
+// back-references are served from it; every time the write position crosses a 32 KiB boundary the completed half is
+// flushed to HBM with coalesced 4-byte stores.
+struct WindowOut {
+    uint8_t *ring; uint8_t *g; uint64_t capacity; uint64_t flushed; uint32_t lane;
     __device__ __forceinline__ uint64_t cap() const { return capacity; }
-    __device__ __forceinline__ void lit(uint64_t pos, uint8_t b) { if (lane == 0) o[pos] = b; }
+    __device__ __forceinline__ void flush_to(uint64_t upto) {
+        if (upto > capacity) upto = capacity;
+        if (upto <= flushed) return;
+        __syncwarp();
+        const uint64_t a = flushed, b = upto;
+        if (((a | b) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 3) == 0) {
+            for (uint64_t i = a + 4ull * lane; i < b; i += 128) *reinterpret_cast<uint32_t *>(g + i) = *reinterpret_cast<const uint32_t *>(ring + (i & kRingMask));
+        } else {
+            for (uint64_t i = a + lane; i < b; i += 32) g[i] = ring[i & kRingMask];
+        }
+        flushed = upto;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void advance(uint64_t newpos) {
+        const uint64_t boundary = newpos & ~32767ull;
+        if (boundary > flushed) flush_to(boundary);
+    }
+    __device__ __forceinline__ void lit(uint64_t pos, uint8_t b) {
+        if (lane == 0) ring[pos & kRingMask] = b;
+        advance(pos + 1);
+    }
     __device__ __forceinline__ void copy(uint64_t pos, uint32_t len, uint32_t dist) {
         __syncwarp();
-        const uint8_t *src = o + pos - dist;
-        if (dist >= len) { for (uint32_t k = lane; k < len; k += 32) o[pos + k] = src[k]; }
-        else { for (uint32_t k = lane; k < len; k += 32) o[pos + k] = src[k % dist]; }
+        const uint64_t src = pos - dist;
+        if (dist >= len) { for (uint32_t k = lane; k < len; k += 32) ring[(pos + k) & kRingMask] = ring[(src + k) & kRingMask]; }
+        else { for (uint32_t k = lane; k < len; k += 32) ring[(pos + k) & kRingMask] = ring[(src + k % dist) & kRingMask]; }
+        advance(pos + len);
     }
-    __device__ __forceinline__ void raw(uint64_t pos, const uint8_t *src, uint64_t n) {
-        for (uint64_t k = lane; k < n; k += 32) o[pos + k] = src[k];
+    __device__ __forceinline__ void raw(uint64_t pos, const uint8_t *src, uint64_t n) {   // stored block: straight to HBM (+ ring for later matches)
+        flush_to(pos);
+        __syncwarp();
+        for (uint64_t k = lane; k < n; k += 32) g[pos + k] = src[k];
+        const uint64_t keep = n > kRingBytes ? kRingBytes : n;
+        for (uint64_t k = n - keep + lane; k < n; k += 32) ring[(pos + k) & kRingMask] = src[k];
+        if (pos + n > flushed) flushed = pos + n;
+        __syncwarp();
     }
+    __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
 };
 
-constexpr uint32_t kInfWarps = 4;
+// pass 1: no output, only sizes; notes back-references that reach before the block's own start
+struct CountOut {
+    uint32_t far;
+    __device__ __forceinline__ uint64_t cap() const { return ~0ull; }
+    __device__ __forceinline__ void lit(uint64_t, uint8_t) {}
+    __device__ __forceinline__ void copy(uint64_t pos, uint32_t, uint32_t dist) { if (dist > pos) far = 1; }
+    __device__ __forceinline__ void raw(uint64_t, const uint8_t *, uint64_t) {}
+    __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
+};
 
-__global__ void __launch_bounds__(kInfWarps * 32) k_inflate_streams(DecDev D) {
+constexpr uint32_t kWinSmem = kRingBytes + (uint32_t)sizeof(InflateTables) + 64;
+
+// ---------------------------------------------------------------------------------- in-order, warp per stream
+__global__ void __launch_bounds__(32) k_inflate_streams(DecDev D) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *ring = smem_raw;
+    InflateTables &T = *reinterpret_cast<InflateTables *>(smem_raw + kRingBytes);
+    const uint32_t lane = threadIdx.x, s = blockIdx.x;
+    if (s >= D.n) return;
+    BitIn b;
+    bi_init(b, D.in + D.in_off[s], D.in_len[s], 0);
+    const uint64_t o0 = D.out_off[s];
+    WindowOut out = { ring, D.out, o0 + D.out_cap[s], o0, lane };
+    InflateResult R;
+    inflate_blocks(b, T, out, o0, 0ull - o0, 0xFFFFFFFFu, (int)lane, 32, WarpSync(), R);
+    out.flush_to(R.out_len);
+    if (lane == 0) { D.status[s] = R.status; D.out_len[s] = R.out_len - o0; D.consumed[s] = R.consumed; }
+}
+
+// ---------------------------------------------------------------------------------- block-boundary finder
+constexpr uint32_t kFindBytes = 1024;       // input bytes (8192 bit offsets) per CTA
+__device__ __forceinline__ uint64_t smem_bits64(const uint32_t *w, uint32_t bit) {
+    const uint32_t byte = bit >> 3, idx = byte >> 2, sh = (byte & 3u) * 8u + (bit & 7u);
+    const uint32_t x0 = w[idx], x1 = w[idx + 1], x2 = w[idx + 2];
+    return (uint64_t)__funnelshift_r(x0, x1, sh) | ((uint64_t)__funnelshift_r(x1, x2, sh) << 32);
+}
+__device__ __forceinline__ uint32_t find_owner_u32(const uint32_t *__restrict__ prefix, uint32_t n, uint32_t idx) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= idx) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256) k_find_blocks(FindDev F) {
+    __shared__ __align__(16) uint32_t sw[(kFindBytes + 64) / 4];
+    __shared__ uint16_t qa[kFindBytes * 8], qb[kFindBytes * 8];
+    __shared__ uint32_t na, nb;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t sel = find_owner_u32(F.seg0, F.n_sel, blockIdx.x);
+    const uint32_t m = F.members[sel];
+    const uint64_t len = F.in_len[m];
+    const uint8_t *__restrict__ p = F.in + F.in_off[m];
+    const uint64_t b0 = (uint64_t)(blockIdx.x - F.seg0[sel]) * kFindBytes;
+    if (tid == 0) { na = 0; nb = 0; }
+    for (uint32_t i = tid; i < (kFindBytes + 64) / 4; i += 256) {
+        uint32_t v = 0;
+        const uint64_t byte = b0 + 4ull * i;
+        for (uint32_t k = 0; k < 4; k++) if (byte + k < len) v |= (uint32_t)p[byte + k] << (8 * k);
+        sw[i] = v;
+    }
+    __syncthreads();
+    const uint64_t limit = len * 8;
+    for (uint32_t k = 0; k < 32; k++) {
+        const uint32_t o = k * 256 + tid;
+        const uint64_t q = b0 * 8 + o;
+        if (q + 17 > limit) continue;
+        if (hdr_precheck((uint32_t)smem_bits64(sw, o))) qa[atomicAdd(&na, 1u)] = (uint16_t)o;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < na; i += 256) {
+        const uint32_t o = qa[i];
+        if (precode_check(smem_bits64(sw, o), smem_bits64(sw, o + 64))) qb[atomicAdd(&nb, 1u)] = (uint16_t)o;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < nb; i += 256) {
+        const uint64_t q = b0 * 8 + qb[i];
+        if (validate_dynamic_header(p, len, q)) {
+            const uint32_t slot = atomicAdd(F.cand_count, 1u);
+            if (slot < F.cand_cap) { F.cand_member[slot] = m; F.cand_bit[slot] = q; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- pass 1: probe
+constexpr uint32_t kProbeWarps = 4;
+__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_blocks(BlockDev B) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateTables *tabs = reinterpret_cast<InflateTables *>(smem_raw);
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t s = blockIdx.x * kInfWarps + wid;
-    if (s >= D.n) return;
-    InflateTables &T = tabs[wid];
+    const uint32_t i = blockIdx.x * kProbeWarps + wid;
+    if (i >= B.n_blocks) return;
+    const uint32_t m = B.blk_member[i];
     BitIn b;
-    bi_init(b, D.in + D.in_off[s], D.in_len[s], 0);
-    WarpOut out = { D.out + D.out_off[s], D.out_cap[s], lane };
+    bi_init(b, B.in + B.in_off[m], B.in_len[m], B.blk_bit[i]);
+    b.stop = B.blk_stop[i];
+    CountOut out = { 0 };
     InflateResult R;
-    inflate_blocks(b, T, out, 0, 0, 0xFFFFFFFFu, (int)lane, 32, WarpSync(), R);
-    if (lane == 0) { D.status[s] = R.status; D.out_len[s] = R.out_len; D.consumed[s] = R.consumed; }
+    inflate_blocks(b, tabs[wid], out, 0, 1ull << 60, 1, (int)lane, 32, WarpSync(), R);
+    if (lane == 0) {
+        B.p_status[i] = R.status; B.p_end_bit[i] = R.end_bit; B.p_out_len[i] = R.out_len;
+        B.p_flags[i] = (R.final_seen ? 1u : 0u) | (out.far ? 2u : 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------------- pass 2: block-parallel decode
+__global__ void __launch_bounds__(32) k_inflate_blocks(BlockDev B) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *ring = smem_raw;
+    InflateTables &T = *reinterpret_cast<InflateTables *>(smem_raw + kRingBytes);
+    const uint32_t lane = threadIdx.x, i = blockIdx.x;
+    if (i >= B.n_blocks) return;
+    const uint32_t m = B.blk_member[i];
+    BitIn b;
+    bi_init(b, B.in + B.in_off[m], B.in_len[m], B.blk_bit[i]);
+    const uint64_t o0 = B.blk_out[i];
+    WindowOut out = { ring, B.out, B.mem_out_end[m], o0, lane };
+    InflateResult R;
+    inflate_blocks(b, T, out, o0, 0ull - B.mem_out_off[m], 1, (int)lane, 32, WarpSync(), R);
+    out.flush_to(R.out_len);
+    if (lane == 0) { B.d_status[i] = R.status; B.d_out_len[i] = R.out_len - o0; }
 }
 
 cudaError_t dec_init_attributes() {
-    return cudaFuncSetAttribute(k_inflate_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInfWarps * sizeof(InflateTables)));
+    cudaError_t e = cudaFuncSetAttribute(k_inflate_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_inflate_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_probe_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kProbeWarps * sizeof(InflateTables)));
 }
 cudaError_t dec_launch_serial(const DecDev &D, cudaStream_t st) {
     if (D.n == 0) return cudaSuccess;
-    k_inflate_streams<<<(D.n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, kInfWarps * sizeof(InflateTables), st>>>(D);
+    k_inflate_streams<<<D.n, 32, kWinSmem, st>>>(D);
+    return cudaGetLastError();
+}
+cudaError_t dec_launch_find(const FindDev &F, cudaStream_t st) {
+    if (F.n_segs == 0) return cudaSuccess;
+    k_find_blocks<<<F.n_segs, 256, 0, st>>>(F);
+    return cudaGetLastError();
+}
+cudaError_t dec_launch_probe(const BlockDev &B, cudaStream_t st) {
+    if (B.n_blocks == 0) return cudaSuccess;
+    k_probe_blocks<<<(B.n_blocks + kProbeWarps - 1) / kProbeWarps, kProbeWarps * 32, kProbeWarps * sizeof(InflateTables), st>>>(B);
+    return cudaGetLastError();
+}
+cudaError_t dec_launch_blocks(const BlockDev &B, cudaStream_t st) {
+    if (B.n_blocks == 0) return cudaSuccess;
+    k_inflate_blocks<<<B.n_blocks, 32, kWinSmem, st>>>(B);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,93 @@
+// finder_core.cuh -- "is there a plausible dynamic-Huffman block header at this bit offset?"
+// Used by the block-boundary finder that makes index-less streams decodable block-parallel
+// (the reference decodes strictly in order: src/deflate/decode.rs:136-164).  A hit is only a CANDIDATE:
+// the decoder trusts it only when the chain of block ends starting from bit 0 lands exactly on it.
+// Checks are necessary conditions that every header written by libflate's (and zlib's) encoder satisfies:
+//   BTYPE == 10, HLIT <= 29, HDIST <= 29                                  (src/deflate/symbol.rs:343-365)
+//   code-length code complete (or a single 1-bit code)                     (huffman.rs:202-209 always yields that)
+//   lit/len + distance widths decode to exactly HLIT+HDIST entries, EOB has a code,
+//   lit/len code complete (or single symbol), distance code complete (or <= 1 symbol)
+#pragma once
+#include "common.cuh"
+
+namespace b2f {
+
+B2F_HD bool hdr_precheck(uint32_t w) {            // w = 32 stream bits starting at the candidate (LSB first)
+    return ((w >> 1) & 3u) == 2u && ((w >> 3) & 31u) <= 29u && ((w >> 8) & 31u) <= 29u;
+}
+
+// w0 = bits [0,64), w1 = bits [64,128) from the candidate
+B2F_HD bool precode_check(uint64_t w0, uint64_t w1) {
+    const uint32_t hclen = (uint32_t)((w0 >> 13) & 15u) + 4u;
+    uint32_t kraft = 0, nz = 0;
+    for (uint32_t i = 0; i < hclen; i++) {
+        const uint32_t pos = 17 + 3 * i;
+        uint64_t v;
+        if (pos >= 64) v = w1 >> (pos - 64);
+        else { v = w0 >> pos; if (pos > 61) v |= w1 << (64 - pos); }
+        const uint32_t len = (uint32_t)v & 7u;
+        if (len) { kraft += 128u >> len; nz++; }
+    }
+    return kraft == 128u || (nz == 1 && kraft == 64u);
+}
+
+B2F_HD uint32_t get_bits_slow(const uint8_t *p, uint64_t nbytes, uint64_t bitpos, uint32_t n) {   // n <= 24
+    uint64_t byte = bitpos >> 3; uint32_t sh = (uint32_t)(bitpos & 7), v = 0;
+    for (uint32_t k = 0; k < 4; k++) if (byte + k < nbytes) v |= (uint32_t)p[byte + k] << (8 * k);
+    return (v >> sh) & ((1u << n) - 1u);
+}
+
+// Full header validation (rare path).  Returns true when every check passes.
+B2F_HD bool validate_dynamic_header(const uint8_t *p, uint64_t nbytes, uint64_t bitpos) {
+    const uint8_t ORDER[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+    const uint64_t limit = nbytes * 8;
+    if (bitpos + 17 > limit) return false;
+    uint64_t q = bitpos + 3;
+    const uint32_t hlit = get_bits_slow(p, nbytes, q, 5) + 257; q += 5;
+    const uint32_t hdist = get_bits_slow(p, nbytes, q, 5) + 1; q += 5;
+    const uint32_t hclen = get_bits_slow(p, nbytes, q, 4) + 4; q += 4;
+    if (hlit > 286 || hdist > 30) return false;
+    uint8_t pw[19];
+    for (int i = 0; i < 19; i++) pw[i] = 0;
+    if (q + 3 * hclen > limit) return false;
+    for (uint32_t k = 0; k < hclen; k++) { pw[ORDER[k]] = (uint8_t)get_bits_slow(p, nbytes, q, 3); q += 3; }
+    uint32_t cnt[8], first[8], off[8]; uint8_t sorted[19];
+    for (int i = 0; i < 8; i++) cnt[i] = 0;
+    for (int i = 0; i < 19; i++) cnt[pw[i]]++;
+    cnt[0] = 0;
+    uint32_t code = 0, o = 0; first[0] = 0; off[0] = 0;
+    for (uint32_t l = 1; l < 8; l++) { code = (code + cnt[l - 1]) << 1; first[l] = code; off[l] = o; o += cnt[l]; if (code + cnt[l] > (1u << l)) return false; }
+    { uint32_t nxt[8]; for (int l = 0; l < 8; l++) nxt[l] = off[l]; for (uint32_t s = 0; s < 19; s++) if (pw[s]) sorted[nxt[pw[s]]++] = (uint8_t)s; }
+    uint32_t total = 0, want = hlit + hdist, prev = 0;
+    uint32_t lit_kraft = 0, dist_kraft = 0, nlit = 0, ndist = 0, eob_len = 0;
+    while (total < want) {
+        if (q + 7 > limit + 7 || q >= limit) return false;
+        const uint32_t peek = get_bits_slow(p, nbytes, q, 7);
+        uint32_t sym = 0xFFu, used = 0, acc = 0;
+        for (uint32_t l = 1; l < 8; l++) {
+            acc = (acc << 1) | ((peek >> (l - 1)) & 1u);            // MSB-first code value of the first l bits
+            if (cnt[l] && acc >= first[l] && acc - first[l] < cnt[l]) { sym = sorted[off[l] + acc - first[l]]; used = l; break; }
+        }
+        if (sym == 0xFFu) return false;
+        q += used;
+        uint32_t rep = 1, val = sym;
+        if (sym == 16) { if (total == 0) return false; rep = get_bits_slow(p, nbytes, q, 2) + 3; q += 2; val = prev; }
+        else if (sym == 17) { rep = get_bits_slow(p, nbytes, q, 3) + 3; q += 3; val = 0; }
+        else if (sym == 18) { rep = get_bits_slow(p, nbytes, q, 7) + 11; q += 7; val = 0; }
+        if (q > limit || total + rep > want) return false;
+        for (uint32_t k = 0; k < rep; k++) {
+            const uint32_t idx = total + k;
+            if (val) {
+                if (idx < hlit) { lit_kraft += 32768u >> val; nlit++; if (idx == 256) eob_len = val; }
+                else { dist_kraft += 32768u >> val; ndist++; }
+            }
+        }
+        total += rep; prev = val;
+    }
+    if (!eob_len) return false;
+    if (!(lit_kraft == 32768u || (nlit == 1 && lit_kraft == 16384u))) return false;
+    if (!(dist_kraft == 32768u || (ndist <= 1 && dist_kraft <= 16384u))) return false;
+    return true;
+}
+
+}  // namespace b2f

@@ -21,6 +21,7 @@ constexpr int kInfOk = 0;
 constexpr int kInfInvalid = -1;        // io::ErrorKind::InvalidData
 constexpr int kInfEof = -2;            // io::ErrorKind::UnexpectedEof
 constexpr int kInfOutFull = -3;
+constexpr int kInfAbort = -4;           // probe ran past its stop bit (block-parallel candidate validation only)
 
 constexpr uint32_t kLitBits = 11, kDistBits = 9;
 
@@ -75,6 +76,7 @@ struct BitIn {
     uint64_t limit;          // 8 * byte length
     uint64_t pos;            // bit position
     uint64_t bb; uint32_t bc; uint64_t next;   // bit buffer: bc valid bits, `next` = byte offset of the next 4-byte load
+    uint64_t stop;           // probes give up when pos passes this bit (~0 = never)
     int err;                 // pending error (last_error), 0 = none
     bool eof;                // a refill has failed
 };
@@ -95,7 +97,7 @@ B2F_HD void bi_seek(BitIn &b, uint64_t bitpos) {
     b.bb = (uint64_t)w >> drop; b.bc = 32 - drop; b.next += 4;
 }
 B2F_HD void bi_init(BitIn &b, const uint8_t *p, uint64_t nbytes, uint64_t bitpos) {
-    b.p = p; b.limit = nbytes * 8; b.err = 0; b.eof = false;
+    b.p = p; b.limit = nbytes * 8; b.err = 0; b.eof = false; b.stop = ~0ull;
     bi_seek(b, bitpos);
 }
 B2F_HD void bi_refill(BitIn &b) {            // keep >= 32 valid bits
@@ -323,7 +325,7 @@ struct InflateResult {
 
 // Decode blocks starting at b.pos until BFINAL (max_blocks limits the count: block-parallel callers pass 1).
 // `hist_base`: number of bytes of history that precede out position 0 (for the "Too long backword reference" check).
-// Out policy: lit(pos, byte), copy(pos, len, dist), raw(pos, src, n), cap().
+// Out policy: lit(pos, byte), copy(pos, len, dist), raw(pos, src, n), cap(), block_end(start_bit, end_bit, out_pos, final).
 template <class Out, class Sync>
 B2F_HD void inflate_blocks(BitIn &b, InflateTables &T, Out &out, uint64_t out_pos, uint64_t hist_base, uint32_t max_blocks,
                            int lane, int nl, Sync SYNC, InflateResult &R) {
@@ -332,6 +334,7 @@ B2F_HD void inflate_blocks(BitIn &b, InflateTables &T, Out &out, uint64_t out_po
     const uint64_t cap = out.cap();
     for (uint32_t nb = 0; nb < max_blocks; nb++) {
         int rc;
+        const uint64_t blk_start = b.pos;
         uint32_t bfinal = bi_read(b, 1); if ((rc = bi_check(b))) { R.status = rc; break; }
         uint32_t btype = bi_read(b, 2); if ((rc = bi_check(b))) { R.status = rc; break; }
         if (btype == 0) {                                        // read_non_compressed_block (decode.rs:81-111)
@@ -368,6 +371,7 @@ B2F_HD void inflate_blocks(BitIn &b, InflateTables &T, Out &out, uint64_t out_po
                     distance = ((d >> 8) & 0xFFFF) + bi_read(b, deb);
                 }
                 if ((rc = bi_check(b))) { R.status = rc; break; }
+                if (b.pos > b.stop) { R.status = kInfAbort; break; }
                 if (kind == kKindEob) break;
                 if (kind == kKindLit) {
                     if (out_pos < cap) out.lit(out_pos, (uint8_t)(e >> 8)); else R.status = kInfOutFull;
@@ -385,6 +389,7 @@ B2F_HD void inflate_blocks(BitIn &b, InflateTables &T, Out &out, uint64_t out_po
             if (R.status && R.status != kInfOutFull) break;
         }
         uint64_t pb = (b.pos + 7) >> 3; if (pb > pulled) pulled = pb;
+        out.block_end(blk_start, b.pos, out_pos, bfinal != 0);
         if (bfinal) { R.final_seen = 1; break; }
     }
     uint64_t pb = (b.pos + 7) >> 3; if (pb > (b.limit >> 3)) pb = b.limit >> 3;

@@ -67,3 +67,24 @@ def inflate(data, cap=None):
     lib().hc_inflate(buf, C.c_uint64(len(data)), out, C.c_uint64(cap), res)
     n = min(res[1], cap)
     return res[0], out.raw[:n], res[2], res[3]
+
+
+def block_starts(data, cap=None):
+    data = bytes(data)
+    if cap is None:
+        cap = max(1 << 16, len(data) * 1100 + 1024)
+    scratch = C.create_string_buffer(cap + 64)
+    starts = (C.c_uint64 * 8192)()
+    buf = C.create_string_buffer(data, len(data) + 64)
+    lib().hc_block_starts.restype = C.c_uint32
+    n = lib().hc_block_starts(buf, C.c_uint64(len(data)), scratch, C.c_uint64(cap), starts, 8192)
+    return list(starts[: min(n, 8192)])
+
+
+def find_candidates(data):
+    data = bytes(data)
+    cands = (C.c_uint64 * 65536)()
+    buf = C.create_string_buffer(data, len(data) + 64)
+    lib().hc_find_candidates.restype = C.c_uint32
+    n = lib().hc_find_candidates(buf, C.c_uint64(len(data)), cands, 65536)
+    return n, list(cands[: min(n, 65536)])

@@ -65,6 +65,7 @@ struct WindowOut {
         __syncwarp();
     }
     __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
+    __device__ __forceinline__ int fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base);
 };
 
 // pass 1: no output, only sizes; notes back-references that reach before the block's own start
@@ -75,7 +76,62 @@ struct CountOut {
     __device__ __forceinline__ void copy(uint64_t pos, uint32_t, uint32_t dist) { if (dist > pos) far = 1; }
     __device__ __forceinline__ void raw(uint64_t, const uint8_t *, uint64_t) {}
     __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
+    __device__ __forceinline__ int fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base);
 };
+
+
+// ---------------------------------------------------------------------------------- fast symbol loop (device only)
+// Register-resident bit buffer with a prefetched input word; handles literals, EndOfBlock and matches whose codes hit the
+// primary tables.  Anything else (long codes, invalid patterns, end of input/output, too-long references, the probe's stop
+// bit) leaves the reader untouched at the symbol boundary and returns 0, so that the exact generic path decides.
+template <class Out>
+__device__ __forceinline__ int fast_symbols(BitIn &b, const InflateTables &T, Out &out, uint64_t &out_pos, uint64_t hist_base) {
+    const uint64_t nbytes = b.limit >> 3;
+    if (b.eof || b.err) return 0;
+    const uint8_t *__restrict__ p = b.p;
+    uint64_t next = b.next;
+    if ((reinterpret_cast<uintptr_t>(p + next) & 3) != 0 || next + 12 > nbytes) return 0;
+    uint64_t bb = b.bb; uint32_t bc = b.bc; uint64_t pos = b.pos;
+    uint32_t nw = *reinterpret_cast<const uint32_t *>(p + next);
+    const uint64_t cap = out.cap();
+    uint64_t op = out_pos;
+    int ret = 0;
+    for (;;) {
+        if (next + 12 > nbytes || op + 258 > cap || pos > b.stop) break;
+        if (bc < 32) { bb |= (uint64_t)nw << bc; bc += 32; next += 4; nw = *reinterpret_cast<const uint32_t *>(p + next); }
+        const uint32_t e = T.lit[(uint32_t)bb & ((1u << kLitBits) - 1u)];
+        const uint32_t w = e & 15u, kind = (e >> 4) & 3u;
+        if (kind == kKindLit) {
+            bb >>= w; bc -= w; pos += w;
+            out.lit(op, (uint8_t)(e >> 8)); op += 1;
+            continue;
+        }
+        if (kind == kKindLen) {
+            const uint32_t eb = (e >> 20) & 15u;
+            const uint32_t len = ((e >> 8) & 0x1FFu) + (((uint32_t)(bb >> w)) & ((1u << eb) - 1u));
+            const uint32_t used = w + eb;
+            uint64_t bb2 = bb >> used; uint32_t bc2 = bc - used; uint64_t next2 = next; uint32_t nw2 = nw;
+            if (bc2 < 32) { bb2 |= (uint64_t)nw2 << bc2; bc2 += 32; next2 += 4; nw2 = *reinterpret_cast<const uint32_t *>(p + next2); }
+            const uint32_t d = T.dist[(uint32_t)bb2 & ((1u << kDistBits) - 1u)];
+            const uint32_t wd = d & 15u;
+            if (wd == 0) break;                                   // long or unassigned distance code
+            const uint32_t deb = (d >> 24) & 15u;
+            const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(bb2 >> wd)) & ((1u << deb) - 1u));
+            if ((uint64_t)dist > op + hist_base) break;          // "Too long backword reference": reported by the generic path
+            const uint32_t used2 = wd + deb;
+            bb = bb2 >> used2; bc = bc2 - used2; next = next2; nw = nw2; pos += used + used2;
+            out.copy(op, len, dist); op += len;
+            continue;
+        }
+        if (kind == kKindEob) { bb >>= w; bc -= w; pos += w; ret = 1; }
+        break;
+    }
+    b.bb = bb; b.bc = bc; b.next = next; b.pos = pos; out_pos = op;
+    return ret;
+}
+
+__device__ __forceinline__ int WindowOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { return fast_symbols(b, T, *this, out_pos, hist_base); }
+__device__ __forceinline__ int CountOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { return fast_symbols(b, T, *this, out_pos, hist_base); }
 
 constexpr uint32_t kWinSmem = kRingBytes + (uint32_t)sizeof(InflateTables) + 64;
 
@@ -127,11 +183,22 @@ __global__ void __launch_bounds__(256) k_find_blocks(FindDev F) {
     }
     __syncthreads();
     const uint64_t limit = len * 8;
-    for (uint32_t k = 0; k < 32; k++) {
-        const uint32_t o = k * 256 + tid;
-        const uint64_t q = b0 * 8 + o;
-        if (q + 17 > limit) continue;
-        if (hdr_precheck((uint32_t)smem_bits64(sw, o))) qa[atomicAdd(&na, 1u)] = (uint16_t)o;
+    const uint32_t lane = tid & 31;
+    {   // step A: thread t tests the 32 bit offsets of word t with one sliding 64-bit window
+        const uint64_t win = smem_bits64(sw, tid * 32);
+        uint32_t pass = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) if (hdr_precheck((uint32_t)(win >> j))) pass |= 1u << j;
+        const uint64_t q0 = b0 * 8 + tid * 32;
+        if (q0 + 32 + 17 > limit) {                 // tail of the stream: drop offsets whose 17 header bits do not fit
+            for (uint32_t j = 0; j < 32; j++) if (q0 + j + 17 > limit) pass &= ~(1u << j);
+        }
+        uint32_t cnt = __popc(pass), incl = cnt;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(&na, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+        while (pass) { const uint32_t j = __ffs((int)pass) - 1; pass &= pass - 1; qa[base++] = (uint16_t)(tid * 32 + j); }
     }
     __syncthreads();
     for (uint32_t i = tid; i < na; i += 256) {

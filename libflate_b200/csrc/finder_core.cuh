@@ -19,14 +19,16 @@ B2F_HD bool hdr_precheck(uint32_t w) {            // w = 32 stream bits starting
 // w0 = bits [0,64), w1 = bits [64,128) from the candidate
 B2F_HD bool precode_check(uint64_t w0, uint64_t w1) {
     const uint32_t hclen = (uint32_t)((w0 >> 13) & 15u) + 4u;
+    // the 19 three-bit fields start at bit 17: fields 0..9 -> f0 (30 bits), fields 10..18 -> f1 (27 bits)
+    const uint32_t f0 = (uint32_t)(w0 >> 17) & 0x3FFFFFFFu;
+    const uint32_t f1 = (uint32_t)((w0 >> 47) | (w1 << 17)) & 0x7FFFFFFu;
     uint32_t kraft = 0, nz = 0;
-    for (uint32_t i = 0; i < hclen; i++) {
-        const uint32_t pos = 17 + 3 * i;
-        uint64_t v;
-        if (pos >= 64) v = w1 >> (pos - 64);
-        else { v = w0 >> pos; if (pos > 61) v |= w1 << (64 - pos); }
-        const uint32_t len = (uint32_t)v & 7u;
-        if (len) { kraft += 128u >> len; nz++; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t i = 0; i < 19; i++) {
+        const uint32_t len = i < 10 ? (f0 >> (3 * i)) & 7u : (f1 >> (3 * (i - 10))) & 7u;
+        if (i < hclen && len) { kraft += 128u >> len; nz++; }
     }
     return kraft == 128u || (nz == 1 && kraft == 64u);
 }

@@ -325,7 +325,9 @@ struct InflateResult {
 
 // Decode blocks starting at b.pos until BFINAL (max_blocks limits the count: block-parallel callers pass 1).
 // `hist_base`: number of bytes of history that precede out position 0 (for the "Too long backword reference" check).
-// Out policy: lit(pos, byte), copy(pos, len, dist), raw(pos, src, n), cap(), block_end(start_bit, end_bit, out_pos, final).
+// Out policy: lit(pos, byte), copy(pos, len, dist), raw(pos, src, n), cap(), block_end(start_bit, end_bit, out_pos, final),
+// fast(b, T, out_pos, hist_base): optional accelerated symbol loop (returns 1 when it consumed EndOfBlock, else 0 and
+// leaves the reader at a symbol boundary for the exact generic path).
 template <class Out, class Sync>
 B2F_HD void inflate_blocks(BitIn &b, InflateTables &T, Out &out, uint64_t out_pos, uint64_t hist_base, uint32_t max_blocks,
                            int lane, int nl, Sync SYNC, InflateResult &R) {
@@ -357,6 +359,7 @@ B2F_HD void inflate_blocks(BitIn &b, InflateTables &T, Out &out, uint64_t out_po
             rc = btype == 1 ? load_fixed(T, lane, nl, SYNC) : load_dynamic(b, T, lane, nl, SYNC);
             if (rc) { R.status = rc; break; }
             for (;;) {                                           // read_compressed_block loop (decode.rs:117-128)
+                if (out.fast(b, T, out_pos, hist_base)) break;   // device fast path: returns 1 after consuming EndOfBlock
                 uint32_t e = decode_code(b, T, true);
                 uint32_t kind = (e >> 4) & 3;
                 uint32_t length = 0, distance = 0;

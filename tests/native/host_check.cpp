@@ -37,6 +37,7 @@ struct HostOut {
     void lit(uint64_t pos, uint8_t b) { o[pos] = b; }
     void copy(uint64_t pos, uint32_t len, uint32_t dist) { for (uint32_t k = 0; k < len; k++) o[pos + k] = o[pos + k - dist]; }
     void raw(uint64_t pos, const uint8_t *src, uint64_t n) { memcpy(o + pos, src, n); }
+    int fast(BitIn &, const InflateTables &, uint64_t &, uint64_t) { return 0; }
     void block_end(uint64_t s, uint64_t e, uint64_t, bool) { if (nblk < 4096) { bstart[nblk] = s; bend[nblk] = e; } nblk++; }
     uint64_t bstart[4096], bend[4096]; uint32_t nblk = 0;
 };

@@ -772,6 +772,8 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     const size_t a_sel = PA.add(big.data(), big.size() * 4), a_seg = PA.add(seg0.data(), seg0.size() * 4);
     const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(1u << 22, big_bytes / 512 + 4096);
     const size_t a_cm = PA.reserve((size_t)cand_cap * 4), a_cb = PA.reserve((size_t)cand_cap * 8), a_cc = PA.reserve(64);
+    const uint32_t q_cap = (uint32_t)std::min<uint64_t>(1u << 24, big_bytes / 32 + 8192);      // ~0.1 % of bit offsets pass the cheap tests
+    const size_t a_qm = PA.reserve((size_t)q_cap * 4), a_qb = PA.reserve((size_t)q_cap * 8);
     CK(PA.commit(ctx->stream));
     std::vector<uint32_t> c_member; std::vector<uint64_t> c_bit;
     if (!big.empty()) {
@@ -779,17 +781,18 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
         F.in = d_in; F.in_off = PA.ptr<uint64_t>(a_io); F.in_len = PA.ptr<uint64_t>(a_il);
         F.members = PA.ptr<uint32_t>(a_sel); F.seg0 = PA.ptr<uint32_t>(a_seg); F.n_sel = (uint32_t)big.size(); F.n_segs = seg0.back();
         F.cand_member = PA.ptr<uint32_t>(a_cm); F.cand_bit = PA.ptr<uint64_t>(a_cb); F.cand_count = PA.ptr<uint32_t>(a_cc); F.cand_cap = cand_cap;
-        CK(cudaMemsetAsync(F.cand_count, 0, 4, ctx->stream));
+        F.q_member = PA.ptr<uint32_t>(a_qm); F.q_bit = PA.ptr<uint64_t>(a_qb); F.q_count = PA.ptr<uint32_t>(a_cc) + 1; F.q_cap = q_cap;
+        CK(cudaMemsetAsync(F.cand_count, 0, 8, ctx->stream));
         ctx->tm.mark(ctx->stream, "find_blocks");
         CK(dec_launch_find(F, ctx->stream));
-        ctx->stats.kernel_launches += 1;
+        ctx->stats.kernel_launches += 2;
         ctx->tm.mark(ctx->stream, "sync");
         CK(ctx->pin_res.ensure(64));
         uint32_t *h_cnt = ctx->pin_res.as<uint32_t>();
-        CK(cudaMemcpyAsync(h_cnt, F.cand_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_cnt, F.cand_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        uint32_t nc = *h_cnt;
-        if (nc > cand_cap) { for (uint32_t m : big) serial.push_back(m); big.clear(); nc = 0; }    // absurd candidate count: do not trust
+        uint32_t nc = h_cnt[0];
+        if (nc > cand_cap || h_cnt[1] > q_cap) { for (uint32_t m : big) serial.push_back(m); big.clear(); nc = 0; }    // absurd candidate count: do not trust
         if (nc) {
             CK(ctx->pin_cand.ensure((size_t)nc * 12 + 64));
             uint8_t *hc = ctx->pin_cand.as<uint8_t>();

@@ -23,7 +23,8 @@ struct FindDev {
     const uint32_t *members;             // [n_sel] member indices to scan
     const uint32_t *seg0;                // [n_sel + 1] prefix of 1 KiB scan segments
     uint32_t n_sel, n_segs;
-    uint32_t *cand_member; uint64_t *cand_bit; uint32_t *cand_count; uint32_t cand_cap;
+    uint32_t *q_member; uint64_t *q_bit; uint32_t *q_count; uint32_t q_cap;            // offsets that passed the cheap tests
+    uint32_t *cand_member; uint64_t *cand_bit; uint32_t *cand_count; uint32_t cand_cap;   // fully validated candidates
 };
 // candidate probe (pass 1) and block decode (pass 2)
 struct BlockDev {

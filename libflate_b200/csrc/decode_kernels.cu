@@ -143,13 +143,15 @@ __global__ void __launch_bounds__(32) k_inflate_streams(DecDev D) {
     const uint32_t lane = threadIdx.x, s = blockIdx.x;
     if (s >= D.n) return;
     BitIn b;
-    bi_init(b, D.in + D.in_off[s], D.in_len[s], 0);
+    const uint8_t *p0 = D.in + D.in_off[s];
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);       // start the reader on an aligned word (the lead bytes are never consumed)
+    bi_init(b, p0 - lead, D.in_len[s] + lead, 8ull * lead);
     const uint64_t o0 = D.out_off[s];
     WindowOut out = { ring, D.out, o0 + D.out_cap[s], o0, lane };
     InflateResult R;
     inflate_blocks(b, T, out, o0, 0ull - o0, 0xFFFFFFFFu, (int)lane, 32, WarpSync(), R);
     out.flush_to(R.out_len);
-    if (lane == 0) { D.status[s] = R.status; D.out_len[s] = R.out_len - o0; D.consumed[s] = R.consumed; }
+    if (lane == 0) { D.status[s] = R.status; D.out_len[s] = R.out_len - o0; D.consumed[s] = R.consumed - lead; }
 }
 
 // ---------------------------------------------------------------------------------- block-boundary finder
@@ -206,12 +208,20 @@ __global__ void __launch_bounds__(256) k_find_blocks(FindDev F) {
         if (precode_check(smem_bits64(sw, o), smem_bits64(sw, o + 64))) qb[atomicAdd(&nb, 1u)] = (uint16_t)o;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < nb; i += 256) {
-        const uint64_t q = b0 * 8 + qb[i];
-        if (validate_dynamic_header(p, len, q)) {
-            const uint32_t slot = atomicAdd(F.cand_count, 1u);
-            if (slot < F.cand_cap) { F.cand_member[slot] = m; F.cand_bit[slot] = q; }
-        }
+    for (uint32_t i = tid; i < nb; i += 256) {                   // survivors go to a global queue; validated densely by k_validate_candidates
+        const uint32_t slot = atomicAdd(F.q_count, 1u);
+        if (slot < F.q_cap) { F.q_member[slot] = m; F.q_bit[slot] = b0 * 8 + qb[i]; }
+    }
+}
+__global__ void __launch_bounds__(128) k_validate_candidates(FindDev F) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t nq = min(*F.q_count, F.q_cap);
+    if (i >= nq) return;
+    const uint32_t m = F.q_member[i];
+    const uint64_t q = F.q_bit[i];
+    if (validate_dynamic_header(F.in + F.in_off[m], F.in_len[m], q)) {
+        const uint32_t slot = atomicAdd(F.cand_count, 1u);
+        if (slot < F.cand_cap) { F.cand_member[slot] = m; F.cand_bit[slot] = q; }
     }
 }
 
@@ -225,13 +235,15 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_blocks(BlockDev B) {
     if (i >= B.n_blocks) return;
     const uint32_t m = B.blk_member[i];
     BitIn b;
-    bi_init(b, B.in + B.in_off[m], B.in_len[m], B.blk_bit[i]);
-    b.stop = B.blk_stop[i];
+    const uint8_t *p0 = B.in + B.in_off[m];
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
+    bi_init(b, p0 - lead, B.in_len[m] + lead, B.blk_bit[i] + 8ull * lead);
+    b.stop = B.blk_stop[i] > ~0ull - 64 ? ~0ull : B.blk_stop[i] + 8ull * lead;
     CountOut out = { 0 };
     InflateResult R;
     inflate_blocks(b, tabs[wid], out, 0, 1ull << 60, 1, (int)lane, 32, WarpSync(), R);
     if (lane == 0) {
-        B.p_status[i] = R.status; B.p_end_bit[i] = R.end_bit; B.p_out_len[i] = R.out_len;
+        B.p_status[i] = R.status; B.p_end_bit[i] = R.end_bit - 8ull * lead; B.p_out_len[i] = R.out_len;
         B.p_flags[i] = (R.final_seen ? 1u : 0u) | (out.far ? 2u : 0u);
     }
 }
@@ -245,7 +257,9 @@ __global__ void __launch_bounds__(32) k_inflate_blocks(BlockDev B) {
     if (i >= B.n_blocks) return;
     const uint32_t m = B.blk_member[i];
     BitIn b;
-    bi_init(b, B.in + B.in_off[m], B.in_len[m], B.blk_bit[i]);
+    const uint8_t *p0 = B.in + B.in_off[m];
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
+    bi_init(b, p0 - lead, B.in_len[m] + lead, B.blk_bit[i] + 8ull * lead);
     const uint64_t o0 = B.blk_out[i];
     WindowOut out = { ring, B.out, B.mem_out_end[m], o0, lane };
     InflateResult R;
@@ -269,6 +283,8 @@ cudaError_t dec_launch_serial(const DecDev &D, cudaStream_t st) {
 cudaError_t dec_launch_find(const FindDev &F, cudaStream_t st) {
     if (F.n_segs == 0) return cudaSuccess;
     k_find_blocks<<<F.n_segs, 256, 0, st>>>(F);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_validate_candidates<<<(F.q_cap + 127) / 128, 128, 0, st>>>(F);      // grid sized for the queue capacity; idle threads exit at once
     return cudaGetLastError();
 }
 cudaError_t dec_launch_probe(const BlockDev &B, cudaStream_t st) {

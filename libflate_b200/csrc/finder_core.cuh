@@ -33,10 +33,26 @@ B2F_HD bool precode_check(uint64_t w0, uint64_t w1) {
     return kraft == 128u || (nz == 1 && kraft == 64u);
 }
 
-B2F_HD uint32_t get_bits_slow(const uint8_t *p, uint64_t nbytes, uint64_t bitpos, uint32_t n) {   // n <= 24
-    uint64_t byte = bitpos >> 3; uint32_t sh = (uint32_t)(bitpos & 7), v = 0;
-    for (uint32_t k = 0; k < 4; k++) if (byte + k < nbytes) v |= (uint32_t)p[byte + k] << (8 * k);
-    return (v >> sh) & ((1u << n) - 1u);
+// small LSB-first reader for the validation pass (aligned 32-bit loads, zero fill past the end)
+struct VBits { const uint8_t *p; uint64_t nbytes; uint64_t next; uint64_t bb; uint32_t bc; uint64_t pos; };
+B2F_HD uint32_t vb_load32(const uint8_t *p, uint64_t off, uint64_t nbytes) {
+    if (off + 4 <= nbytes && ((reinterpret_cast<uintptr_t>(p + off)) & 3) == 0) return *reinterpret_cast<const uint32_t *>(p + off);
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 4; k++) if (off + k < nbytes) v |= (uint32_t)p[off + k] << (8 * k);
+    return v;
+}
+B2F_HD void vb_init(VBits &b, const uint8_t *p, uint64_t nbytes, uint64_t bitpos) {
+    b.p = p; b.nbytes = nbytes; b.pos = bitpos; b.next = bitpos >> 3;
+    uint32_t drop = (uint32_t)(bitpos & 7);
+    uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p + b.next) & 3);
+    if (mis && b.next >= mis) { b.next -= mis; drop += 8 * mis; }
+    b.bb = (uint64_t)vb_load32(p, b.next, nbytes) >> drop; b.bc = 32 - drop; b.next += 4;
+}
+B2F_HD uint32_t vb_get(VBits &b, uint32_t n) {          // n <= 16
+    if (b.bc < 32) { b.bb |= (uint64_t)vb_load32(b.p, b.next, b.nbytes) << b.bc; b.bc += 32; b.next += 4; }
+    uint32_t v = (uint32_t)b.bb & ((1u << n) - 1u);
+    b.bb >>= n; b.bc -= n; b.pos += n;
+    return v;
 }
 
 // Full header validation (rare path).  Returns true when every check passes.
@@ -44,15 +60,14 @@ B2F_HD bool validate_dynamic_header(const uint8_t *p, uint64_t nbytes, uint64_t 
     const uint8_t ORDER[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
     const uint64_t limit = nbytes * 8;
     if (bitpos + 17 > limit) return false;
-    uint64_t q = bitpos + 3;
-    const uint32_t hlit = get_bits_slow(p, nbytes, q, 5) + 257; q += 5;
-    const uint32_t hdist = get_bits_slow(p, nbytes, q, 5) + 1; q += 5;
-    const uint32_t hclen = get_bits_slow(p, nbytes, q, 4) + 4; q += 4;
+    VBits b; vb_init(b, p, nbytes, bitpos);
+    vb_get(b, 3);
+    const uint32_t hlit = vb_get(b, 5) + 257, hdist = vb_get(b, 5) + 1, hclen = vb_get(b, 4) + 4;
     if (hlit > 286 || hdist > 30) return false;
+    if (b.pos + 3 * hclen > limit) return false;
     uint8_t pw[19];
     for (int i = 0; i < 19; i++) pw[i] = 0;
-    if (q + 3 * hclen > limit) return false;
-    for (uint32_t k = 0; k < hclen; k++) { pw[ORDER[k]] = (uint8_t)get_bits_slow(p, nbytes, q, 3); q += 3; }
+    for (uint32_t k = 0; k < hclen; k++) pw[ORDER[k]] = (uint8_t)vb_get(b, 3);
     uint32_t cnt[8], first[8], off[8]; uint8_t sorted[19];
     for (int i = 0; i < 8; i++) cnt[i] = 0;
     for (int i = 0; i < 19; i++) cnt[pw[i]]++;
@@ -63,26 +78,28 @@ B2F_HD bool validate_dynamic_header(const uint8_t *p, uint64_t nbytes, uint64_t 
     uint32_t total = 0, want = hlit + hdist, prev = 0;
     uint32_t lit_kraft = 0, dist_kraft = 0, nlit = 0, ndist = 0, eob_len = 0;
     while (total < want) {
-        if (q + 7 > limit + 7 || q >= limit) return false;
-        const uint32_t peek = get_bits_slow(p, nbytes, q, 7);
+        if (b.pos >= limit) return false;
+        if (b.bc < 32) { b.bb |= (uint64_t)vb_load32(b.p, b.next, b.nbytes) << b.bc; b.bc += 32; b.next += 4; }
+        const uint32_t peek = (uint32_t)b.bb & 127u;
         uint32_t sym = 0xFFu, used = 0, acc = 0;
         for (uint32_t l = 1; l < 8; l++) {
             acc = (acc << 1) | ((peek >> (l - 1)) & 1u);            // MSB-first code value of the first l bits
             if (cnt[l] && acc >= first[l] && acc - first[l] < cnt[l]) { sym = sorted[off[l] + acc - first[l]]; used = l; break; }
         }
         if (sym == 0xFFu) return false;
-        q += used;
+        b.bb >>= used; b.bc -= used; b.pos += used;
         uint32_t rep = 1, val = sym;
-        if (sym == 16) { if (total == 0) return false; rep = get_bits_slow(p, nbytes, q, 2) + 3; q += 2; val = prev; }
-        else if (sym == 17) { rep = get_bits_slow(p, nbytes, q, 3) + 3; q += 3; val = 0; }
-        else if (sym == 18) { rep = get_bits_slow(p, nbytes, q, 7) + 11; q += 7; val = 0; }
-        if (q > limit || total + rep > want) return false;
-        for (uint32_t k = 0; k < rep; k++) {
-            const uint32_t idx = total + k;
-            if (val) {
+        if (sym == 16) { if (total == 0) return false; rep = vb_get(b, 2) + 3; val = prev; }
+        else if (sym == 17) { rep = vb_get(b, 3) + 3; val = 0; }
+        else if (sym == 18) { rep = vb_get(b, 7) + 11; val = 0; }
+        if (b.pos > limit || total + rep > want) return false;
+        if (val) {
+            for (uint32_t k = 0; k < rep; k++) {
+                const uint32_t idx = total + k;
                 if (idx < hlit) { lit_kraft += 32768u >> val; nlit++; if (idx == 256) eob_len = val; }
                 else { dist_kraft += 32768u >> val; ndist++; }
             }
+            if (lit_kraft > 32768u || dist_kraft > 32768u) return false;      // over-subscribed: give up early
         }
         total += rep; prev = val;
     }

@@ -215,6 +215,61 @@ class Context:
     def decode(self, fmt, data, cap=None):
         return self.decode_batch(fmt, [data], None if cap is None else [cap])[0]
 
+    # ---- device-resident variants (pointers are raw device addresses, e.g. torch tensor.data_ptr())
+    def encode_device(self, fmt, d_in, in_off, in_len, d_out, out_off, out_cap, schedules=None, **kw):
+        L = lib()
+        o = make_opts(**kw)
+        n = len(in_len)
+        a_off = (C.c_uint64 * n)(*in_off); a_len = (C.c_size_t * n)(*in_len)
+        o_off = (C.c_uint64 * n)(*out_off); o_cap = (C.c_size_t * n)(*out_cap)
+        out_len, status = (C.c_size_t * n)(), (C.c_int * n)()
+        sched_arrs, sched_ptrs, n_sched = [], (C.c_void_p * n)(), (C.c_size_t * n)()
+        if schedules is not None:
+            for i, sc in enumerate(schedules):
+                if sc is None:
+                    sched_ptrs[i] = None; n_sched[i] = 0
+                else:
+                    a = sc if isinstance(sc, np.ndarray) else np.asarray(list(sc) + [0], dtype=np.int64)
+                    sched_arrs.append(a); sched_ptrs[i] = a.ctypes.data; n_sched[i] = len(sc)
+        self._check(L.b2f_encode_device(self._h, fmt, C.byref(o), n, C.c_void_p(d_in), a_off, a_len,
+                                        sched_ptrs if schedules is not None else None, n_sched if schedules is not None else None,
+                                        C.c_void_p(d_out), o_off, o_cap, out_len, status))
+        return list(out_len), list(status)
+
+    def decode_device(self, fmt, d_in, in_off, in_len, d_out, out_off, out_cap):
+        L = lib()
+        n = len(in_len)
+        a_off = (C.c_uint64 * n)(*in_off); a_len = (C.c_size_t * n)(*in_len)
+        o_off = (C.c_uint64 * n)(*out_off); o_cap = (C.c_size_t * n)(*out_cap)
+        out_len, used, status = (C.c_size_t * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        self._check(L.b2f_decode_device(self._h, fmt, n, C.c_void_p(d_in), a_off, a_len, C.c_void_p(d_out), o_off, o_cap, out_len, used, status))
+        return list(out_len), list(used), list(status)
+
+    # ---- host-buffer calls on caller-owned numpy buffers (no copies in Python; used by bench.py's e2e leg)
+    def encode_into(self, fmt, src, dst, schedule=None, **kw):
+        L = lib()
+        o = make_opts(**kw)
+        in_len = (C.c_size_t * 1)(src.size); out_cap = (C.c_size_t * 1)(dst.size)
+        out_len, status = (C.c_size_t * 1)(), (C.c_int * 1)()
+        in_ptrs = (C.c_void_p * 1)(src.ctypes.data); out_ptrs = (C.c_void_p * 1)(dst.ctypes.data)
+        if schedule is not None:
+            a = schedule if isinstance(schedule, np.ndarray) else np.asarray(list(schedule) + [0], dtype=np.int64)
+            sp = (C.c_void_p * 1)(a.ctypes.data); ns = (C.c_size_t * 1)(len(schedule))
+        else:
+            sp, ns = None, None
+        self._check(L.b2f_encode_batch(self._h, fmt, C.byref(o), 1, in_ptrs, in_len, sp, ns, out_ptrs, out_cap, out_len, status))
+        if status[0] != OK:
+            raise B2fError(status[0], "encode_into")
+        return out_len[0]
+
+    def decode_into(self, fmt, src, src_len, dst):
+        L = lib()
+        in_len = (C.c_size_t * 1)(src_len); out_cap = (C.c_size_t * 1)(dst.size)
+        out_len, used, status = (C.c_size_t * 1)(), (C.c_size_t * 1)(), (C.c_int * 1)()
+        in_ptrs = (C.c_void_p * 1)(src.ctypes.data); out_ptrs = (C.c_void_p * 1)(dst.ctypes.data)
+        self._check(L.b2f_decode_batch(self._h, fmt, 1, in_ptrs, in_len, out_ptrs, out_cap, out_len, used, status))
+        return out_len[0], used[0], status[0]
+
     # ---- checksums
     def _cksum(self, fn, datas, init):
         ins = [_as_u8(d) for d in datas]

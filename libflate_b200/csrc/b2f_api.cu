@@ -420,7 +420,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     auto put = [&](const void *src, size_t bytes) -> uint8_t * { memcpy(hp, src, bytes); uint8_t *d = dp0 + (hp - hp0); hp += align_up(bytes ? bytes : 1, 256); return d; };
     std::vector<uint32_t> hdr_len(n_streams, (uint32_t)hdr.size());
     EncDev E; memset(&E, 0, sizeof E);
-    E.in = job.d_in;
+    E.in = job.d_in; E.in_size = in_span;
     E.chunks = (const ChunkDesc *)put(P.chunks.data(), n_chunks * sizeof(ChunkDesc)); E.n_chunks = n_chunks;
     E.blocks = (const BlockDesc *)put(P.blocks.data(), n_blocks * sizeof(BlockDesc)); E.n_blocks = n_blocks;
     E.seg0 = (const uint32_t *)put(P.seg0.data(), (n_chunks + 1) * 4); E.pt0 = (const uint32_t *)put(P.pt0.data(), (n_chunks + 1) * 4);
@@ -643,7 +643,7 @@ extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, ui
     uint8_t *dp = ctx->buf[NB_DESC].as<uint8_t>();
     CK(cudaMemcpyAsync(dp, hp, 512, cudaMemcpyHostToDevice, ctx->stream));
     EncDev E; memset(&E, 0, sizeof E);
-    E.in = d_in; E.chunks = (const ChunkDesc *)dp; E.n_chunks = 1;
+    E.in = d_in; E.in_size = len; E.chunks = (const ChunkDesc *)dp; E.n_chunks = 1;
     const uint32_t *dpref = (const uint32_t *)(dp + 256);
     E.seg0 = dpref; E.pt0 = dpref + 2; E.tile0 = dpref + 4; E.grp0 = dpref + 6;
     E.n_segs = pref[1]; E.n_ptiles = pref[3]; E.n_tiles = n_tiles; E.n_grps = pref[7];

@@ -81,57 +81,94 @@ struct CountOut {
 
 
 // ---------------------------------------------------------------------------------- fast symbol loop (device only)
-// Register-resident bit buffer with a prefetched input word; handles literals, EndOfBlock and matches whose codes hit the
-// primary tables.  Anything else (long codes, invalid patterns, end of input/output, too-long references, the probe's stop
-// bit) leaves the reader untouched at the symbol boundary and returns 0, so that the exact generic path decides.
-template <class Out>
-__device__ __forceinline__ int fast_symbols(BitIn &b, const InflateTables &T, Out &out, uint64_t &out_pos, uint64_t hist_base) {
+// Register-resident bit buffer with a prefetched input word, explicit 32-bit shared-memory addresses for the decode tables
+// and the output ring, 32-bit loop counters.  Handles literals, EndOfBlock and matches whose codes hit the primary tables.
+// Anything else (long codes, invalid patterns, end of input/output, too-long references, the probe's stop bit) leaves the
+// reader untouched at the symbol boundary and returns 0, so that the exact generic path decides.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
+template <bool kCount>
+__device__ __forceinline__ int fast_symbols(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base, uint64_t cap,
+                                            uint8_t *ring, uint64_t &flushed, uint8_t *g, uint32_t lane, uint32_t &far) {
     const uint64_t nbytes = b.limit >> 3;
     if (b.eof || b.err) return 0;
-    const uint8_t *__restrict__ p = b.p;
     uint64_t next = b.next;
-    if ((reinterpret_cast<uintptr_t>(p + next) & 3) != 0 || next + 12 > nbytes) return 0;
-    uint64_t bb = b.bb; uint32_t bc = b.bc; uint64_t pos = b.pos;
-    uint32_t nw = *reinterpret_cast<const uint32_t *>(p + next);
-    const uint64_t cap = out.cap();
-    uint64_t op = out_pos;
+    if ((reinterpret_cast<uintptr_t>(b.p + next) & 3) != 0 || next + 16 > nbytes || out_pos + 600 > cap || b.pos > b.stop) return 0;
+    const uint32_t *__restrict__ ip = reinterpret_cast<const uint32_t *>(b.p + next);
+    // budgets (all 32-bit): input words, output bytes, bits before the probe's stop
+    uint32_t words_left = (uint32_t)min((nbytes - next - 12) >> 2, (uint64_t)0x7FFFFFFFu);
+    const uint32_t out_budget = (uint32_t)min(cap - out_pos - 258, (uint64_t)0x7FFFFFF0u);
+    const uint32_t bit_budget = (uint32_t)min(b.stop - b.pos, (uint64_t)0x7FFFFFF0u);
+    const uint32_t rel_hist = (uint32_t)min(out_pos + hist_base, (uint64_t)0x7FFFFFF0u);   // bytes of history before this call
+    const uint32_t rel_blk = (uint32_t)min(out_pos, (uint64_t)0x7FFFFFF0u);                  // probe: bytes this block has produced so far
+    uint64_t bb = b.bb; uint32_t bc = b.bc;
+    uint32_t nw = __ldg(ip);
+    uint32_t used_words = 0, bits = 0, produced = 0;
+    const uint32_t lit_s = (uint32_t)__cvta_generic_to_shared(T.lit), dist_s = (uint32_t)__cvta_generic_to_shared(T.dist);
+    const uint32_t ring_s = kCount ? 0u : (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t op0 = (uint32_t)out_pos;                        // low 32 bits of the absolute output offset (ring index = low 16 bits)
+    uint32_t region = (uint32_t)flushed & ~32767u;
     int ret = 0;
     for (;;) {
-        if (next + 12 > nbytes || op + 258 > cap || pos > b.stop) break;
-        if (bc < 32) { bb |= (uint64_t)nw << bc; bc += 32; next += 4; nw = *reinterpret_cast<const uint32_t *>(p + next); }
-        const uint32_t e = T.lit[(uint32_t)bb & ((1u << kLitBits) - 1u)];
+        if (used_words + 2 >= words_left || produced > out_budget || bits > bit_budget) break;
+        if (bc < 32) { bb |= (uint64_t)nw << bc; bc += 32; used_words++; nw = __ldg(ip + used_words); }
+        const uint32_t lo = (uint32_t)bb;
+        const uint32_t e = lds_u32(lit_s + ((lo & ((1u << kLitBits) - 1u)) << 2));
         const uint32_t w = e & 15u, kind = (e >> 4) & 3u;
         if (kind == kKindLit) {
-            bb >>= w; bc -= w; pos += w;
-            out.lit(op, (uint8_t)(e >> 8)); op += 1;
-            continue;
-        }
-        if (kind == kKindLen) {
+            bb >>= w; bc -= w; bits += w;
+            if (!kCount) { if (lane == 0) sts_u8(ring_s + ((op0 + produced) & kRingMask), e >> 8); }
+            produced += 1;
+        } else if (kind == kKindLen) {
             const uint32_t eb = (e >> 20) & 15u;
-            const uint32_t len = ((e >> 8) & 0x1FFu) + (((uint32_t)(bb >> w)) & ((1u << eb) - 1u));
+            const uint32_t len = ((e >> 8) & 0x1FFu) + ((lo >> w) & ((1u << eb) - 1u));
             const uint32_t used = w + eb;
-            uint64_t bb2 = bb >> used; uint32_t bc2 = bc - used; uint64_t next2 = next; uint32_t nw2 = nw;
-            if (bc2 < 32) { bb2 |= (uint64_t)nw2 << bc2; bc2 += 32; next2 += 4; nw2 = *reinterpret_cast<const uint32_t *>(p + next2); }
-            const uint32_t d = T.dist[(uint32_t)bb2 & ((1u << kDistBits) - 1u)];
+            uint64_t bb2 = bb >> used; uint32_t bc2 = bc - used; uint32_t uw2 = used_words, nw2 = nw;
+            if (bc2 < 32) { bb2 |= (uint64_t)nw2 << bc2; bc2 += 32; uw2++; nw2 = __ldg(ip + uw2); }
+            const uint32_t lo2 = (uint32_t)bb2;
+            const uint32_t d = lds_u32(dist_s + ((lo2 & ((1u << kDistBits) - 1u)) << 2));
             const uint32_t wd = d & 15u;
-            if (wd == 0) break;                                   // long or unassigned distance code
+            if (wd == 0) break;                                    // long or unassigned distance code
             const uint32_t deb = (d >> 24) & 15u;
-            const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(bb2 >> wd)) & ((1u << deb) - 1u));
-            if ((uint64_t)dist > op + hist_base) break;          // "Too long backword reference": reported by the generic path
+            const uint32_t dist = ((d >> 8) & 0xFFFFu) + ((lo2 >> wd) & ((1u << deb) - 1u));
+            if (kCount) { if (dist > produced + rel_blk) far = 1; }   // reference reaches before this block's own output
+            else if (dist > produced + rel_hist) break;            // "Too long backword reference": reported by the generic path
             const uint32_t used2 = wd + deb;
-            bb = bb2 >> used2; bc = bc2 - used2; next = next2; nw = nw2; pos += used + used2;
-            out.copy(op, len, dist); op += len;
-            continue;
+            bb = bb2 >> used2; bc = bc2 - used2; used_words = uw2; nw = nw2; bits += used + used2;
+            if (!kCount) {
+                __syncwarp();
+                const uint32_t dst = op0 + produced, src = dst - dist;
+                if (dist >= len) { for (uint32_t k = lane; k < len; k += 32) sts_u8(ring_s + ((dst + k) & kRingMask), lds_u8(ring_s + ((src + k) & kRingMask))); }
+                else { for (uint32_t k = lane; k < len; k += 32) sts_u8(ring_s + ((dst + k) & kRingMask), lds_u8(ring_s + ((src + k % dist) & kRingMask))); }
+            }
+            produced += len;
+        } else {
+            if (kind == kKindEob) { bb >>= w; bc -= w; bits += w; ret = 1; }
+            break;
         }
-        if (kind == kKindEob) { bb >>= w; bc -= w; pos += w; ret = 1; }
-        break;
+        if (!kCount) {
+            if (((op0 + produced) & ~32767u) != region) {          // crossed a 32 KiB boundary: flush the completed half of the ring
+                const uint64_t abs_now = out_pos + produced, upto = abs_now & ~32767ull;
+                __syncwarp();
+                const uint64_t a0 = flushed;
+                if (((a0 | upto) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 3) == 0) {
+                    for (uint64_t i = a0 + 4ull * lane; i < upto; i += 128) *reinterpret_cast<uint32_t *>(g + i) = lds_u32(ring_s + ((uint32_t)i & kRingMask));
+                } else {
+                    for (uint64_t i = a0 + lane; i < upto; i += 32) g[i] = (uint8_t)lds_u8(ring_s + ((uint32_t)i & kRingMask));
+                }
+                flushed = upto; region = (uint32_t)upto & ~32767u;
+                __syncwarp();
+            }
+        }
     }
-    b.bb = bb; b.bc = bc; b.next = next; b.pos = pos; out_pos = op;
+    b.bb = bb; b.bc = bc; b.next = next + 4ull * used_words; b.pos += bits; out_pos += produced;
     return ret;
 }
 
-__device__ __forceinline__ int WindowOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { return fast_symbols(b, T, *this, out_pos, hist_base); }
-__device__ __forceinline__ int CountOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { return fast_symbols(b, T, *this, out_pos, hist_base); }
+__device__ __forceinline__ int WindowOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { uint32_t f = 0; return fast_symbols<false>(b, T, out_pos, hist_base, capacity, ring, flushed, g, lane, f); }
+__device__ __forceinline__ int CountOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { uint64_t fl = 0; return fast_symbols<true>(b, T, out_pos, hist_base, ~0ull, nullptr, fl, nullptr, 0, far); }
 
 constexpr uint32_t kWinSmem = kRingBytes + (uint32_t)sizeof(InflateTables) + 64;
 

@@ -7,7 +7,8 @@ namespace b2f {
 
 struct EncDev {
     // inputs
-    const uint8_t *in;            // concatenated stream bytes (+ >= 64 B readable padding)
+    const uint8_t *in;            // concatenated stream bytes
+    uint64_t in_size;             // bytes readable at `in` (kernels never load beyond it)
     const ChunkDesc *chunks; uint32_t n_chunks;
     const BlockDesc *blocks; uint32_t n_blocks;
     const uint32_t *seg0, *pt0, *tile0, *grp0;       // per-chunk prefix arrays, n_chunks + 1 entries each

@@ -29,6 +29,14 @@ __device__ __forceinline__ uint32_t find_owner(const uint32_t *__restrict__ pref
     return lo;
 }
 
+// 32-bit load at byte offset `off` of the input that never touches bytes at or beyond in_size (zero fill)
+__device__ __forceinline__ uint32_t ld_in32(const uint8_t *__restrict__ in, uint64_t off, uint64_t in_size) {
+    if (off + 4 <= in_size) return __ldg(reinterpret_cast<const uint32_t *>(in + off));
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 4; k++) if (off + k < in_size) v |= (uint32_t)in[off + k] << (8 * k);
+    return v;
+}
+
 // =============================================================================== K1 lz_chain
 // link[p] = distance to the nearest earlier position of the same chunk whose trigram has the same
 // 14-bit hash (0 = none within 32768).  Every position < end is "inserted" exactly once in
@@ -50,27 +58,51 @@ __global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
     const uint8_t *__restrict__ p = E.in + cd.off;
     uint16_t *__restrict__ lk = E.link + cd.off;
     for (uint32_t q = max(lim, s_start) + lane; q < s_end; q += 32) lk[q] = 0;   // tail without a trigram
-    for (uint32_t base = ws; base < lim; base += 32) {
-        const uint32_t pos = base + lane;
-        const bool valid = pos < lim;
-        uint32_t h = 0x80000000u | lane, old = 0;
-        if (valid) {
-            uint32_t t = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
-            h = (t * 0x9E3779B1u) >> (32 - kHashBits);
-            old = head[h];
-        }
-        const uint32_t m = __match_any_sync(0xFFFFFFFFu, h);
-        const uint32_t lower = m & ((1u << lane) - 1u);
-        const uint32_t prev1 = lower ? (base + (31 - __clz((int)lower)) + 1) : old;
-        if (valid) {
-            if (pos >= s_start) {
+    if (ws >= lim) return;
+    // The input is consumed as 128-byte blocks: lane L holds the aligned word at block + 4L; the next block is prefetched
+    // one block (4 steps) ahead, so no load sits on the critical path.  Positions are int64 relative to the chunk because the
+    // aligned start can lie up to 3 bytes before position `ws` (those lanes are masked off).
+    const int64_t a0 = (int64_t)ws - (int64_t)((cd.off + ws) & 3u);
+    const uint64_t g0 = (uint64_t)((int64_t)cd.off + a0);          // 4-byte aligned offset into E.in
+    uint32_t cur = ld_in32(E.in, g0 + 4ull * lane, E.in_size);
+    uint32_t blk = 0;
+    for (int64_t bpos = a0; bpos < (int64_t)lim; bpos += 128, blk++) {
+        const uint32_t nxt = ld_in32(E.in, g0 + 128ull * (blk + 1) + 4ull * lane, E.in_size);
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) {
+            const int64_t base = bpos + 32 * s4;
+            if (base >= (int64_t)lim) break;
+            const uint32_t wi = (32 * s4 + lane) >> 2, bo = lane & 3u;
+            const uint32_t lo = __shfl_sync(0xFFFFFFFFu, cur, wi);
+            const uint32_t hc = __shfl_sync(0xFFFFFFFFu, cur, (wi + 1) & 31u);
+            const uint32_t hn = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+            const uint32_t hi = wi == 31 ? hn : hc;
+            const uint32_t t = __funnelshift_r(lo, hi, bo * 8u) & 0xFFFFFFu;
+            const int64_t pos64 = base + lane;
+            const bool valid = pos64 >= (int64_t)ws && pos64 < (int64_t)lim;
+            const uint32_t pos = (uint32_t)pos64;
+            const uint32_t h = valid ? (t * 0x9E3779B1u) >> (32 - kHashBits) : 0;
+            const uint32_t old = valid ? head[h] : 0;
+            __syncwarp();
+            if (valid) head[h] = pos + 1;                            // same-hash lanes: one of them wins
+            __syncwarp();
+            const bool lost = valid && head[h] != pos + 1;
+            uint32_t prev1 = old;
+            if (__any_sync(0xFFFFFFFFu, lost)) {                     // rare: two positions of this step share a hash -> exact ordered resolution
+                const uint32_t key = valid ? h : (0x80000000u | lane);
+                const uint32_t m = __match_any_sync(0xFFFFFFFFu, key);
+                const uint32_t lower = m & ((1u << lane) - 1u);
+                if (lower) prev1 = (uint32_t)(base + (31 - __clz((int)lower))) + 1;
+                if (valid && (m >> lane) == 1u) head[h] = pos + 1;   // highest lane of the group publishes
+                __syncwarp();
+            }
+            if (valid && pos >= s_start) {
                 uint32_t d = prev1 ? pos + 1 - prev1 : 0;
                 if (d > kLookback) d = 0;
                 lk[pos] = (uint16_t)d;
             }
-            if ((m >> lane) == 1u) head[h] = pos + 1;     // highest lane of the group publishes
         }
-        __syncwarp();
+        cur = nxt;
     }
 }
 
@@ -101,41 +133,53 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     const uint32_t nvec = (hi - lo + shift + 15) >> 4;
     const uint4 *__restrict__ gsrc = reinterpret_cast<const uint4 *>(E.in + g_al);
     uint4 *sdst = reinterpret_cast<uint4 *>(sb);
-    for (uint32_t i = tid; i < nvec; i += 512) sdst[i] = __ldg(gsrc + i);
+    for (uint32_t i = tid; i < nvec; i += 512) {
+        const uint64_t off = g_al + 16ull * i;
+        if (off + 16 <= E.in_size) sdst[i] = __ldg(gsrc + i);
+        else { uint4 v; v.x = ld_in32(E.in, off, E.in_size); v.y = ld_in32(E.in, off + 4, E.in_size); v.z = ld_in32(E.in, off + 8, E.in_size); v.w = ld_in32(E.in, off + 12, E.in_size); sdst[i] = v; }
+    }
     __syncthreads();
     const uint16_t *__restrict__ lk = E.link + cd.off;
     uint32_t *__restrict__ md = E.md + cd.off;
     const uint32_t sbase = shift - lo;        // smem index of chunk position x is x + sbase (mod 2^32 arithmetic)
-    for (uint32_t pos = ts + tid; pos < te; pos += 512) {
-        uint32_t out = 0;
-        if (pos < end) {
-            const uint32_t si = pos + sbase;
-            const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
-            uint32_t d = lk[pos], total = 0, j = pos;
-            bool found = false;
-            while (d) {
-                total += d;
-                if (total > E.window) break;
-                j -= d;
-                const uint32_t sj = j + sbase;
-                const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
-                if (tj == t) { found = true; break; }
-                d = lk[j];
-            }
-            if (found) {
-                const uint32_t a = si + 3, b = j + sbase + 3;
-                const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
-                uint32_t k = 0;
-                while (k < limit) {
-                    const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
-                    if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                    k += 4;
+    for (uint32_t pos0 = ts + tid; pos0 < te; pos0 += 4 * 512) {
+        uint32_t dpre[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) { const uint32_t q = pos0 + u * 512; dpre[u] = (q < te && q < end) ? lk[q] : 0; }   // independent loads first
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t pos = pos0 + u * 512;
+            if (pos >= te) break;
+            uint32_t out = 0;
+            if (pos < end) {
+                const uint32_t si = pos + sbase;
+                const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
+                uint32_t d = dpre[u], total = 0, j = pos;
+                bool found = false;
+                while (d) {
+                    total += d;
+                    if (total > E.window) break;
+                    j -= d;
+                    const uint32_t sj = j + sbase;
+                    const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
+                    if (tj == t) { found = true; break; }
+                    d = lk[j];
                 }
-                if (k > limit) k = limit;
-                out = ((3 + k) << 16) | total;
+                if (found) {
+                    const uint32_t a = si + 3, b = j + sbase + 3;
+                    const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
+                    uint32_t k = 0;
+                    while (k < limit) {
+                        const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
+                        if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        k += 4;
+                    }
+                    if (k > limit) k = limit;
+                    out = ((3 + k) << 16) | total;
+                }
             }
+            md[pos] = out;
         }
-        md[pos] = out;
     }
 }
 

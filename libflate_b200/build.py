@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libb2f.so")
-SOURCES = ["b2f_api.cu", "encode_kernels.cu", "decode_kernels.cu", "checksum_kernels.cu"]
+SOURCES = ["b2f_api.cu", "encode_kernels.cu", "decode_kernels.cu", "spec_kernels.cu", "checksum_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-cudart", "static"]
 

@@ -16,6 +16,7 @@
 #include "encode_dev.cuh"
 #include "decode_dev.cuh"
 #include "checksum_dev.cuh"
+#include "spec_dev.cuh"
 #include "inflate_core.cuh"
 
 using namespace b2f;
@@ -52,13 +53,13 @@ struct PinBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_DEC_CAND, NB_DEC_BLK, NB_DEC_SER, NB_COUNT };
+enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_DEC_CAND, NB_DEC_BLK, NB_DEC_SER, NB_SPEC_TAB, NB_SPEC_SEG, NB_SPEC_TOK, NB_SPEC_SEL, NB_COUNT };
 
 struct b2f_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevBuf buf[NB_COUNT];
-    PinBuf pin_meta, pin_res, pin_ck, pin_win, pin_cand, pin_blk, pin_ser;
+    PinBuf pin_meta, pin_res, pin_ck, pin_win, pin_cand, pin_blk, pin_ser, pin_sel;
     StageTimer tm;
     std::string err;
     b2f_stats stats;
@@ -87,7 +88,7 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     ctx->device = device;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        enc_init_attributes() != cudaSuccess || dec_init_attributes() != cudaSuccess || checksum_init_tables() != cudaSuccess) {
+        enc_init_attributes() != cudaSuccess || dec_init_attributes() != cudaSuccess || spec_init_attributes() != cudaSuccess || checksum_init_tables() != cudaSuccess) {
         g_create_err = cudaGetErrorString(cudaGetLastError());
         delete ctx;
         return B2F_ERR_CUDA;
@@ -101,7 +102,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->buf) b.release();
-    ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release(); ctx->pin_cand.release(); ctx->pin_blk.release(); ctx->pin_ser.release();
+    ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release(); ctx->pin_cand.release(); ctx->pin_blk.release(); ctx->pin_ser.release(); ctx->pin_sel.release();
     ctx->tm.destroy();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -804,102 +805,137 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
             c_bit.assign(hb, hb + nc);
         }
     }
-    // ---- phase B: probe all candidates (plus bit 0 of every big member)
+    // ---- phase B: every candidate (plus bit 0 of every big member) becomes a speculative block
     std::vector<std::pair<uint32_t, uint64_t>> cands;      // (member, bit) sorted
     for (size_t i = 0; i < c_member.size(); i++) cands.push_back({ c_member[i], c_bit[i] });
     for (uint32_t m : big) cands.push_back({ m, 0 });
     std::sort(cands.begin(), cands.end());
     cands.erase(std::unique(cands.begin(), cands.end()), cands.end());
     const size_t ncand = cands.size();
-    std::vector<int32_t> p_status; std::vector<uint64_t> p_end, p_len; std::vector<uint32_t> p_flags;
+    SpecDev S; memset(&S, 0, sizeof S);
+    std::vector<uint32_t> sel_blocks;                      // indices into cands of the verified chains
+    std::vector<uint64_t> k_out, k_len;                    // per selected block
     if (ncand) {
-        std::vector<uint32_t> bm(ncand); std::vector<uint64_t> bb(ncand), bs(ncand);
+        std::vector<uint32_t> bm(ncand), seg0(ncand + 1, 0), cta0(ncand + 1, 0); std::vector<uint64_t> bb(ncand), be(ncand);
+        bool too_big = false;
         for (size_t i = 0; i < ncand; i++) {
             bm[i] = cands[i].first; bb[i] = cands[i].second;
-            size_t j = i + 8;                               // a true block contains no true boundary; allow a few false positives inside
-            bs[i] = (j < ncand && cands[j].first == bm[i]) ? cands[j].second : ~0ull;
+            be[i] = (i + 1 < ncand && cands[i + 1].first == bm[i]) ? cands[i + 1].second : in_len[bm[i]] * 8;
+            const uint64_t bits = be[i] - bb[i];
+            if (bits >= 0xFFFF0000ull) too_big = true;
+            const uint32_t ns = (uint32_t)((bits + kSpecBits - 1) / kSpecBits);
+            seg0[i + 1] = seg0[i] + ns; cta0[i + 1] = cta0[i] + (ns + kSpecCta - 1) / kSpecCta;
         }
-        Packer PB(ctx->pin_cand, ctx->buf[NB_DEC_CAND]);
-        const size_t b_m = PB.add(bm.data(), ncand * 4), b_b = PB.add(bb.data(), ncand * 8), b_s = PB.add(bs.data(), ncand * 8);
-        const size_t b_st = PB.reserve(ncand * 4), b_en = PB.reserve(ncand * 8), b_ln = PB.reserve(ncand * 8), b_fl = PB.reserve(ncand * 4);
-        CK(PB.commit(ctx->stream));
-        BlockDev B; memset(&B, 0, sizeof B);
-        B.in = d_in; B.in_off = PA.ptr<uint64_t>(a_io); B.in_len = PA.ptr<uint64_t>(a_il); B.n_blocks = (uint32_t)ncand;
-        B.blk_member = PB.ptr<uint32_t>(b_m); B.blk_bit = PB.ptr<uint64_t>(b_b); B.blk_stop = PB.ptr<uint64_t>(b_s);
-        B.p_status = PB.ptr<int32_t>(b_st); B.p_end_bit = PB.ptr<uint64_t>(b_en); B.p_out_len = PB.ptr<uint64_t>(b_ln); B.p_flags = PB.ptr<uint32_t>(b_fl);
-        ctx->tm.mark(ctx->stream, "probe_blocks");
-        CK(dec_launch_probe(B, ctx->stream));
-        ctx->stats.kernel_launches += 1;
-        ctx->tm.mark(ctx->stream, "sync");
-        const size_t res_bytes = PB.off - b_st;
-        CK(ctx->pin_res.ensure(res_bytes + 64));
-        uint8_t *hr = ctx->pin_res.as<uint8_t>();
-        CK(cudaMemcpyAsync(hr, PB.ptr<uint8_t>(b_st), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        p_status.assign((int32_t *)hr, (int32_t *)hr + ncand);
-        p_end.assign((uint64_t *)(hr + (b_en - b_st)), (uint64_t *)(hr + (b_en - b_st)) + ncand);
-        p_len.assign((uint64_t *)(hr + (b_ln - b_st)), (uint64_t *)(hr + (b_ln - b_st)) + ncand);
-        p_flags.assign((uint32_t *)(hr + (b_fl - b_st)), (uint32_t *)(hr + (b_fl - b_st)) + ncand);
-    }
-    // ---- phase C: chain walk from bit 0 of every big member
-    std::vector<uint32_t> k_member; std::vector<uint64_t> k_bit, k_out, k_len;
-    for (uint32_t m : big) {
-        uint64_t pos = 0, out = 0; bool ok = true, fin = false;
-        const size_t first_blk = k_member.size();
-        while (!fin) {
-            auto it = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, pos));
-            if (it == cands.end() || it->first != m || it->second != pos) { ok = false; break; }
-            const size_t ci = (size_t)(it - cands.begin());
-            if (p_status[ci] != kInfOk || (p_flags[ci] & 2u)) { ok = false; break; }
-            k_member.push_back(m); k_bit.push_back(pos); k_out.push_back(out_off[m] + out); k_len.push_back(p_len[ci]);
-            out += p_len[ci]; pos = p_end[ci]; fin = (p_flags[ci] & 1u) != 0;
+        if (too_big) { for (uint32_t m : big) serial.push_back(m); big.clear(); }
+        else {
+            const uint32_t nseg = seg0.back();
+            Packer PB(ctx->pin_cand, ctx->buf[NB_DEC_CAND]);
+            const size_t b_m = PB.add(bm.data(), ncand * 4), b_b = PB.add(bb.data(), ncand * 8), b_e = PB.add(be.data(), ncand * 8),
+                         b_s0 = PB.add(seg0.data(), (ncand + 1) * 4), b_c0 = PB.add(cta0.data(), (ncand + 1) * 4);
+            const size_t r_dr = PB.reserve(ncand * 4), r_fl = PB.reserve(ncand * 4), r_st = PB.reserve(ncand * 4), r_ee = PB.reserve(ncand * 4),
+                         r_es = PB.reserve(ncand * 4), r_no = PB.reserve(ncand * 8), r_nt = PB.reserve(ncand * 8), r_end = PB.reserve(16);
+            CK(PB.commit(ctx->stream));
+            CK(ctx->buf[NB_SPEC_TAB].ensure(ncand * sizeof(InflateTables) + 256));
+            const size_t seg_bytes = (size_t)nseg * (6 * 4 + 2 * 8) + 8 * 256 + 1024;
+            CK(ctx->buf[NB_SPEC_SEG].ensure(seg_bytes));
+            uint8_t *sp = ctx->buf[NB_SPEC_SEG].as<uint8_t>();
+            S.in = d_in; S.in_off = PA.ptr<uint64_t>(a_io); S.in_len = PA.ptr<uint64_t>(a_il);
+            S.n_blocks = (uint32_t)ncand; S.blk_member = PB.ptr<uint32_t>(b_m); S.blk_bit = PB.ptr<uint64_t>(b_b); S.blk_end = PB.ptr<uint64_t>(b_e);
+            S.blk_seg0 = PB.ptr<uint32_t>(b_s0); S.blk_cta0 = PB.ptr<uint32_t>(b_c0); S.n_segs = nseg; S.n_ctas = cta0.back();
+            S.tabs = ctx->buf[NB_SPEC_TAB].as<InflateTables>();
+            S.blk_data_rel = PB.ptr<uint32_t>(r_dr); S.blk_flags = PB.ptr<uint32_t>(r_fl); S.blk_status = PB.ptr<uint32_t>(r_st);
+            S.blk_eob_end = PB.ptr<uint32_t>(r_ee); S.blk_eob_seg = PB.ptr<uint32_t>(r_es); S.blk_nout = PB.ptr<uint64_t>(r_no); S.blk_ntok = PB.ptr<uint64_t>(r_nt);
+            S.s_start = carve<uint32_t>(sp, nseg); S.s_exit = carve<uint32_t>(sp, nseg); S.s_exit_prev = carve<uint32_t>(sp, nseg);
+            S.s_eob_end = carve<uint32_t>(sp, nseg); S.s_nsym = carve<uint32_t>(sp, nseg); S.s_nbytes = carve<uint32_t>(sp, nseg);
+            S.s_out_rel = carve<uint64_t>(sp, nseg); S.s_tok_rel = carve<uint64_t>(sp, nseg);
+            S.changed = carve<uint32_t>(sp, 64);
+            CK(cudaMemsetAsync(S.changed, 0, 256, ctx->stream));
+            ctx->tm.mark(ctx->stream, "spec_parse");
+            CK(spec_launch_parse(S, 5, ctx->stream));
+            ctx->stats.kernel_launches += 7;
+            ctx->tm.mark(ctx->stream, "sync");
+            const size_t res_bytes = r_end - r_dr;
+            CK(ctx->pin_res.ensure(res_bytes + 64));
+            uint8_t *hr = ctx->pin_res.as<uint8_t>();
+            CK(cudaMemcpyAsync(hr, PB.ptr<uint8_t>(r_dr), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const uint32_t *h_fl = (const uint32_t *)(hr + (r_fl - r_dr)), *h_st = (const uint32_t *)(hr + (r_st - r_dr)), *h_ee = (const uint32_t *)(hr + (r_ee - r_dr));
+            const uint64_t *h_no = (const uint64_t *)(hr + (r_no - r_dr)), *h_nt = (const uint64_t *)(hr + (r_nt - r_dr));
+            // ---- phase C: chain walk from bit 0 of every big member
+            std::vector<uint32_t> blk_sel(ncand, 0); std::vector<uint64_t> blk_out0(ncand, 0), blk_tok0(ncand, 0);
+            uint64_t tok_total = 0;
+            for (uint32_t m : big) {
+                uint64_t pos = 0, out = 0; bool ok = true, fin = false;
+                const size_t first_sel = sel_blocks.size(); const uint64_t tok_first = tok_total;
+                while (!fin) {
+                    auto it = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, pos));
+                    if (it == cands.end() || it->first != m || it->second != pos) { ok = false; break; }
+                    const size_t ci = (size_t)(it - cands.begin());
+                    if (h_st[ci] != 0) { ok = false; break; }
+                    sel_blocks.push_back((uint32_t)ci); k_out.push_back(out_off[m] + out); k_len.push_back(h_no[ci]);
+                    blk_out0[ci] = out_off[m] + out; blk_tok0[ci] = tok_total;
+                    tok_total += h_nt[ci]; out += h_no[ci]; pos += h_ee[ci]; fin = (h_fl[ci] & 1u) != 0;
+                }
+                if (ok && out > out_cap[m]) ok = false;
+                if (!ok) { sel_blocks.resize(first_sel); k_out.resize(first_sel); k_len.resize(first_sel); tok_total = tok_first; serial.push_back(m); continue; }
+                is_par[m] = 1; st[m] = kInfOk; olen[m] = out; cons[m] = (pos + 7) >> 3;
+            }
+            for (uint32_t ci : sel_blocks) blk_sel[ci] = 1;
+            const size_t nsel = sel_blocks.size();
+            if (nsel) {
+                CK(ctx->buf[NB_SPEC_TOK].ensure(tok_total * 4 + 256));
+                Packer PS(ctx->pin_sel, ctx->buf[NB_SPEC_SEL]);
+                const size_t s_sel = PS.add(blk_sel.data(), ncand * 4), s_o0 = PS.add(blk_out0.data(), ncand * 8), s_t0 = PS.add(blk_tok0.data(), ncand * 8),
+                             s_lst = PS.add(sel_blocks.data(), nsel * 4);
+                const size_t s_err = PS.reserve(nsel * 4), s_len = PS.reserve(nsel * 8), s_end = PS.reserve(16);
+                CK(PS.commit(ctx->stream));
+                S.blk_sel = PS.ptr<uint32_t>(s_sel); S.blk_out0 = PS.ptr<uint64_t>(s_o0); S.blk_tok0 = PS.ptr<uint64_t>(s_t0); S.sel_blocks = PS.ptr<uint32_t>(s_lst);
+                S.mem_out_off = PA.ptr<uint64_t>(a_oo);
+                S.tokens = ctx->buf[NB_SPEC_TOK].as<uint32_t>(); S.out = d_out;
+                S.res_err = PS.ptr<uint32_t>(s_err); S.res_len = PS.ptr<uint64_t>(s_len);
+                ctx->tm.mark(ctx->stream, "spec_write");
+                CK(spec_launch_write(S, (uint32_t)nsel, ctx->stream));
+                ctx->stats.kernel_launches += 2;
+                ctx->tm.mark(ctx->stream, "sync");
+                CK(ctx->pin_res.ensure((s_end - s_err) + 64));
+                uint8_t *hr2 = ctx->pin_res.as<uint8_t>();
+                CK(cudaMemcpyAsync(hr2, PS.ptr<uint8_t>(s_err), s_end - s_err, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                const uint32_t *h_err = (const uint32_t *)hr2; const uint64_t *h_len = (const uint64_t *)(hr2 + (s_len - s_err));
+                // a block whose matches reach before its own start (foreign stream) or an inconsistent size: redo the member in order
+                std::vector<char> redo(n, 0);
+                for (size_t k = 0; k < nsel; k++) if (h_err[k] || h_len[k] != k_len[k]) redo[cands[sel_blocks[k]].first] = 1;
+                for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; serial.push_back(m); }
+            }
         }
-        if (ok && out > out_cap[m]) ok = false;
-        if (!ok) { k_member.resize(first_blk); k_bit.resize(first_blk); k_out.resize(first_blk); k_len.resize(first_blk); serial.push_back(m); continue; }
-        is_par[m] = 1; st[m] = kInfOk; olen[m] = out; cons[m] = (pos + 7) >> 3;
     }
     for (size_t i = 0; i < n; i++) if (in_len[i] < kParallelMinBytes) serial.push_back((uint32_t)i);
-    // ---- pass 2 + in-order kernel
-    const size_t nblk = k_member.size(), nser = serial.size();
-    Packer PC(ctx->pin_blk, ctx->buf[NB_DEC_BLK]);
-    const size_t c_m = PC.add(k_member.data(), nblk * 4), c_b = PC.add(k_bit.data(), nblk * 8), c_o = PC.add(k_out.data(), nblk * 8);
-    const size_t c_st = PC.reserve(nblk * 4), c_ln = PC.reserve(nblk * 8);
-    std::vector<uint64_t> s_io(nser), s_il(nser), s_oo(nser), s_oc(nser);
-    for (size_t k = 0; k < nser; k++) { uint32_t m = serial[k]; s_io[k] = in_off[m]; s_il[k] = in_len[m]; s_oo[k] = out_off[m]; s_oc[k] = out_cap[m]; }
-    const size_t s_a = PC.add(s_io.data(), nser * 8), s_b = PC.add(s_il.data(), nser * 8), s_c = PC.add(s_oo.data(), nser * 8), s_d = PC.add(s_oc.data(), nser * 8);
-    const size_t s_st = PC.reserve(nser * 4), s_ol = PC.reserve(nser * 8), s_cs = PC.reserve(nser * 8);
-    CK(PC.commit(ctx->stream));
-    ctx->tm.mark(ctx->stream, "inflate");
-    if (nblk) {
-        BlockDev B; memset(&B, 0, sizeof B);
-        B.in = d_in; B.in_off = PA.ptr<uint64_t>(a_io); B.in_len = PA.ptr<uint64_t>(a_il); B.n_blocks = (uint32_t)nblk;
-        B.blk_member = PC.ptr<uint32_t>(c_m); B.blk_bit = PC.ptr<uint64_t>(c_b); B.blk_out = PC.ptr<uint64_t>(c_o);
-        B.out = d_out; B.mem_out_off = PA.ptr<uint64_t>(a_oo); B.mem_out_end = PA.ptr<uint64_t>(a_oe);
-        B.d_status = PC.ptr<int32_t>(c_st); B.d_out_len = PC.ptr<uint64_t>(c_ln);
-        CK(dec_launch_blocks(B, ctx->stream));
-        ctx->stats.kernel_launches += 1;
-    }
+    // ---- in-order kernel for everything that is not on a verified chain
+    const size_t nser = serial.size();
     if (nser) {
+        Packer PC(ctx->pin_blk, ctx->buf[NB_DEC_BLK]);
+        std::vector<uint64_t> s_io(nser), s_il(nser), s_oo(nser), s_oc(nser);
+        for (size_t k = 0; k < nser; k++) { uint32_t m = serial[k]; s_io[k] = in_off[m]; s_il[k] = in_len[m]; s_oo[k] = out_off[m]; s_oc[k] = out_cap[m]; }
+        const size_t s_a = PC.add(s_io.data(), nser * 8), s_b = PC.add(s_il.data(), nser * 8), s_c = PC.add(s_oo.data(), nser * 8), s_d = PC.add(s_oc.data(), nser * 8);
+        const size_t s_st = PC.reserve(nser * 4), s_ol = PC.reserve(nser * 8), s_cs = PC.reserve(nser * 8);
+        CK(PC.commit(ctx->stream));
+        ctx->tm.mark(ctx->stream, "inflate_inorder");
         DecDev D;
         D.in = d_in; D.in_off = PC.ptr<uint64_t>(s_a); D.in_len = PC.ptr<uint64_t>(s_b);
         D.out = d_out; D.out_off = PC.ptr<uint64_t>(s_c); D.out_cap = PC.ptr<uint64_t>(s_d); D.n = (uint32_t)nser;
         D.status = PC.ptr<int32_t>(s_st); D.out_len = PC.ptr<uint64_t>(s_ol); D.consumed = PC.ptr<uint64_t>(s_cs);
         CK(dec_launch_serial(D, ctx->stream));
         ctx->stats.kernel_launches += 1;
-    }
-    ctx->tm.mark(ctx->stream, "results");
-    const size_t res_bytes = PC.off - c_st;
-    CK(ctx->pin_res.ensure(res_bytes + 64));
-    uint8_t *hr = ctx->pin_res.as<uint8_t>();
-    CK(cudaMemcpyAsync(hr, PC.ptr<uint8_t>(c_st), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (size_t k = 0; k < nblk; k++) {
-        const int32_t ds = ((int32_t *)hr)[k]; const uint64_t dl = ((uint64_t *)(hr + (c_ln - c_st)))[k];
-        if (ds != kInfOk || dl != k_len[k]) { ctx->err = "internal: block-parallel decode disagrees with its probe"; return B2F_ERR_CUDA; }
-    }
-    for (size_t k = 0; k < nser; k++) {
-        uint32_t m = serial[k];
-        st[m] = ((int32_t *)(hr + (s_st - c_st)))[k]; olen[m] = ((uint64_t *)(hr + (s_ol - c_st)))[k]; cons[m] = ((uint64_t *)(hr + (s_cs - c_st)))[k];
+        ctx->tm.mark(ctx->stream, "results");
+        const size_t res_bytes = PC.off - s_st;
+        CK(ctx->pin_res.ensure(res_bytes + 64));
+        uint8_t *hr = ctx->pin_res.as<uint8_t>();
+        CK(cudaMemcpyAsync(hr, PC.ptr<uint8_t>(s_st), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t k = 0; k < nser; k++) {
+            uint32_t m = serial[k];
+            st[m] = ((int32_t *)hr)[k]; olen[m] = ((uint64_t *)(hr + (s_ol - s_st)))[k]; cons[m] = ((uint64_t *)(hr + (s_cs - s_st)))[k];
+        }
     }
     return B2F_OK;
 }

@@ -29,7 +29,7 @@ constexpr uint32_t kLitBits = 11, kDistBits = 9;
 constexpr uint32_t kKindLit = 0, kKindEob = 1, kKindLen = 2, kKindSpecial = 3;
 constexpr uint32_t kSpecInvalid = 0, kSpecLong = 1, kSpecBadSym = 2;
 
-struct InflateTables {
+struct alignas(16) InflateTables {
     uint32_t lit[1u << kLitBits];
     uint32_t dist[1u << kDistBits];
     uint16_t lit_sorted[288];

@@ -1,0 +1,364 @@
+// spec_kernels.cu -- sub-block parallel inflate (sm_100a).
+//
+// A DEFLATE block is one serial bit stream, but Huffman parses self-synchronise: a decoder started at an arbitrary bit
+// falls into step with the true parse after a few symbols.  Each candidate block (from the boundary finder) is cut into
+// 4096-bit subsegments, one THREAD each:
+//   k_spec_headers   warp per block : parse the dynamic header, build the decode tables (kept in HBM, 12 KiB per block)
+//   k_spec_round     thread per subsegment, Jacobi iteration: round 0 decodes from the subsegment's first bit (the first
+//                    subsegment from the true first symbol); round r restarts from the exit of the left neighbour of
+//                    round r-1 if that differs from the start used so far.  Fixed point == the true parse.
+//   k_spec_verify    CTA per block  : checks that every start equals its left neighbour's exit (=> by induction the true
+//                    parse), finds EndOfBlock, exclusive scans of symbol/byte counts
+//   k_spec_tokens    thread per subsegment: final decode from the true start, writes one token per symbol
+//   k_spec_resolve   warp per block : LZ77 resolution of the token stream, 32 tokens per step, 64 KiB output ring in
+//                    shared memory (history window), multi-round resolution of matches that depend on each other,
+//                    coalesced 32 KiB flushes to HBM
+// Nothing here is trusted blindly: the host accepts a block only if its verified EndOfBlock lands exactly on the next
+// block of the chain; otherwise the stream goes to the exact in-order kernel (decode_kernels.cu).
+// Reference behaviour being reproduced: src/deflate/decode.rs:112-130, symbol.rs:193-243, libflate_lz77/src/lib.rs:164-194.
+#include "common.cuh"
+#include "inflate_core.cuh"
+#include "spec_dev.cuh"
+
+namespace b2f {
+
+struct WarpSyncS { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+
+// ---------------------------------------------------------------------------------- headers -> tables in HBM
+__global__ void __launch_bounds__(128) k_spec_headers(SpecDev S) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflateTables *tabs = reinterpret_cast<InflateTables *>(smem_raw);
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * 4 + wid;
+    if (b >= S.n_blocks) return;
+    InflateTables &T = tabs[wid];
+    const uint32_t m = S.blk_member[b];
+    const uint8_t *p0 = S.in + S.in_off[m];
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
+    BitIn bi;
+    bi_init(bi, p0 - lead, S.in_len[m] + lead, S.blk_bit[b] + 8ull * lead);
+    uint32_t data_rel = 0xFFFFFFFFu, flags = 0;
+    const uint32_t bfinal = bi_read(bi, 1);
+    const uint32_t btype = bi_read(bi, 2);
+    if (!bi_check(bi) && btype == 2) {
+        if (load_dynamic(bi, T, (int)lane, 32, WarpSyncS()) == kInfOk) {
+            const uint64_t rel = bi.pos - 8ull * lead - S.blk_bit[b];
+            if (rel < 0xFFFFFF00ull && T.lit_maxbw) { data_rel = (uint32_t)rel; flags = bfinal; }
+        }
+    }
+    __syncwarp();
+    if (data_rel != 0xFFFFFFFFu) {                 // publish the tables (coalesced 16-byte copies)
+        const uint4 *src = reinterpret_cast<const uint4 *>(&T);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.tabs + b);
+        for (uint32_t i = lane; i < sizeof(InflateTables) / 16; i += 32) dst[i] = src[i];
+    }
+    if (lane == 0) { S.blk_data_rel[b] = data_rel; S.blk_flags[b] = flags; }
+}
+
+// ---------------------------------------------------------------------------------- per-thread bit reader over HBM
+struct TBits {
+    const uint32_t *wp;      // aligned word pointer of the member (covers `lead` bytes before it)
+    uint64_t nwords;         // readable words (zero fill beyond)
+    uint64_t widx;           // next word to load
+    uint64_t bb; uint32_t bc;
+    uint64_t pos;            // absolute bit position inside the (lead-shifted) member
+};
+__device__ __forceinline__ uint32_t tb_word(const TBits &t, uint64_t i) { return i < t.nwords ? __ldg(t.wp + i) : 0u; }
+__device__ __forceinline__ void tb_seek(TBits &t, uint64_t bit) {
+    t.pos = bit; t.widx = bit >> 5;
+    const uint32_t drop = (uint32_t)bit & 31u;
+    t.bb = (uint64_t)tb_word(t, t.widx) >> drop; t.bc = 32 - drop; t.widx++;
+}
+__device__ __forceinline__ void tb_refill(TBits &t) {
+    if (t.bc < 32) { t.bb |= (uint64_t)tb_word(t, t.widx) << t.bc; t.bc += 32; t.widx++; }
+}
+__device__ __forceinline__ void tb_skip(TBits &t, uint32_t n) { t.bb >>= n; t.bc -= n; t.pos += n; }
+
+constexpr uint32_t kExitEob = 0xFFFFFFFFu, kExitBad = 0xFFFFFFFEu, kExitDead = 0xFFFFFFFDu;
+
+// Decodes symbols from t.pos until t.pos >= stop_abs, EndOfBlock or an undecodable pattern.
+// kEmit: writes one token per symbol to tok[].  Returns the exit code (kExit* or 0 = ran to stop).
+template <bool kEmit>
+__device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T, uint64_t stop_abs, uint32_t &nsym, uint32_t &nbytes,
+                                                uint32_t *__restrict__ tok) {
+    for (;;) {
+        if (t.pos >= stop_abs) return 0;
+        tb_refill(t);
+        uint32_t e = T.lit[(uint32_t)t.bb & ((1u << kLitBits) - 1u)];
+        if ((e & 15u) == 0) e = lookup_code(T, true, (uint32_t)t.bb & 0x7FFFu);     // long code or unassigned
+        const uint32_t w = e & 15u, kind = (e >> 4) & 3u;
+        if (w == 0 || kind == kKindSpecial) return kExitBad;
+        if (kind == kKindLit) {
+            tb_skip(t, w);
+            if (kEmit) tok[nsym] = e >> 8;
+            nsym++; nbytes++;
+            continue;
+        }
+        if (kind == kKindEob) { tb_skip(t, w); return kExitEob; }
+        const uint32_t eb = (e >> 20) & 15u;
+        const uint32_t len = ((e >> 8) & 0x1FFu) + (((uint32_t)(t.bb >> w)) & ((1u << eb) - 1u));
+        tb_skip(t, w + eb);
+        tb_refill(t);
+        uint32_t d = T.dist[(uint32_t)t.bb & ((1u << kDistBits) - 1u)];
+        if ((d & 15u) == 0) d = lookup_code(T, false, (uint32_t)t.bb & 0x7FFFu);
+        const uint32_t wd = d & 15u;
+        if (wd == 0) return kExitBad;
+        const uint32_t deb = (d >> 24) & 15u;
+        const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(t.bb >> wd)) & ((1u << deb) - 1u));
+        tb_skip(t, wd + deb);
+        if (kEmit) tok[nsym] = kSymPtr | (len << 16) | dist;
+        nsym++; nbytes += len;
+    }
+}
+
+__device__ __forceinline__ uint32_t owner_u32(const uint32_t *__restrict__ prefix, uint32_t n, uint32_t idx) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= idx) lo = mid; else hi = mid; }
+    return lo;
+}
+
+struct SegCtx { uint32_t b, k, sg; uint64_t lead8, blk_abs, blk_len; uint32_t data_rel; bool usable; };
+
+__device__ __forceinline__ void load_tables_smem(InflateTables &Ts, const InflateTables *g) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(g);
+    uint4 *dst = reinterpret_cast<uint4 *>(&Ts);
+    for (uint32_t i = threadIdx.x; i < sizeof(InflateTables) / 16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------- speculative rounds
+// CTA = 128 consecutive subsegments of ONE block (tables staged in shared memory).
+__global__ void __launch_bounds__(kSpecCta) k_spec_round(SpecDev S, uint32_t round) {
+    __shared__ __align__(16) InflateTables Ts;
+    const uint32_t b = owner_u32(S.blk_cta0, S.n_blocks, blockIdx.x);
+    const uint32_t data_rel = S.blk_data_rel[b];
+    if (data_rel == 0xFFFFFFFFu) return;                         // unusable header: the block never enters the chain
+    load_tables_smem(Ts, S.tabs + b);
+    const uint32_t nseg = S.blk_seg0[b + 1] - S.blk_seg0[b];
+    const uint32_t k = (blockIdx.x - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
+    if (k >= nseg) return;
+    const uint32_t sg = S.blk_seg0[b] + k;
+    const uint32_t k0 = data_rel / kSpecBits;
+    if (k < k0) { S.s_start[sg] = kExitDead; S.s_exit[sg] = kExitDead; return; }       // header bits only
+    const uint32_t m = S.blk_member[b];
+    const uint8_t *p0 = S.in + S.in_off[m];
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
+    const uint64_t blk_abs = S.blk_bit[b] + 8ull * lead, blk_len = S.blk_end[b] - S.blk_bit[b];
+    uint32_t start;
+    if (round == 0) start = k == k0 ? data_rel : k * kSpecBits;
+    else {
+        if (k == k0) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }   // the first subsegment starts at the true first symbol: carry over
+        const uint32_t pe = S.s_exit_prev[sg - 1];
+        const uint32_t cur = S.s_start[sg];
+        uint32_t want = pe >= kExitDead ? kExitDead : pe;        // left neighbour ended the block / failed: nothing to do here
+        if (want == cur) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }       // unchanged: carry the previous result over
+        start = want;
+        if (start == kExitDead) { S.s_start[sg] = kExitDead; S.s_exit[sg] = kExitDead; S.s_nsym[sg] = 0; S.s_nbytes[sg] = 0; atomicOr(S.changed + round, 1u); return; }
+    }
+    TBits t;
+    t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
+    t.nwords = (S.in_len[m] + lead + 3) >> 2;
+    const uint64_t seg_end = min((uint64_t)(k + 1) * kSpecBits, blk_len);
+    uint32_t nsym = 0, nbytes = 0, ex;
+    if (start >= seg_end) ex = start;                            // the neighbour's last symbol already covers this subsegment
+    else {
+        tb_seek(t, blk_abs + start);
+        const uint32_t r = spec_decode<false>(t, Ts, blk_abs + seg_end, nsym, nbytes, nullptr);
+        if (r == kExitEob) { ex = kExitEob; S.s_eob_end[sg] = (uint32_t)(t.pos - blk_abs); }
+        else if (r == kExitBad) ex = kExitBad;
+        else ex = (uint32_t)(t.pos - blk_abs);
+    }
+    S.s_start[sg] = start; S.s_exit[sg] = ex; S.s_nsym[sg] = nsym; S.s_nbytes[sg] = nbytes;
+    if (round) atomicOr(S.changed + round, 1u);
+}
+
+// ---------------------------------------------------------------------------------- verify + scan (CTA per block)
+__global__ void __launch_bounds__(256) k_spec_verify(SpecDev S) {
+    __shared__ uint64_t wsum_b[8], wsum_s[8];
+    __shared__ uint64_t carry_b, carry_s;
+    __shared__ uint32_t bad, eob_seg;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t data_rel = S.blk_data_rel[b];
+    if (tid == 0) { carry_b = 0; carry_s = 0; bad = data_rel == 0xFFFFFFFFu ? 1u : 0u; eob_seg = 0xFFFFFFFFu; }
+    __syncthreads();
+    const uint32_t s0 = S.blk_seg0[b], nseg = S.blk_seg0[b + 1] - s0;
+    const uint32_t k0 = data_rel == 0xFFFFFFFFu ? 0 : data_rel / kSpecBits;
+    const uint32_t *ex_final = S.s_exit;                         // results of the last round
+    if (!bad) {
+        // pass 1: first EndOfBlock on the chain + consistency of every link before it
+        for (uint32_t base = k0; base < nseg; base += 256) {
+            const uint32_t k = base + tid;
+            if (k < nseg) {
+                const uint32_t ex = ex_final[s0 + k];
+                if (ex == kExitEob) atomicMin(&eob_seg, k);
+            }
+        }
+        __syncthreads();
+        const uint32_t e = eob_seg;
+        if (e == 0xFFFFFFFFu) { if (tid == 0) bad = 1; }
+        __syncthreads();
+        if (!bad) {
+            for (uint32_t base = k0; base <= e; base += 256) {
+                const uint32_t k = base + tid;
+                if (k <= e) {
+                    const uint32_t st = S.s_start[s0 + k], ex = ex_final[s0 + k];
+                    const uint32_t want = k == k0 ? data_rel : ex_final[s0 + k - 1];
+                    if (st != want || st >= kExitDead || (k < e && ex >= kExitDead)) atomicOr(&bad, 1u);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (bad) { if (tid == 0) { S.blk_status[b] = 1; S.blk_nout[b] = 0; S.blk_ntok[b] = 0; S.blk_eob_end[b] = 0; } return; }
+    const uint32_t e = eob_seg;
+    // pass 2: exclusive scans of bytes / symbols over subsegments k0..e
+    for (uint32_t base = k0; base <= e; base += 256) {
+        const uint32_t k = base + tid;
+        const bool in = k <= e;
+        const uint64_t xb = in ? S.s_nbytes[s0 + k] : 0, xs = in ? S.s_nsym[s0 + k] : 0;
+        uint64_t ib = xb, is = xs;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t tb = __shfl_up_sync(0xFFFFFFFFu, ib, d), ts = __shfl_up_sync(0xFFFFFFFFu, is, d);
+            if ((int)lane >= d) { ib += tb; is += ts; }
+        }
+        if (lane == 31) { wsum_b[wid] = ib; wsum_s[wid] = is; }
+        __syncthreads();
+        uint64_t ob = 0, os = 0;
+        for (uint32_t w = 0; w < wid; w++) { ob += wsum_b[w]; os += wsum_s[w]; }
+        const uint64_t cb = carry_b, cs = carry_s;
+        if (in) { S.s_out_rel[s0 + k] = cb + ob + ib - xb; S.s_tok_rel[s0 + k] = cs + os + is - xs; }
+        __syncthreads();
+        if (tid == 255) { carry_b = cb + ob + ib; carry_s = cs + os + is; }
+        __syncthreads();
+    }
+    if (tid == 0) { S.blk_status[b] = 0; S.blk_nout[b] = carry_b; S.blk_ntok[b] = carry_s; S.blk_eob_end[b] = S.s_eob_end[s0 + e]; S.blk_eob_seg[b] = e; }
+}
+
+// ---------------------------------------------------------------------------------- final decode -> tokens
+__global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
+    __shared__ __align__(16) InflateTables Ts;
+    const uint32_t b = owner_u32(S.blk_cta0, S.n_blocks, blockIdx.x);
+    if (S.blk_sel[b] == 0) return;                               // not on the verified chain
+    load_tables_smem(Ts, S.tabs + b);
+    const uint32_t data_rel = S.blk_data_rel[b];
+    const uint32_t k = (blockIdx.x - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
+    const uint32_t k0 = data_rel / kSpecBits, e = S.blk_eob_seg[b];
+    if (k < k0 || k > e) return;
+    const uint32_t sg = S.blk_seg0[b] + k;
+    const uint32_t m = S.blk_member[b];
+    const uint8_t *p0 = S.in + S.in_off[m];
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
+    const uint64_t blk_abs = S.blk_bit[b] + 8ull * lead, blk_len = S.blk_end[b] - S.blk_bit[b];
+    const uint32_t start = S.s_start[sg];
+    const uint64_t seg_end = min((uint64_t)(k + 1) * kSpecBits, blk_len);
+    if (start >= seg_end) return;
+    TBits t;
+    t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
+    t.nwords = (S.in_len[m] + lead + 3) >> 2;
+    tb_seek(t, blk_abs + start);
+    uint32_t nsym = 0, nbytes = 0;
+    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg]);
+}
+
+// ---------------------------------------------------------------------------------- LZ77 resolution (warp per block)
+__device__ __forceinline__ uint32_t r_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void r_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+constexpr uint32_t kResRing = 65536, kResMask = kResRing - 1;
+
+__global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
+    extern __shared__ __align__(16) uint8_t ring[];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t b = S.sel_blocks[blockIdx.x];
+    const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b];
+    const uint64_t ntok = S.blk_ntok[b];
+    const uint64_t out0 = S.blk_out0[b];                        // absolute offset in S.out of the block's first byte
+    const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
+    uint8_t *__restrict__ g = S.out;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    uint64_t pos = out0, flushed = out0;
+    uint32_t err = 0;
+    uint32_t tnext = ntok ? (lane < ntok ? __ldg(tok + lane) : 0u) : 0u;
+    for (uint64_t i0 = 0; i0 < ntok; i0 += 32) {
+        const uint32_t tk = tnext;
+        const uint64_t in = i0 + 32 + lane;
+        tnext = in < ntok ? __ldg(tok + in) : 0u;                // prefetch the next step's tokens
+        const bool live = i0 + lane < ntok;
+        const bool is_m = live && (tk & kSymPtr);
+        const uint32_t len = !live ? 0u : is_m ? (tk >> 16) & 0x1FFu : 1u;
+        uint32_t incl = len;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint64_t dst = pos + incl - len;
+        const uint32_t dst32 = (uint32_t)dst;
+        if (live && !is_m) r_sts8(ring_s + (dst32 & kResMask), tk & 0xFFu);
+        const uint32_t dist = tk & 0xFFFFu;
+        if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the block (1) / before the stream (2)
+        __syncwarp();
+        // multi-round resolution: a match may copy once everything it reads lies before the first unresolved match
+        uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m);
+        bool done = !is_m;
+        while (pending) {
+            const uint32_t first = __ffs((int)pending) - 1;
+            const uint32_t xlo = __shfl_sync(0xFFFFFFFFu, dst32, first);      // low 32 bits suffice: the step spans < 2^14 bytes
+            const uint32_t need = dist >= len ? len : dist;                    // bytes read before dst: [dst-dist, dst-dist+need)
+            const bool ready = !done && (int32_t)((dst32 - dist + need) - xlo) <= 0;
+            if (ready) {
+                const uint32_t src = dst32 - dist;
+                if (dist >= len) { for (uint32_t k = 0; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((src + k) & kResMask))); }
+                else { for (uint32_t k = 0; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((dst32 + k - dist) & kResMask))); }
+                done = true;
+            }
+            __syncwarp();
+            pending = __ballot_sync(0xFFFFFFFFu, !done);
+        }
+        pos += total;
+        const uint64_t boundary = pos & ~32767ull;
+        if (boundary > flushed) {
+            __syncwarp();
+            if (((flushed | boundary) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 3) == 0) {
+                for (uint64_t i = flushed + 4ull * lane; i < boundary; i += 128) *reinterpret_cast<uint32_t *>(g + i) = r_lds32(ring_s + ((uint32_t)i & kResMask));
+            } else {
+                for (uint64_t i = flushed + lane; i < boundary; i += 32) g[i] = (uint8_t)r_lds8(ring_s + ((uint32_t)i & kResMask));
+            }
+            flushed = boundary;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (uint64_t i = flushed + lane; i < pos; i += 32) g[i] = (uint8_t)r_lds8(ring_s + ((uint32_t)i & kResMask));
+    err = __reduce_or_sync(0xFFFFFFFFu, err);
+    if (lane == 0) { S.res_err[blockIdx.x] = err; S.res_len[blockIdx.x] = pos - out0; }
+}
+
+// ---------------------------------------------------------------------------------- launchers
+cudaError_t spec_init_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(k_spec_headers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(InflateTables)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_spec_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResRing);
+}
+cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st) {
+    if (!S.n_blocks) return cudaSuccess;
+    k_spec_headers<<<(S.n_blocks + 3) / 4, 128, 4 * sizeof(InflateTables), st>>>(S);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    SpecDev R = S;
+    for (uint32_t r = 0; r < rounds; r++) {
+        // Jacobi iteration: round r reads the exits of round r-1 (s_exit_prev) and writes s_exit
+        if (r & 1) { R.s_exit = S.s_exit_prev; R.s_exit_prev = S.s_exit; } else { R.s_exit = S.s_exit; R.s_exit_prev = S.s_exit_prev; }
+        k_spec_round<<<S.n_ctas, kSpecCta, 0, st>>>(R, r);
+        e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    }
+    if (((rounds - 1) & 1)) { R.s_exit = S.s_exit_prev; R.s_exit_prev = S.s_exit; } else { R.s_exit = S.s_exit; R.s_exit_prev = S.s_exit_prev; }
+    k_spec_verify<<<S.n_blocks, 256, 0, st>>>(R);
+    return cudaGetLastError();
+}
+cudaError_t spec_launch_write(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
+    if (!n_sel) return cudaSuccess;
+    k_spec_tokens<<<S.n_ctas, kSpecCta, 0, st>>>(S);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_spec_resolve<<<n_sel, 32, kResRing, st>>>(S);
+    return cudaGetLastError();
+}
+
+}  // namespace b2f

@@ -229,6 +229,42 @@ def test_decode_matches_oracle_valid_and_corrupt(ctx):
                 assert used == wused
 
 
+def test_decode_large_streams_block_parallel_path(ctx):
+    """streams >= 128 KiB compressed go through the finder + speculative sub-block decode; anything irregular must fall
+    back to the in-order kernel and still match the oracle / zlib bit for bit"""
+    rng = random.Random(41)
+    text = _text(rng, 6 << 20, nwords=5000)
+    rnd = bytes(rng.getrandbits(8) for _ in range(1 << 20))
+    mixed = text[: 1 << 20] + rnd[: 300000] + b"\x00" * 700000 + (b"abc" * 100000) + text[1 << 20: 2 << 20] + bytes([7]) * 500000
+    cases = {
+        "text_A": orc.encode(0, text, [8192] * (len(text) // 8192 + 1)),
+        "text_single_write": orc.encode(0, text),                                   # one 6 MiB block
+        "text_small_blocks": orc.encode(0, text, block_size=100000),
+        "mixed": orc.encode(0, mixed, [8192] * (len(mixed) // 8192 + 1)),
+        "random": orc.encode(0, rnd * 3, [8192] * 400),
+        "zlib6_foreign": pyzlib.compress(text, 6)[2:-4],                            # cross-block references -> fallback
+        "zlib1_foreign": pyzlib.compress(mixed, 1)[2:-4],
+        "fixed_mode": orc.encode(0, text[: 2 << 20], mode=orc.MODE_FIXED),          # no dynamic headers -> fallback
+        "stored_mode": orc.encode(0, text[: 1 << 20], mode=orc.MODE_STORED),
+    }
+    plain = {"text_A": text, "text_single_write": text, "text_small_blocks": text, "mixed": mixed, "random": rnd * 3,
+             "zlib6_foreign": text, "zlib1_foreign": mixed, "fixed_mode": text[: 2 << 20], "stored_mode": text[: 1 << 20]}
+    names = list(cases)
+    res = ctx.decode_batch(0, [cases[k] for k in names], caps=[len(plain[k]) + 64 for k in names])
+    for k, (st, out, used, _) in zip(names, res):
+        assert st == 0, k
+        assert out == plain[k], (k, len(out), len(plain[k]), next((i for i in range(min(len(out), len(plain[k]))) if out[i] != plain[k][i]), -1))
+        assert used == len(cases[k]), k
+    # corrupt one bit in the middle of a large stream: same status and partial output as the oracle
+    b = bytearray(cases["text_A"]); b[len(b) // 2] ^= 0x10
+    st, out, used, _ = ctx.decode(0, bytes(b), cap=len(text) + 64)
+    rc, want, _, msg = orc.decode(0, bytes(b), cap=len(text) + 64)
+    assert st == rc and out == want, (st, rc, len(out), len(want), msg)
+    # too-small output for a large stream
+    st, out, _, need = ctx.decode(0, cases["text_A"], cap=1 << 20)
+    assert st == -3 and out == text[: 1 << 20] and need == len(text)
+
+
 def test_decode_output_too_small(ctx):
     d = b"abcabcabc" * 5000
     enc = orc.encode(orc.FMT_ZLIB, d)

@@ -165,6 +165,8 @@ typedef struct b2f_stats {
     float last_kernel_ms[16];     /* per-stage device time of the last encode/decode call (CUDA events on ctx's stream) */
     uint32_t last_n_stages;
     float last_device_ms;         /* whole device section of the last call */
+    uint64_t decode_parallel_streams;  /* DEFLATE streams decoded by the block/sub-block parallel path since ctx creation */
+    uint64_t decode_inorder_streams;   /* streams decoded by the in-order kernel (small, irregular or erroneous streams)  */
 } b2f_stats;
 int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out);
 const char *b2f_stage_name(b2f_ctx *ctx, uint32_t stage);   /* name of stage i of the last call */

@@ -26,7 +26,7 @@ class EncodeOpts(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("last_kernel_ms", C.c_float * 16), ("last_n_stages", C.c_uint32),
-                ("last_device_ms", C.c_float)]
+                ("last_device_ms", C.c_float), ("decode_parallel_streams", C.c_uint64), ("decode_inorder_streams", C.c_uint64)]
 
 
 EXPORTS = [
@@ -291,7 +291,8 @@ class Context:
         s = Stats()
         lib().b2f_get_stats(self._h, C.byref(s))
         stages = [((lib().b2f_stage_name(self._h, i) or b"").decode(), s.last_kernel_ms[i]) for i in range(s.last_n_stages)]
-        return {"kernel_launches": s.kernel_launches, "stages": stages, "device_ms": s.last_device_ms}
+        return {"kernel_launches": s.kernel_launches, "stages": stages, "device_ms": s.last_device_ms,
+                "decode_parallel_streams": s.decode_parallel_streams, "decode_inorder_streams": s.decode_inorder_streams}
 
 
 def plan_from_writes(sched, in_len, block_size=1 << 20, window=32768):

@@ -65,6 +65,7 @@ struct b2f_ctx {
     b2f_stats stats;
     const char *stage_names[16];
     bool last_is_decode = false;
+    uint64_t n_spec_members = 0, n_inorder_members = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -109,7 +110,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
 }
 extern "C" const char *b2f_last_error(const b2f_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 extern "C" void *b2f_ctx_stream(b2f_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-extern "C" int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out) { if (!ctx || !out) return B2F_ERR_INVALID_ARG; *out = ctx->stats; return B2F_OK; }
+extern "C" int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out) { if (!ctx || !out) return B2F_ERR_INVALID_ARG; ctx->stats.decode_parallel_streams = ctx->n_spec_members; ctx->stats.decode_inorder_streams = ctx->n_inorder_members; *out = ctx->stats; return B2F_OK; }
 extern "C" const char *b2f_stage_name(b2f_ctx *ctx, uint32_t i) { return (ctx && i < 16 && ctx->stage_names[i]) ? ctx->stage_names[i] : ""; }
 
 extern "C" void b2f_encode_opts_default(b2f_encode_opts *o) {
@@ -877,6 +878,29 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     tok_total += h_nt[ci]; out += h_no[ci]; pos += h_ee[ci]; fin = (h_fl[ci] & 1u) != 0;
                 }
                 if (ok && out > out_cap[m]) ok = false;
+                if (!ok && getenv("B2F_DEBUG")) {
+                    auto it = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, pos));
+                    const bool found = it != cands.end() && it->first == m && it->second == pos;
+                    const size_t ci = found ? (size_t)(it - cands.begin()) : 0;
+                    fprintf(stderr, "[b2f] member %u: chain broke at bit %llu after %zu blocks (candidate %s, status %u, out %llu cap %llu)\n", m,
+                            (unsigned long long)pos, sel_blocks.size() - first_sel, found ? "found" : "missing", found ? h_st[ci] : 99u,
+                            (unsigned long long)out, (unsigned long long)out_cap[m]);
+                    if (found) {   // dump the verification state of the failing block
+                        const uint32_t s0 = seg0[ci], ns = seg0[ci + 1] - seg0[ci];
+                        std::vector<uint32_t> hs(ns), he(ns), hp(ns);
+                        cudaMemcpy(hs.data(), S.s_start + s0, ns * 4, cudaMemcpyDeviceToHost);
+                        cudaMemcpy(he.data(), S.s_exit + s0, ns * 4, cudaMemcpyDeviceToHost);
+                        cudaMemcpy(hp.data(), S.s_exit_prev + s0, ns * 4, cudaMemcpyDeviceToHost);
+                        uint32_t dr = 0; cudaMemcpy(&dr, S.blk_data_rel + ci, 4, cudaMemcpyDeviceToHost);
+                        fprintf(stderr, "[b2f]   block %zu: bit %llu len %llu bits, %u subsegments, data_rel %u\n", ci, (unsigned long long)bb[ci],
+                                (unsigned long long)(be[ci] - bb[ci]), ns, dr);
+                        uint32_t shown = 0;
+                        for (uint32_t k = 0; k < ns && shown < 12; k++) {
+                            const uint32_t want = k == 0 ? dr : he[k - 1];
+                            if (k == 0 || hs[k] != want || he[k] >= 0xFFFFFFFDu) { fprintf(stderr, "[b2f]     k=%u start=%u want=%u exitA=%u exitB=%u\n", k, hs[k], want, he[k], hp[k]); shown++; }
+                        }
+                    }
+                }
                 if (!ok) { sel_blocks.resize(first_sel); k_out.resize(first_sel); k_len.resize(first_sel); tok_total = tok_first; serial.push_back(m); continue; }
                 is_par[m] = 1; st[m] = kInfOk; olen[m] = out; cons[m] = (pos + 7) >> 3;
             }
@@ -912,6 +936,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     for (size_t i = 0; i < n; i++) if (in_len[i] < kParallelMinBytes) serial.push_back((uint32_t)i);
     // ---- in-order kernel for everything that is not on a verified chain
     const size_t nser = serial.size();
+    ctx->n_inorder_members += nser; ctx->n_spec_members += n - nser;
     if (nser) {
         Packer PC(ctx->pin_blk, ctx->buf[NB_DEC_BLK]);
         std::vector<uint64_t> s_io(nser), s_il(nser), s_oo(nser), s_oc(nser);

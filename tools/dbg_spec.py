@@ -1,0 +1,11 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["B2F_DEBUG"] = "1"
+from libflate_b200 import native, titles
+ctx = native.Context(0)
+for mib in (1, 4, 8):
+    d = titles.generate(mib << 20, seed=42, workers=4)
+    enc = ctx.encode(native.FMT_DEFLATE, d, [8192] * (d.size // 8192 + 1))
+    st, out, used, _ = ctx.decode(native.FMT_DEFLATE, enc, cap=d.size + 64)
+    s = ctx.stats()
+    print(mib, "MiB: status", st, "ok", out == d.tobytes(), "parallel", s["decode_parallel_streams"], "inorder", s["decode_inorder_streams"], s["stages"])

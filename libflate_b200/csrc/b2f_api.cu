@@ -263,7 +263,6 @@ int run_checksums(b2f_ctx *ctx, const uint8_t *d_base, const std::vector<uint64_
     CK(ctx->pin_res.ensure(n * 8));
     uint32_t *hr = ctx->pin_res.as<uint32_t>();
     CK(cudaMemcpyAsync(hr, dm + o_oc, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->tm.finish(ctx->stream);
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t s = 0; s < n; s++) { crc[s] = hr[s]; adler[s] = hr[n + s]; }
     return B2F_OK;
@@ -281,6 +280,8 @@ int checksum_batch_host(b2f_ctx *ctx, size_t n, const uint8_t *const *buf, const
     std::vector<uint32_t> crc, adler;
     int rc = run_checksums(ctx, d, off, ln, is_crc, !is_crc, init, crc, adler);
     if (rc) return rc;
+    ctx->tm.finish(ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
     for (size_t s = 0; s < n; s++) out[s] = is_crc ? crc[s] : adler[s];
     collect_stats(ctx, false);
     return B2F_OK;
@@ -594,6 +595,8 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         std::vector<uint32_t> crc, adler;
         rc = run_checksums(ctx, d_in, job.in_off, job.in_len, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
         if (rc) return rc;
+        ctx->tm.finish(ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
         for (size_t s = 0; s < n_streams; s++) {
             std::vector<uint8_t> o;
             stored_stream(fmt, *opts, in[s], (size_t)job.in_len[s], sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, crc[s], adler[s], o);
@@ -1113,6 +1116,8 @@ extern "C" int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams, const u
     InputAccess IA = { ctx, in, d_in, in_off.data(), in_len };
     int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status);
     if (rc) return rc;
+    ctx->tm.finish(ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
     collect_stats(ctx, true);
     for (size_t s = 0; s < n_streams; s++) {
         size_t w = std::min(out_len[s], out_cap[s]);
@@ -1131,6 +1136,8 @@ extern "C" int b2f_decode_device(b2f_ctx *ctx, int fmt, size_t n_streams, const 
     InputAccess IA = { ctx, nullptr, d_in, in_off, in_len };
     int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off, in_len, d_out, out_off, out_cap, out_len, in_consumed, status);
     if (rc) return rc;
+    ctx->tm.finish(ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
     collect_stats(ctx, true);
     return B2F_OK;
 }

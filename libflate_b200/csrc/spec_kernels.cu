@@ -150,10 +150,11 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_round(SpecDev S, uint32_t rou
         if (k == k0) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }   // the first subsegment starts at the true first symbol: carry over
         const uint32_t pe = S.s_exit_prev[sg - 1];
         const uint32_t cur = S.s_start[sg];
-        uint32_t want = pe >= kExitDead ? kExitDead : pe;        // left neighbour ended the block / failed: nothing to do here
-        if (want == cur) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }       // unchanged: carry the previous result over
-        start = want;
-        if (start == kExitDead) { S.s_start[sg] = kExitDead; S.s_exit[sg] = kExitDead; S.s_nsym[sg] = 0; S.s_nbytes[sg] = 0; atomicOr(S.changed + round, 1u); return; }
+        // An unusable neighbour exit (its speculative parse ran into EndOfBlock / an unassigned code, or the block really ends
+        // there) carries no information about this subsegment: keep the current parse.  Propagating it would send a "dead"
+        // pulse one subsegment to the right per round.
+        if (pe >= kExitDead || pe == cur) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }
+        start = pe;
     }
     TBits t;
     t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
@@ -306,8 +307,22 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
             const bool ready = !done && (int32_t)((dst32 - dist + need) - xlo) <= 0;
             if (ready) {
                 const uint32_t src = dst32 - dist;
-                if (dist >= len) { for (uint32_t k = 0; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((src + k) & kResMask))); }
-                else { for (uint32_t k = 0; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((dst32 + k - dist) & kResMask))); }
+                if (dist >= 4) {
+                    // 4 bytes per iteration: two aligned word loads + funnel shift; stores stay bytewise because neighbouring tokens
+                    // share words.  With dist >= 4 the 4 source bytes of an iteration were written before this iteration.
+                    uint32_t k = 0;
+                    for (; k + 4 <= len; k += 4) {
+                        const uint32_t sa = (src + k) & kResMask;
+                        const uint32_t w0 = r_lds32(ring_s + (sa & ~3u)), w1 = r_lds32(ring_s + ((sa + 4) & kResMask & ~3u));
+                        const uint32_t v = __funnelshift_r(w0, w1, (sa & 3u) * 8u);
+                        const uint32_t da = dst32 + k;
+                        r_sts8(ring_s + (da & kResMask), v & 0xFFu); r_sts8(ring_s + ((da + 1) & kResMask), (v >> 8) & 0xFFu);
+                        r_sts8(ring_s + ((da + 2) & kResMask), (v >> 16) & 0xFFu); r_sts8(ring_s + ((da + 3) & kResMask), v >> 24);
+                    }
+                    for (; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((src + k) & kResMask)));
+                } else {
+                    for (uint32_t k = 0; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((dst32 + k - dist) & kResMask)));
+                }
                 done = true;
             }
             __syncwarp();

@@ -250,7 +250,12 @@ def test_decode_large_streams_block_parallel_path(ctx):
     plain = {"text_A": text, "text_single_write": text, "text_small_blocks": text, "mixed": mixed, "random": rnd * 3,
              "zlib6_foreign": text, "zlib1_foreign": mixed, "fixed_mode": text[: 2 << 20], "stored_mode": text[: 1 << 20]}
     names = list(cases)
+    before = ctx.stats()
     res = ctx.decode_batch(0, [cases[k] for k in names], caps=[len(plain[k]) + 64 for k in names])
+    after = ctx.stats()
+    # the five libflate-style streams must really take the parallel path; the foreign / fixed / stored ones fall back
+    assert after["decode_parallel_streams"] - before["decode_parallel_streams"] == 5, (before, after)
+    assert after["decode_inorder_streams"] - before["decode_inorder_streams"] == 4
     for k, (st, out, used, _) in zip(names, res):
         assert st == 0, k
         assert out == plain[k], (k, len(out), len(plain[k]), next((i for i in range(min(len(out), len(plain[k]))) if out[i] != plain[k][i]), -1))

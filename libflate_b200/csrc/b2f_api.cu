@@ -815,10 +815,14 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     for (uint32_t m : big) cands.push_back({ m, 0 });
     std::sort(cands.begin(), cands.end());
     cands.erase(std::unique(cands.begin(), cands.end()), cands.end());
-    const size_t ncand = cands.size();
     SpecDev S; memset(&S, 0, sizeof S);
     std::vector<uint32_t> sel_blocks;                      // indices into cands of the verified chains
     std::vector<uint64_t> k_out, k_len;                    // per selected block
+    std::vector<uint32_t> serial_spec;                     // members given up by the speculative path
+    for (int attempt = 0; attempt < 12; attempt++) {
+    bool retry = false;
+    sel_blocks.clear(); k_out.clear(); k_len.clear(); serial_spec.clear();
+    const size_t ncand = cands.size();
     if (ncand) {
         std::vector<uint32_t> bm(ncand), seg0(ncand + 1, 0), cta0(ncand + 1, 0); std::vector<uint64_t> bb(ncand), be(ncand);
         bool too_big = false;
@@ -830,7 +834,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
             const uint32_t ns = (uint32_t)((bits + kSpecBits - 1) / kSpecBits);
             seg0[i + 1] = seg0[i] + ns; cta0[i + 1] = cta0[i] + (ns + kSpecCta - 1) / kSpecCta;
         }
-        if (too_big) { for (uint32_t m : big) serial.push_back(m); big.clear(); }
+        if (too_big) { for (uint32_t m : big) serial_spec.push_back(m); big.clear(); }
         else {
             const uint32_t nseg = seg0.back();
             Packer PB(ctx->pin_cand, ctx->buf[NB_DEC_CAND]);
@@ -868,6 +872,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
             // ---- phase C: chain walk from bit 0 of every big member
             std::vector<uint32_t> blk_sel(ncand, 0); std::vector<uint64_t> blk_out0(ncand, 0), blk_tok0(ncand, 0);
             uint64_t tok_total = 0;
+            std::vector<std::pair<uint32_t, uint64_t>> drop;
             for (uint32_t m : big) {
                 uint64_t pos = 0, out = 0; bool ok = true, fin = false;
                 const size_t first_sel = sel_blocks.size(); const uint64_t tok_first = tok_total;
@@ -904,8 +909,23 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                         }
                     }
                 }
-                if (!ok) { sel_blocks.resize(first_sel); k_out.resize(first_sel); k_len.resize(first_sel); tok_total = tok_first; serial.push_back(m); continue; }
+                if (!ok) {
+                    sel_blocks.resize(first_sel); k_out.resize(first_sel); k_len.resize(first_sel); tok_total = tok_first; serial_spec.push_back(m);
+                    // A false-positive candidate inside a true block cuts that block short (no EndOfBlock before the next candidate):
+                    // drop the candidate that follows the failing block and parse again.
+                    auto it = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, pos));
+                    if (it != cands.end() && it->first == m && it->second == pos && (it + 1) != cands.end() && (it + 1)->first == m && out <= out_cap[m]) {
+                        drop.push_back(*(it + 1)); retry = true;
+                    }
+                    continue;
+                }
                 is_par[m] = 1; st[m] = kInfOk; olen[m] = out; cons[m] = (pos + 7) >> 3;
+            }
+            if (retry && attempt + 1 < 12) {
+                for (auto &d : drop) cands.erase(std::remove(cands.begin(), cands.end(), d), cands.end());
+                for (uint32_t m : big) is_par[m] = 0;
+                ctx->tm.mark(ctx->stream, "spec_retry");
+                continue;
             }
             for (uint32_t ci : sel_blocks) blk_sel[ci] = 1;
             const size_t nsel = sel_blocks.size();
@@ -932,10 +952,13 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 // a block whose matches reach before its own start (foreign stream) or an inconsistent size: redo the member in order
                 std::vector<char> redo(n, 0);
                 for (size_t k = 0; k < nsel; k++) if (h_err[k] || h_len[k] != k_len[k]) redo[cands[sel_blocks[k]].first] = 1;
-                for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; serial.push_back(m); }
+                for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; serial_spec.push_back(m); }
             }
         }
     }
+    break;
+    }   // attempts
+    for (uint32_t m : serial_spec) if (!is_par[m]) serial.push_back(m);
     for (size_t i = 0; i < n; i++) if (in_len[i] < kParallelMinBytes) serial.push_back((uint32_t)i);
     // ---- in-order kernel for everything that is not on a verified chain
     const size_t nser = serial.size();

@@ -297,36 +297,25 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
         const uint32_t dist = tk & 0xFFFFu;
         if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the block (1) / before the stream (2)
         __syncwarp();
-        // multi-round resolution: a match may copy once everything it reads lies before the first unresolved match
+        // matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on the
+        // bytes written just before them, so resolving them independently buys nothing)
         uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m);
-        bool done = !is_m;
         while (pending) {
-            const uint32_t first = __ffs((int)pending) - 1;
-            const uint32_t xlo = __shfl_sync(0xFFFFFFFFu, dst32, first);      // low 32 bits suffice: the step spans < 2^14 bytes
-            const uint32_t need = dist >= len ? len : dist;                    // bytes read before dst: [dst-dist, dst-dist+need)
-            const bool ready = !done && (int32_t)((dst32 - dist + need) - xlo) <= 0;
-            if (ready) {
-                const uint32_t src = dst32 - dist;
-                if (dist >= 4) {
-                    // 4 bytes per iteration: two aligned word loads + funnel shift; stores stay bytewise because neighbouring tokens
-                    // share words.  With dist >= 4 the 4 source bytes of an iteration were written before this iteration.
-                    uint32_t k = 0;
-                    for (; k + 4 <= len; k += 4) {
-                        const uint32_t sa = (src + k) & kResMask;
-                        const uint32_t w0 = r_lds32(ring_s + (sa & ~3u)), w1 = r_lds32(ring_s + ((sa + 4) & kResMask & ~3u));
-                        const uint32_t v = __funnelshift_r(w0, w1, (sa & 3u) * 8u);
-                        const uint32_t da = dst32 + k;
-                        r_sts8(ring_s + (da & kResMask), v & 0xFFu); r_sts8(ring_s + ((da + 1) & kResMask), (v >> 8) & 0xFFu);
-                        r_sts8(ring_s + ((da + 2) & kResMask), (v >> 16) & 0xFFu); r_sts8(ring_s + ((da + 3) & kResMask), v >> 24);
-                    }
-                    for (; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((src + k) & kResMask)));
-                } else {
-                    for (uint32_t k = 0; k < len; k++) r_sts8(ring_s + ((dst32 + k) & kResMask), r_lds8(ring_s + ((dst32 + k - dist) & kResMask)));
+            const uint32_t j = __ffs((int)pending) - 1;
+            pending &= pending - 1;
+            const uint32_t mdst = __shfl_sync(0xFFFFFFFFu, dst32, j);
+            const uint32_t mtk = __shfl_sync(0xFFFFFFFFu, tk, j);
+            const uint32_t mlen = (mtk >> 16) & 0x1FFu, mdist = mtk & 0xFFFFu;
+            const uint32_t msrc = mdst - mdist;
+            if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) r_sts8(ring_s + ((mdst + k) & kResMask), r_lds8(ring_s + ((msrc + k) & kResMask))); }
+            else if (mdist >= 32) {                                 // overlapping but every 32-byte slice reads bytes written by earlier slices
+                for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    if (k < mlen) r_sts8(ring_s + ((mdst + k) & kResMask), r_lds8(ring_s + ((msrc + k) & kResMask)));
+                    __syncwarp();
                 }
-                done = true;
-            }
+            } else { for (uint32_t k = lane; k < mlen; k += 32) r_sts8(ring_s + ((mdst + k) & kResMask), r_lds8(ring_s + ((msrc + k % mdist) & kResMask))); }
             __syncwarp();
-            pending = __ballot_sync(0xFFFFFFFFu, !done);
         }
         pos += total;
         const uint64_t boundary = pos & ~32767ull;

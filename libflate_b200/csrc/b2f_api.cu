@@ -940,8 +940,10 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 S.mem_out_off = PA.ptr<uint64_t>(a_oo);
                 S.tokens = ctx->buf[NB_SPEC_TOK].as<uint32_t>(); S.out = d_out;
                 S.res_err = PS.ptr<uint32_t>(s_err); S.res_len = PS.ptr<uint64_t>(s_len);
-                ctx->tm.mark(ctx->stream, "spec_write");
-                CK(spec_launch_write(S, (uint32_t)nsel, ctx->stream));
+                ctx->tm.mark(ctx->stream, "spec_tokens");
+                CK(spec_launch_tokens(S, (uint32_t)nsel, ctx->stream));
+                ctx->tm.mark(ctx->stream, "lz_resolve");
+                CK(spec_launch_resolve(S, (uint32_t)nsel, ctx->stream));
                 ctx->stats.kernel_launches += 2;
                 ctx->tm.mark(ctx->stream, "sync");
                 CK(ctx->pin_res.ensure((s_end - s_err) + 64));

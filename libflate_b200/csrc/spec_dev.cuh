@@ -25,5 +25,6 @@ struct SpecDev {
 };
 cudaError_t spec_init_attributes();
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st);
-cudaError_t spec_launch_write(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
+cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
+cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
 }

@@ -357,10 +357,13 @@ cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st
     k_spec_verify<<<S.n_blocks, 256, 0, st>>>(R);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_write(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
+cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
     if (!n_sel) return cudaSuccess;
     k_spec_tokens<<<S.n_ctas, kSpecCta, 0, st>>>(S);
-    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
+    if (!n_sel) return cudaSuccess;
     k_spec_resolve<<<n_sel, 32, kResRing, st>>>(S);
     return cudaGetLastError();
 }

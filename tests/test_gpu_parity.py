@@ -253,9 +253,10 @@ def test_decode_large_streams_block_parallel_path(ctx):
     before = ctx.stats()
     res = ctx.decode_batch(0, [cases[k] for k in names], caps=[len(plain[k]) + 64 for k in names])
     after = ctx.stats()
-    # the five libflate-style streams must really take the parallel path; the foreign / fixed / stored ones fall back
-    assert after["decode_parallel_streams"] - before["decode_parallel_streams"] == 5, (before, after)
-    assert after["decode_inorder_streams"] - before["decode_inorder_streams"] == 4
+    # the four compressible libflate-style streams must really take the parallel path; incompressible data (fixed-width
+    # codes never self-synchronise), foreign streams with cross-block references, fixed and stored blocks fall back
+    assert after["decode_parallel_streams"] - before["decode_parallel_streams"] == 4, (before, after)
+    assert after["decode_inorder_streams"] - before["decode_inorder_streams"] == 5
     for k, (st, out, used, _) in zip(names, res):
         assert st == 0, k
         assert out == plain[k], (k, len(out), len(plain[k]), next((i for i in range(min(len(out), len(plain[k]))) if out[i] != plain[k][i]), -1))

@@ -844,7 +844,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                          r_es = PB.reserve(ncand * 4), r_no = PB.reserve(ncand * 8), r_nt = PB.reserve(ncand * 8), r_end = PB.reserve(16);
             CK(PB.commit(ctx->stream));
             CK(ctx->buf[NB_SPEC_TAB].ensure(ncand * sizeof(InflateTables) + 256));
-            const size_t seg_bytes = (size_t)nseg * (6 * 4 + 2 * 8) + 8 * 256 + 1024;
+            const size_t seg_bytes = (size_t)nseg * (6 * 4 + 3 * 8) + 10 * 256 + 1024;
             CK(ctx->buf[NB_SPEC_SEG].ensure(seg_bytes));
             uint8_t *sp = ctx->buf[NB_SPEC_SEG].as<uint8_t>();
             S.in = d_in; S.in_off = PA.ptr<uint64_t>(a_io); S.in_len = PA.ptr<uint64_t>(a_il);
@@ -855,7 +855,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
             S.blk_eob_end = PB.ptr<uint32_t>(r_ee); S.blk_eob_seg = PB.ptr<uint32_t>(r_es); S.blk_nout = PB.ptr<uint64_t>(r_no); S.blk_ntok = PB.ptr<uint64_t>(r_nt);
             S.s_start = carve<uint32_t>(sp, nseg); S.s_exit = carve<uint32_t>(sp, nseg); S.s_exit_prev = carve<uint32_t>(sp, nseg);
             S.s_eob_end = carve<uint32_t>(sp, nseg); S.s_nsym = carve<uint32_t>(sp, nseg); S.s_nbytes = carve<uint32_t>(sp, nseg);
-            S.s_out_rel = carve<uint64_t>(sp, nseg); S.s_tok_rel = carve<uint64_t>(sp, nseg);
+            S.s_out_rel = carve<uint64_t>(sp, nseg); S.s_tok_rel = carve<uint64_t>(sp, nseg); S.s_min_src = carve<int64_t>(sp, nseg);
             S.changed = carve<uint32_t>(sp, 64);
             CK(cudaMemsetAsync(S.changed, 0, 256, ctx->stream));
             ctx->tm.mark(ctx->stream, "spec_parse");
@@ -934,26 +934,42 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 Packer PS(ctx->pin_sel, ctx->buf[NB_SPEC_SEL]);
                 const size_t s_sel = PS.add(blk_sel.data(), ncand * 4), s_o0 = PS.add(blk_out0.data(), ncand * 8), s_t0 = PS.add(blk_tok0.data(), ncand * 8),
                              s_lst = PS.add(sel_blocks.data(), nsel * 4);
-                const size_t s_err = PS.reserve(nsel * 4), s_len = PS.reserve(nsel * 8), s_end = PS.reserve(16);
+                // unit slots: a block of n output bytes can be cut into at most n / kUnitMinBytes + 1 independent LZ77 units
+                std::vector<uint32_t> unit0(nsel + 1, 0);
+                for (size_t k = 0; k < nsel; k++) unit0[k + 1] = unit0[k] + (uint32_t)(k_len[k] / kUnitMinBytes + 1);
+                const uint32_t nunits = unit0.back();
+                const size_t s_u0 = PS.add(unit0.data(), (nsel + 1) * 4);
+                const size_t s_uo = PS.reserve((size_t)nunits * 8), s_ut = PS.reserve((size_t)nunits * 8), s_un = PS.reserve((size_t)nunits * 8),
+                             s_ub = PS.reserve((size_t)nunits * 8), s_uk = PS.reserve((size_t)nunits * 4);
+                const size_t s_err = PS.reserve((size_t)nunits * 4), s_len = PS.reserve((size_t)nunits * 8), s_end = PS.reserve(16);
                 CK(PS.commit(ctx->stream));
                 S.blk_sel = PS.ptr<uint32_t>(s_sel); S.blk_out0 = PS.ptr<uint64_t>(s_o0); S.blk_tok0 = PS.ptr<uint64_t>(s_t0); S.sel_blocks = PS.ptr<uint32_t>(s_lst);
                 S.mem_out_off = PA.ptr<uint64_t>(a_oo);
                 S.tokens = ctx->buf[NB_SPEC_TOK].as<uint32_t>(); S.out = d_out;
+                S.sel_unit0 = PS.ptr<uint32_t>(s_u0); S.unit_out = PS.ptr<uint64_t>(s_uo); S.unit_tok = PS.ptr<uint64_t>(s_ut); S.unit_ntok = PS.ptr<uint64_t>(s_un);
+                S.unit_nout = PS.ptr<uint64_t>(s_ub); S.unit_blk = PS.ptr<uint32_t>(s_uk);
                 S.res_err = PS.ptr<uint32_t>(s_err); S.res_len = PS.ptr<uint64_t>(s_len);
                 ctx->tm.mark(ctx->stream, "spec_tokens");
                 CK(spec_launch_tokens(S, (uint32_t)nsel, ctx->stream));
                 ctx->tm.mark(ctx->stream, "lz_resolve");
-                CK(spec_launch_resolve(S, (uint32_t)nsel, ctx->stream));
-                ctx->stats.kernel_launches += 2;
+                CK(spec_launch_resolve(S, (uint32_t)nsel, nunits, ctx->stream));
+                ctx->stats.kernel_launches += 3;
                 ctx->tm.mark(ctx->stream, "sync");
-                CK(ctx->pin_res.ensure((s_end - s_err) + 64));
+                const size_t rb = s_end - s_ub;                      // unit_nout | unit_blk | res_err | res_len
+                CK(ctx->pin_res.ensure(rb + 64));
                 uint8_t *hr2 = ctx->pin_res.as<uint8_t>();
-                CK(cudaMemcpyAsync(hr2, PS.ptr<uint8_t>(s_err), s_end - s_err, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(hr2, PS.ptr<uint8_t>(s_ub), rb, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
-                const uint32_t *h_err = (const uint32_t *)hr2; const uint64_t *h_len = (const uint64_t *)(hr2 + (s_len - s_err));
-                // a block whose matches reach before its own start (foreign stream) or an inconsistent size: redo the member in order
+                const uint64_t *h_un = (const uint64_t *)hr2; const uint32_t *h_ub = (const uint32_t *)(hr2 + (s_uk - s_ub));
+                const uint32_t *h_err = (const uint32_t *)(hr2 + (s_err - s_ub)); const uint64_t *h_len = (const uint64_t *)(hr2 + (s_len - s_ub));
+                // a unit whose matches reach before its own start (foreign stream with cross-block references) or an inconsistent
+                // size: redo the member with the in-order kernel
                 std::vector<char> redo(n, 0);
-                for (size_t k = 0; k < nsel; k++) if (h_err[k] || h_len[k] != k_len[k]) redo[cands[sel_blocks[k]].first] = 1;
+                for (size_t k = 0; k < nsel; k++) {
+                    uint64_t sum = 0; bool bad = false;
+                    for (uint32_t u = unit0[k]; u < unit0[k + 1]; u++) if (h_ub[u] != 0xFFFFFFFFu) { sum += h_len[u]; if (h_err[u] || h_len[u] != h_un[u]) bad = true; }
+                    if (bad || sum != k_len[k]) redo[cands[sel_blocks[k]].first] = 1;
+                }
                 for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; serial_spec.push_back(m); }
             }
         }

@@ -80,7 +80,7 @@ constexpr uint32_t kExitEob = 0xFFFFFFFFu, kExitBad = 0xFFFFFFFEu, kExitDead = 0
 // kEmit: writes one token per symbol to tok[].  Returns the exit code (kExit* or 0 = ran to stop).
 template <bool kEmit>
 __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T, uint64_t stop_abs, uint32_t &nsym, uint32_t &nbytes,
-                                                uint32_t *__restrict__ tok) {
+                                                uint32_t *__restrict__ tok, int64_t out_rel0 = 0, int64_t *min_src = nullptr) {
     for (;;) {
         if (t.pos >= stop_abs) return 0;
         tb_refill(t);
@@ -106,7 +106,11 @@ __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T
         const uint32_t deb = (d >> 24) & 15u;
         const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(t.bb >> wd)) & ((1u << deb) - 1u));
         tb_skip(t, wd + deb);
-        if (kEmit) tok[nsym] = kSymPtr | (len << 16) | dist;
+        if (kEmit) {
+            tok[nsym] = kSymPtr | (len << 16) | dist;
+            const int64_t src = out_rel0 + (int64_t)nbytes - (int64_t)dist;
+            if (src < *min_src) *min_src = src;
+        }
         nsym++; nbytes += len;
     }
 }
@@ -252,13 +256,50 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
     const uint64_t blk_abs = S.blk_bit[b] + 8ull * lead, blk_len = S.blk_end[b] - S.blk_bit[b];
     const uint32_t start = S.s_start[sg];
     const uint64_t seg_end = min((uint64_t)(k + 1) * kSpecBits, blk_len);
-    if (start >= seg_end) return;
+    if (start >= seg_end) { S.s_min_src[sg] = INT64_MAX; return; }      // no symbol starts in this subsegment
     TBits t;
     t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
     t.nwords = (S.in_len[m] + lead + 3) >> 2;
     tb_seek(t, blk_abs + start);
     uint32_t nsym = 0, nbytes = 0;
-    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg]);
+    int64_t min_src = INT64_MAX;
+    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg], (int64_t)S.s_out_rel[sg], &min_src);
+    S.s_min_src[sg] = min_src;
+}
+
+// ---------------------------------------------------------------------------------- independent LZ77 units inside a block
+// A subsegment boundary is a cut point when no later match of the block reaches back across it (libflate's 256 KiB LZ77
+// chunks never reference each other: libflate_lz77/src/default.rs:73,108).  Units between cut points resolve in parallel.
+__global__ void __launch_bounds__(32) k_spec_units(SpecDev S) {
+    const uint32_t b = S.sel_blocks[blockIdx.x];
+    if (threadIdx.x != 0) return;
+    const uint32_t s0 = S.blk_seg0[b];
+    const uint32_t k0 = S.blk_data_rel[b] / kSpecBits, e = S.blk_eob_seg[b];
+    const uint32_t u0 = S.sel_unit0[blockIdx.x], umax = S.sel_unit0[blockIdx.x + 1] - u0;
+    const uint64_t nout = S.blk_nout[b], ntok = S.blk_ntok[b];
+    // walk right to left keeping the suffix minimum of referenced sources; cut where suffix_min >= start of the subsegment,
+    // keeping units at least kUnitMinBytes long
+    uint32_t nu = 0;
+    int64_t suf = INT64_MAX;
+    uint64_t unit_end_out = nout, unit_end_tok = ntok;
+    // temporary: cuts are produced right-to-left into the slots from the back, then compacted to the front
+    for (uint32_t k = e + 1; k-- > k0;) {
+        const int64_t ms = S.s_min_src[s0 + k];
+        if (ms < suf) suf = ms;
+        const uint64_t o = S.s_out_rel[s0 + k], tkn = S.s_tok_rel[s0 + k];
+        const bool can_cut = k > k0 && suf >= (int64_t)o;
+        if (k == k0 || (can_cut && unit_end_out - o >= kUnitMinBytes && nu + 1 < umax)) {
+            const uint32_t slot = u0 + umax - 1 - nu;
+            S.unit_out[slot] = o; S.unit_tok[slot] = tkn; S.unit_ntok[slot] = unit_end_tok - tkn; S.unit_nout[slot] = unit_end_out - o; S.unit_blk[slot] = b;
+            unit_end_out = o; unit_end_tok = tkn; nu++;
+        }
+    }
+    // compact to the front of the block's slot range (order does not matter for correctness); mark the rest empty
+    for (uint32_t i = 0; i < nu; i++) {
+        const uint32_t from = u0 + umax - nu + i, to = u0 + i;
+        if (from != to) { S.unit_out[to] = S.unit_out[from]; S.unit_tok[to] = S.unit_tok[from]; S.unit_ntok[to] = S.unit_ntok[from]; S.unit_nout[to] = S.unit_nout[from]; S.unit_blk[to] = S.unit_blk[from]; }
+    }
+    for (uint32_t i = nu; i < umax; i++) S.unit_blk[u0 + i] = 0xFFFFFFFFu;
 }
 
 // ---------------------------------------------------------------------------------- LZ77 resolution (warp per block)
@@ -271,16 +312,17 @@ constexpr uint32_t kResRing = 65536, kResMask = kResRing - 1;
 __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
     extern __shared__ __align__(16) uint8_t ring[];
     const uint32_t lane = threadIdx.x;
-    const uint32_t b = S.sel_blocks[blockIdx.x];
-    const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b];
-    const uint64_t ntok = S.blk_ntok[b];
-    const uint64_t out0 = S.blk_out0[b];                        // absolute offset in S.out of the block's first byte
+    const uint32_t u = blockIdx.x;
+    const uint32_t b = S.unit_blk[u];
+    if (b == 0xFFFFFFFFu) return;                                // unused slot
+    const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b] + S.unit_tok[u];
+    const uint64_t ntok = S.unit_ntok[u];
+    const uint64_t out0 = S.blk_out0[b] + S.unit_out[u];        // absolute offset in S.out of the unit's first byte
     const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
     uint8_t *__restrict__ g = S.out;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     uint64_t pos = out0, flushed = out0;
     uint32_t err = 0;
-    uint32_t tnext = ntok ? (lane < ntok ? __ldg(tok + lane) : 0u) : 0u;
+    uint32_t tnext = lane < ntok ? __ldg(tok + lane) : 0u;
     for (uint64_t i0 = 0; i0 < ntok; i0 += 32) {
         const uint32_t tk = tnext;
         const uint64_t in = i0 + 32 + lane;
@@ -293,9 +335,9 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const uint64_t dst = pos + incl - len;
         const uint32_t dst32 = (uint32_t)dst;
-        if (live && !is_m) r_sts8(ring_s + (dst32 & kResMask), tk & 0xFFu);
+        if (live && !is_m) ring[dst32 & kResMask] = (uint8_t)tk;
         const uint32_t dist = tk & 0xFFFFu;
-        if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the block (1) / before the stream (2)
+        if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
         __syncwarp();
         // matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on the
         // bytes written just before them, so resolving them independently buys nothing)
@@ -307,14 +349,14 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
             const uint32_t mtk = __shfl_sync(0xFFFFFFFFu, tk, j);
             const uint32_t mlen = (mtk >> 16) & 0x1FFu, mdist = mtk & 0xFFFFu;
             const uint32_t msrc = mdst - mdist;
-            if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) r_sts8(ring_s + ((mdst + k) & kResMask), r_lds8(ring_s + ((msrc + k) & kResMask))); }
-            else if (mdist >= 32) {                                 // overlapping but every 32-byte slice reads bytes written by earlier slices
+            if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) ring[(mdst + k) & kResMask] = ring[(msrc + k) & kResMask]; }
+            else if (mdist >= 32) {                                 // overlapping, but each 32-byte slice only reads bytes of earlier slices
                 for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
                     const uint32_t k = k0 + lane;
-                    if (k < mlen) r_sts8(ring_s + ((mdst + k) & kResMask), r_lds8(ring_s + ((msrc + k) & kResMask)));
+                    if (k < mlen) ring[(mdst + k) & kResMask] = ring[(msrc + k) & kResMask];
                     __syncwarp();
                 }
-            } else { for (uint32_t k = lane; k < mlen; k += 32) r_sts8(ring_s + ((mdst + k) & kResMask), r_lds8(ring_s + ((msrc + k % mdist) & kResMask))); }
+            } else { for (uint32_t k = lane; k < mlen; k += 32) ring[(mdst + k) & kResMask] = ring[(msrc + k % mdist) & kResMask]; }
             __syncwarp();
         }
         pos += total;
@@ -322,18 +364,18 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
         if (boundary > flushed) {
             __syncwarp();
             if (((flushed | boundary) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 3) == 0) {
-                for (uint64_t i = flushed + 4ull * lane; i < boundary; i += 128) *reinterpret_cast<uint32_t *>(g + i) = r_lds32(ring_s + ((uint32_t)i & kResMask));
+                for (uint64_t i = flushed + 4ull * lane; i < boundary; i += 128) *reinterpret_cast<uint32_t *>(g + i) = *reinterpret_cast<const uint32_t *>(ring + ((uint32_t)i & kResMask));
             } else {
-                for (uint64_t i = flushed + lane; i < boundary; i += 32) g[i] = (uint8_t)r_lds8(ring_s + ((uint32_t)i & kResMask));
+                for (uint64_t i = flushed + lane; i < boundary; i += 32) g[i] = ring[(uint32_t)i & kResMask];
             }
             flushed = boundary;
             __syncwarp();
         }
     }
     __syncwarp();
-    for (uint64_t i = flushed + lane; i < pos; i += 32) g[i] = (uint8_t)r_lds8(ring_s + ((uint32_t)i & kResMask));
+    for (uint64_t i = flushed + lane; i < pos; i += 32) g[i] = ring[(uint32_t)i & kResMask];
     err = __reduce_or_sync(0xFFFFFFFFu, err);
-    if (lane == 0) { S.res_err[blockIdx.x] = err; S.res_len[blockIdx.x] = pos - out0; }
+    if (lane == 0) { S.res_err[u] = err; S.res_len[u] = pos - out0; }
 }
 
 // ---------------------------------------------------------------------------------- launchers
@@ -362,9 +404,11 @@ cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st
     k_spec_tokens<<<S.n_ctas, kSpecCta, 0, st>>>(S);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
+cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t n_sel, uint32_t n_units, cudaStream_t st) {
     if (!n_sel) return cudaSuccess;
-    k_spec_resolve<<<n_sel, 32, kResRing, st>>>(S);
+    k_spec_units<<<n_sel, 32, 0, st>>>(S);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_spec_resolve<<<n_units, 32, kResRing, st>>>(S);
     return cudaGetLastError();
 }
 

@@ -80,7 +80,7 @@ constexpr uint32_t kExitEob = 0xFFFFFFFFu, kExitBad = 0xFFFFFFFEu, kExitDead = 0
 // kEmit: writes one token per symbol to tok[].  Returns the exit code (kExit* or 0 = ran to stop).
 template <bool kEmit>
 __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T, uint64_t stop_abs, uint32_t &nsym, uint32_t &nbytes,
-                                                uint32_t *__restrict__ tok, int64_t out_rel0 = 0, int64_t *min_src = nullptr) {
+                                                uint32_t *__restrict__ tok, int32_t &min_rel) {
     for (;;) {
         if (t.pos >= stop_abs) return 0;
         tb_refill(t);
@@ -108,8 +108,8 @@ __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T
         tb_skip(t, wd + deb);
         if (kEmit) {
             tok[nsym] = kSymPtr | (len << 16) | dist;
-            const int64_t src = out_rel0 + (int64_t)nbytes - (int64_t)dist;
-            if (src < *min_src) *min_src = src;
+            const int32_t src = (int32_t)nbytes - (int32_t)dist;          // relative to the subsegment's first output byte
+            if (src < min_rel) min_rel = src;
         }
         nsym++; nbytes += len;
     }
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_round(SpecDev S, uint32_t rou
     if (start >= seg_end) ex = start;                            // the neighbour's last symbol already covers this subsegment
     else {
         tb_seek(t, blk_abs + start);
-        const uint32_t r = spec_decode<false>(t, Ts, blk_abs + seg_end, nsym, nbytes, nullptr);
+        int32_t dummy = 0;
+        const uint32_t r = spec_decode<false>(t, Ts, blk_abs + seg_end, nsym, nbytes, nullptr, dummy);
         if (r == kExitEob) { ex = kExitEob; S.s_eob_end[sg] = (uint32_t)(t.pos - blk_abs); }
         else if (r == kExitBad) ex = kExitBad;
         else ex = (uint32_t)(t.pos - blk_abs);
@@ -262,9 +263,9 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
     t.nwords = (S.in_len[m] + lead + 3) >> 2;
     tb_seek(t, blk_abs + start);
     uint32_t nsym = 0, nbytes = 0;
-    int64_t min_src = INT64_MAX;
-    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg], (int64_t)S.s_out_rel[sg], &min_src);
-    S.s_min_src[sg] = min_src;
+    int32_t min_rel = INT32_MAX;
+    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg], min_rel);
+    S.s_min_src[sg] = min_rel == INT32_MAX ? INT64_MAX : (int64_t)S.s_out_rel[sg] + min_rel;
 }
 
 // ---------------------------------------------------------------------------------- independent LZ77 units inside a block
@@ -277,24 +278,37 @@ __global__ void __launch_bounds__(32) k_spec_units(SpecDev S) {
     const uint32_t k0 = S.blk_data_rel[b] / kSpecBits, e = S.blk_eob_seg[b];
     const uint32_t u0 = S.sel_unit0[blockIdx.x], umax = S.sel_unit0[blockIdx.x + 1] - u0;
     const uint64_t nout = S.blk_nout[b], ntok = S.blk_ntok[b];
-    // walk right to left keeping the suffix minimum of referenced sources; cut where suffix_min >= start of the subsegment,
-    // keeping units at least kUnitMinBytes long
+    const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b];
+    // Right to left over the subsegments with `after` = lowest position read by any token of LATER subsegments.  A cut can
+    // only lie inside subsegment k when after >= start(k); the exact token is found by walking k's tokens backwards.
     uint32_t nu = 0;
-    int64_t suf = INT64_MAX;
+    int64_t after = INT64_MAX;
     uint64_t unit_end_out = nout, unit_end_tok = ntok;
-    // temporary: cuts are produced right-to-left into the slots from the back, then compacted to the front
+    auto emit = [&](uint64_t o, uint64_t tkn) {
+        const uint32_t slot = u0 + umax - 1 - nu;
+        S.unit_out[slot] = o; S.unit_tok[slot] = tkn; S.unit_ntok[slot] = unit_end_tok - tkn; S.unit_nout[slot] = unit_end_out - o; S.unit_blk[slot] = b;
+        unit_end_out = o; unit_end_tok = tkn; nu++;
+    };
     for (uint32_t k = e + 1; k-- > k0;) {
-        const int64_t ms = S.s_min_src[s0 + k];
-        if (ms < suf) suf = ms;
-        const uint64_t o = S.s_out_rel[s0 + k], tkn = S.s_tok_rel[s0 + k];
-        const bool can_cut = k > k0 && suf >= (int64_t)o;
-        if (k == k0 || (can_cut && unit_end_out - o >= kUnitMinBytes && nu + 1 < umax)) {
-            const uint32_t slot = u0 + umax - 1 - nu;
-            S.unit_out[slot] = o; S.unit_tok[slot] = tkn; S.unit_ntok[slot] = unit_end_tok - tkn; S.unit_nout[slot] = unit_end_out - o; S.unit_blk[slot] = b;
-            unit_end_out = o; unit_end_tok = tkn; nu++;
+        const uint64_t o = S.s_out_rel[s0 + k], t0 = S.s_tok_rel[s0 + k];
+        const uint64_t o_next = k == e ? nout : S.s_out_rel[s0 + k + 1], t_next = k == e ? ntok : S.s_tok_rel[s0 + k + 1];
+        if (k > k0 && after >= (int64_t)o && unit_end_out - o >= kUnitMinBytes && nu + 1 < umax && t_next > t0) {
+            // walk the tokens of subsegment k backwards: cut before token t iff every token >= t reads at or after dst(t)
+            int64_t run = after; uint64_t dst_end = o_next;
+            for (uint64_t t = t_next; t-- > t0;) {
+                const uint32_t tk = tok[t];
+                const uint32_t len = (tk & kSymPtr) ? (tk >> 16) & 0x1FFu : 1u;
+                const uint64_t dst = dst_end - len;
+                if (tk & kSymPtr) { const int64_t src = (int64_t)dst - (int64_t)(tk & 0xFFFFu); if (src < run) run = src; }
+                if (run >= (int64_t)dst && unit_end_out - dst >= kUnitMinBytes && (t > t0 || k > k0)) { emit(dst, t); break; }
+                dst_end = dst;
+            }
         }
+        const int64_t ms = S.s_min_src[s0 + k];
+        if (ms < after) after = ms;
     }
-    // compact to the front of the block's slot range (order does not matter for correctness); mark the rest empty
+    emit(S.s_out_rel[s0 + k0], S.s_tok_rel[s0 + k0]);             // the block's first unit
+    // compact to the front of the block's slot range (order does not matter); mark the rest empty
     for (uint32_t i = 0; i < nu; i++) {
         const uint32_t from = u0 + umax - nu + i, to = u0 + i;
         if (from != to) { S.unit_out[to] = S.unit_out[from]; S.unit_tok[to] = S.unit_tok[from]; S.unit_ntok[to] = S.unit_ntok[from]; S.unit_nout[to] = S.unit_nout[from]; S.unit_blk[to] = S.unit_blk[from]; }

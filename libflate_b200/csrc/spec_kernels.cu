@@ -75,12 +75,26 @@ __device__ __forceinline__ void tb_refill(TBits &t) {
 __device__ __forceinline__ void tb_skip(TBits &t, uint32_t n) { t.bb >>= n; t.bc -= n; t.pos += n; }
 
 constexpr uint32_t kExitEob = 0xFFFFFFFFu, kExitBad = 0xFFFFFFFEu, kExitDead = 0xFFFFFFFDu;
+constexpr uint32_t kTokSkip = 0x7FFFFFFFu;      // padding token (produces no output)
 
 // Decodes symbols from t.pos until t.pos >= stop_abs, EndOfBlock or an undecodable pattern.
 // kEmit: writes one token per symbol to tok[].  Returns the exit code (kExit* or 0 = ran to stop).
+// Token sink of the final pass: 8 tokens (one 32-byte sector) are staged in shared memory per thread and written with two
+// 16-byte stores, so HBM sees full sectors instead of 4-byte read-modify-writes.
+struct TokSink {
+    uint32_t *stage;            // 8 words in shared memory (per thread)
+    uint4 *gout;                // 32-byte aligned destination
+    uint32_t n;
+    __device__ __forceinline__ void put(uint32_t v) {
+        stage[n & 7u] = v; n++;
+        if ((n & 7u) == 0) { const uint4 *s4 = reinterpret_cast<const uint4 *>(stage); gout[0] = s4[0]; gout[1] = s4[1]; gout += 2; }
+    }
+    __device__ __forceinline__ void finish() { while (n & 7u) put(kTokSkip); }
+};
+
 template <bool kEmit>
 __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T, uint64_t stop_abs, uint32_t &nsym, uint32_t &nbytes,
-                                                uint32_t *__restrict__ tok, int32_t &min_rel) {
+                                                TokSink *tok, int32_t &min_rel) {
     for (;;) {
         if (t.pos >= stop_abs) return 0;
         tb_refill(t);
@@ -90,7 +104,7 @@ __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T
         if (w == 0 || kind == kKindSpecial) return kExitBad;
         if (kind == kKindLit) {
             tb_skip(t, w);
-            if (kEmit) tok[nsym] = e >> 8;
+            if (kEmit) tok->put(e >> 8);
             nsym++; nbytes++;
             continue;
         }
@@ -107,7 +121,7 @@ __device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T
         const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(t.bb >> wd)) & ((1u << deb) - 1u));
         tb_skip(t, wd + deb);
         if (kEmit) {
-            tok[nsym] = kSymPtr | (len << 16) | dist;
+            tok->put(kSymPtr | (len << 16) | dist);
             const int32_t src = (int32_t)nbytes - (int32_t)dist;          // relative to the subsegment's first output byte
             if (src < min_rel) min_rel = src;
         }
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(256) k_spec_verify(SpecDev S) {
     for (uint32_t base = k0; base <= e; base += 256) {
         const uint32_t k = base + tid;
         const bool in = k <= e;
-        const uint64_t xb = in ? S.s_nbytes[s0 + k] : 0, xs = in ? S.s_nsym[s0 + k] : 0;
+        const uint64_t xb = in ? S.s_nbytes[s0 + k] : 0, xs = in ? ((uint64_t)S.s_nsym[s0 + k] + 7) & ~7ull : 0;   // token regions are padded to 8
         uint64_t ib = xb, is = xs;
         for (int d = 1; d < 32; d <<= 1) {
             const uint64_t tb = __shfl_up_sync(0xFFFFFFFFu, ib, d), ts = __shfl_up_sync(0xFFFFFFFFu, is, d);
@@ -243,6 +257,7 @@ __global__ void __launch_bounds__(256) k_spec_verify(SpecDev S) {
 // ---------------------------------------------------------------------------------- final decode -> tokens
 __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
     __shared__ __align__(16) InflateTables Ts;
+    __shared__ __align__(16) uint32_t stage[kSpecCta * 8];
     const uint32_t b = owner_u32(S.blk_cta0, S.n_blocks, blockIdx.x);
     if (S.blk_sel[b] == 0) return;                               // not on the verified chain
     load_tables_smem(Ts, S.tabs + b);
@@ -264,7 +279,9 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
     tb_seek(t, blk_abs + start);
     uint32_t nsym = 0, nbytes = 0;
     int32_t min_rel = INT32_MAX;
-    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg], min_rel);
+    TokSink sink = { stage + threadIdx.x * 8, reinterpret_cast<uint4 *>(S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg]), 0 };
+    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, &sink, min_rel);
+    sink.finish();
     S.s_min_src[sg] = min_rel == INT32_MAX ? INT64_MAX : (int64_t)S.s_out_rel[sg] + min_rel;
 }
 
@@ -297,10 +314,10 @@ __global__ void __launch_bounds__(32) k_spec_units(SpecDev S) {
             int64_t run = after; uint64_t dst_end = o_next;
             for (uint64_t t = t_next; t-- > t0;) {
                 const uint32_t tk = tok[t];
-                const uint32_t len = (tk & kSymPtr) ? (tk >> 16) & 0x1FFu : 1u;
+                const uint32_t len = (tk & kSymPtr) ? (tk >> 16) & 0x1FFu : (tk == kTokSkip ? 0u : 1u);
                 const uint64_t dst = dst_end - len;
                 if (tk & kSymPtr) { const int64_t src = (int64_t)dst - (int64_t)(tk & 0xFFFFu); if (src < run) run = src; }
-                if (run >= (int64_t)dst && unit_end_out - dst >= kUnitMinBytes && (t > t0 || k > k0)) { emit(dst, t); break; }
+                if (len && run >= (int64_t)dst && unit_end_out - dst >= kUnitMinBytes && (t > t0 || k > k0)) { emit(dst, t); break; }
                 dst_end = dst;
             }
         }
@@ -321,7 +338,10 @@ __device__ __forceinline__ uint32_t r_lds8(uint32_t a) { uint32_t v; asm volatil
 __device__ __forceinline__ void r_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
-constexpr uint32_t kResRing = 65536, kResMask = kResRing - 1;
+// The ring keeps the most recent kResRing bytes; every step is written through to HBM, so sources older than the ring are
+// read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
+constexpr uint32_t kResRing = 24576;
+__device__ __forceinline__ uint32_t rix(uint32_t a) { return a % kResRing; }
 
 __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
     extern __shared__ __align__(16) uint8_t ring[];
@@ -334,14 +354,14 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
     const uint64_t out0 = S.blk_out0[b] + S.unit_out[u];        // absolute offset in S.out of the unit's first byte
     const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
     uint8_t *__restrict__ g = S.out;
-    uint64_t pos = out0, flushed = out0;
+    uint64_t pos = out0;
     uint32_t err = 0;
     uint32_t tnext = lane < ntok ? __ldg(tok + lane) : 0u;
     for (uint64_t i0 = 0; i0 < ntok; i0 += 32) {
         const uint32_t tk = tnext;
         const uint64_t in = i0 + 32 + lane;
         tnext = in < ntok ? __ldg(tok + in) : 0u;                // prefetch the next step's tokens
-        const bool live = i0 + lane < ntok;
+        const bool live = i0 + lane < ntok && tk != kTokSkip;
         const bool is_m = live && (tk & kSymPtr);
         const uint32_t len = !live ? 0u : is_m ? (tk >> 16) & 0x1FFu : 1u;
         uint32_t incl = len;
@@ -349,9 +369,10 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const uint64_t dst = pos + incl - len;
         const uint32_t dst32 = (uint32_t)dst;
-        if (live && !is_m) ring[dst32 & kResMask] = (uint8_t)tk;
+        if (live && !is_m) ring[rix(dst32)] = (uint8_t)tk;
         const uint32_t dist = tk & 0xFFFFu;
         if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
+        const uint32_t step_end = (uint32_t)pos + total;
         __syncwarp();
         // matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on the
         // bytes written just before them, so resolving them independently buys nothing)
@@ -363,31 +384,24 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
             const uint32_t mtk = __shfl_sync(0xFFFFFFFFu, tk, j);
             const uint32_t mlen = (mtk >> 16) & 0x1FFu, mdist = mtk & 0xFFFFu;
             const uint32_t msrc = mdst - mdist;
-            if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) ring[(mdst + k) & kResMask] = ring[(msrc + k) & kResMask]; }
+            if ((int32_t)(step_end - msrc) > (int32_t)kResRing) {   // source older than the ring: it was written through to HBM (never overlaps: dist > len)
+                const uint8_t *gs = g + (pos + (uint32_t)(mdst - (uint32_t)pos)) - mdist;   // exact 64-bit source address
+                for (uint32_t k = lane; k < mlen; k += 32) ring[rix(mdst + k)] = __ldcg(gs + k);
+            } else if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) ring[rix(mdst + k)] = ring[rix(msrc + k)]; }
             else if (mdist >= 32) {                                 // overlapping, but each 32-byte slice only reads bytes of earlier slices
                 for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
                     const uint32_t k = k0 + lane;
-                    if (k < mlen) ring[(mdst + k) & kResMask] = ring[(msrc + k) & kResMask];
+                    if (k < mlen) ring[rix(mdst + k)] = ring[rix(msrc + k)];
                     __syncwarp();
                 }
-            } else { for (uint32_t k = lane; k < mlen; k += 32) ring[(mdst + k) & kResMask] = ring[(msrc + k % mdist) & kResMask]; }
+            } else { for (uint32_t k = lane; k < mlen; k += 32) ring[rix(mdst + k)] = ring[rix(msrc + k % mdist)]; }
             __syncwarp();
         }
+        // write the step through to HBM
+        for (uint32_t k = lane; k < total; k += 32) g[pos + k] = ring[rix((uint32_t)pos + k)];
         pos += total;
-        const uint64_t boundary = pos & ~32767ull;
-        if (boundary > flushed) {
-            __syncwarp();
-            if (((flushed | boundary) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 3) == 0) {
-                for (uint64_t i = flushed + 4ull * lane; i < boundary; i += 128) *reinterpret_cast<uint32_t *>(g + i) = *reinterpret_cast<const uint32_t *>(ring + ((uint32_t)i & kResMask));
-            } else {
-                for (uint64_t i = flushed + lane; i < boundary; i += 32) g[i] = ring[(uint32_t)i & kResMask];
-            }
-            flushed = boundary;
-            __syncwarp();
-        }
+        __syncwarp();
     }
-    __syncwarp();
-    for (uint64_t i = flushed + lane; i < pos; i += 32) g[i] = ring[(uint32_t)i & kResMask];
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) { S.res_err[u] = err; S.res_len[u] = pos - out0; }
 }

@@ -92,41 +92,52 @@ struct TokSink {
     __device__ __forceinline__ void finish() { while (n & 7u) put(kTokSkip); }
 };
 
+// Decodes symbols from t.pos until t.pos >= stop_abs, EndOfBlock or an undecodable pattern.
+// The loop is WARP-UNIFORM: every lane of `mask` iterates until all of them are done, one symbol per iteration, so the
+// lanes re-converge after every symbol (independent per-lane loops drift apart and end up fully serialised).
+// `run` = this lane has work.  kEmit: writes one token per symbol.  Returns the exit code (kExit* or 0 = ran to stop).
 template <bool kEmit>
-__device__ __forceinline__ uint32_t spec_decode(TBits &t, const InflateTables &T, uint64_t stop_abs, uint32_t &nsym, uint32_t &nbytes,
-                                                TokSink *tok, int32_t &min_rel) {
-    for (;;) {
-        if (t.pos >= stop_abs) return 0;
-        tb_refill(t);
-        uint32_t e = T.lit[(uint32_t)t.bb & ((1u << kLitBits) - 1u)];
-        if ((e & 15u) == 0) e = lookup_code(T, true, (uint32_t)t.bb & 0x7FFFu);     // long code or unassigned
-        const uint32_t w = e & 15u, kind = (e >> 4) & 3u;
-        if (w == 0 || kind == kKindSpecial) return kExitBad;
-        if (kind == kKindLit) {
-            tb_skip(t, w);
-            if (kEmit) tok->put(e >> 8);
-            nsym++; nbytes++;
-            continue;
+__device__ __forceinline__ uint32_t spec_decode(uint32_t mask, bool run, TBits &t, const InflateTables &T, uint64_t stop_abs,
+                                                uint32_t &nsym, uint32_t &nbytes, TokSink *tok, int32_t &min_rel) {
+    uint32_t result = 0;
+    bool active = run && t.pos < stop_abs;
+    while (__any_sync(mask, active)) {
+        if (active) {
+            tb_refill(t);
+            uint32_t e = T.lit[(uint32_t)t.bb & ((1u << kLitBits) - 1u)];
+            if ((e & 15u) == 0) e = lookup_code(T, true, (uint32_t)t.bb & 0x7FFFu);     // long code or unassigned
+            const uint32_t w = e & 15u, kind = (e >> 4) & 3u;
+            if (w == 0 || kind == kKindSpecial) { result = kExitBad; active = false; }
+            else if (kind == kKindLit) {
+                tb_skip(t, w);
+                if (kEmit) tok->put(e >> 8);
+                nsym++; nbytes++;
+            } else if (kind == kKindEob) { tb_skip(t, w); result = kExitEob; active = false; }
+            else {
+                const uint32_t eb = (e >> 20) & 15u;
+                const uint32_t len = ((e >> 8) & 0x1FFu) + (((uint32_t)(t.bb >> w)) & ((1u << eb) - 1u));
+                tb_skip(t, w + eb);
+                tb_refill(t);
+                uint32_t d = T.dist[(uint32_t)t.bb & ((1u << kDistBits) - 1u)];
+                if ((d & 15u) == 0) d = lookup_code(T, false, (uint32_t)t.bb & 0x7FFFu);
+                const uint32_t wd = d & 15u;
+                if (wd == 0) { result = kExitBad; active = false; }
+                else {
+                    const uint32_t deb = (d >> 24) & 15u;
+                    const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(t.bb >> wd)) & ((1u << deb) - 1u));
+                    tb_skip(t, wd + deb);
+                    if (kEmit) {
+                        tok->put(kSymPtr | (len << 16) | dist);
+                        const int32_t src = (int32_t)nbytes - (int32_t)dist;          // relative to the subsegment's first output byte
+                        if (src < min_rel) min_rel = src;
+                    }
+                    nsym++; nbytes += len;
+                }
+            }
+            if (active && t.pos >= stop_abs) active = false;
         }
-        if (kind == kKindEob) { tb_skip(t, w); return kExitEob; }
-        const uint32_t eb = (e >> 20) & 15u;
-        const uint32_t len = ((e >> 8) & 0x1FFu) + (((uint32_t)(t.bb >> w)) & ((1u << eb) - 1u));
-        tb_skip(t, w + eb);
-        tb_refill(t);
-        uint32_t d = T.dist[(uint32_t)t.bb & ((1u << kDistBits) - 1u)];
-        if ((d & 15u) == 0) d = lookup_code(T, false, (uint32_t)t.bb & 0x7FFFu);
-        const uint32_t wd = d & 15u;
-        if (wd == 0) return kExitBad;
-        const uint32_t deb = (d >> 24) & 15u;
-        const uint32_t dist = ((d >> 8) & 0xFFFFu) + (((uint32_t)(t.bb >> wd)) & ((1u << deb) - 1u));
-        tb_skip(t, wd + deb);
-        if (kEmit) {
-            tok->put(kSymPtr | (len << 16) | dist);
-            const int32_t src = (int32_t)nbytes - (int32_t)dist;          // relative to the subsegment's first output byte
-            if (src < min_rel) min_rel = src;
-        }
-        nsym++; nbytes += len;
     }
+    return result;
 }
 
 __device__ __forceinline__ uint32_t owner_u32(const uint32_t *__restrict__ prefix, uint32_t n, uint32_t idx) {
@@ -154,42 +165,48 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_round(SpecDev S, uint32_t rou
     load_tables_smem(Ts, S.tabs + b);
     const uint32_t nseg = S.blk_seg0[b + 1] - S.blk_seg0[b];
     const uint32_t k = (blockIdx.x - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
-    if (k >= nseg) return;
-    const uint32_t sg = S.blk_seg0[b] + k;
+    const uint32_t sg = S.blk_seg0[b] + min(k, nseg - 1);
     const uint32_t k0 = data_rel / kSpecBits;
-    if (k < k0) { S.s_start[sg] = kExitDead; S.s_exit[sg] = kExitDead; return; }       // header bits only
     const uint32_t m = S.blk_member[b];
     const uint8_t *p0 = S.in + S.in_off[m];
     const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
     const uint64_t blk_abs = S.blk_bit[b] + 8ull * lead, blk_len = S.blk_end[b] - S.blk_bit[b];
-    uint32_t start;
-    if (round == 0) start = k == k0 ? data_rel : k * kSpecBits;
-    else {
-        if (k == k0) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }   // the first subsegment starts at the true first symbol: carry over
-        const uint32_t pe = S.s_exit_prev[sg - 1];
-        const uint32_t cur = S.s_start[sg];
-        // An unusable neighbour exit (its speculative parse ran into EndOfBlock / an unassigned code, or the block really ends
-        // there) carries no information about this subsegment: keep the current parse.  Propagating it would send a "dead"
-        // pulse one subsegment to the right per round.
-        if (pe >= kExitDead || pe == cur) { S.s_exit[sg] = S.s_exit_prev[sg]; return; }
-        start = pe;
+    const uint64_t seg_end = min((uint64_t)(k + 1) * kSpecBits, blk_len);
+    // decide what this lane does: nothing (out of range), bookkeeping only, or a (re-)decode from `start`
+    bool decode = false, store = false;
+    uint32_t start = 0, ex = 0;
+    if (k < nseg) {
+        if (k < k0) { S.s_start[sg] = kExitDead; S.s_exit[sg] = kExitDead; }                    // header bits only
+        else if (round == 0) { start = k == k0 ? data_rel : k * kSpecBits; store = true; }
+        else if (k == k0) S.s_exit[sg] = S.s_exit_prev[sg];                                      // starts at the true first symbol: carry over
+        else {
+            const uint32_t pe = S.s_exit_prev[sg - 1];
+            const uint32_t cur = S.s_start[sg];
+            // An unusable neighbour exit (its speculative parse ran into EndOfBlock / an unassigned code, or the block really
+            // ends there) carries no information about this subsegment: keep the current parse.
+            if (pe >= kExitDead || pe == cur) S.s_exit[sg] = S.s_exit_prev[sg];
+            else { start = pe; store = true; }
+        }
+        if (store) { if (start >= seg_end) ex = start; else decode = true; }     // neighbour's last symbol may already cover this subsegment
     }
     TBits t;
     t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
     t.nwords = (S.in_len[m] + lead + 3) >> 2;
-    const uint64_t seg_end = min((uint64_t)(k + 1) * kSpecBits, blk_len);
-    uint32_t nsym = 0, nbytes = 0, ex;
-    if (start >= seg_end) ex = start;                            // the neighbour's last symbol already covers this subsegment
-    else {
-        tb_seek(t, blk_abs + start);
-        int32_t dummy = 0;
-        const uint32_t r = spec_decode<false>(t, Ts, blk_abs + seg_end, nsym, nbytes, nullptr, dummy);
+    t.pos = 0; t.bb = 0; t.bc = 0; t.widx = 0;
+    if (decode) tb_seek(t, blk_abs + start);
+    uint32_t nsym = 0, nbytes = 0;
+    int32_t dummy = 0;
+    const uint32_t mask = __activemask();
+    const uint32_t r = spec_decode<false>(mask, decode, t, Ts, blk_abs + seg_end, nsym, nbytes, nullptr, dummy);
+    if (decode) {
         if (r == kExitEob) { ex = kExitEob; S.s_eob_end[sg] = (uint32_t)(t.pos - blk_abs); }
         else if (r == kExitBad) ex = kExitBad;
         else ex = (uint32_t)(t.pos - blk_abs);
     }
-    S.s_start[sg] = start; S.s_exit[sg] = ex; S.s_nsym[sg] = nsym; S.s_nbytes[sg] = nbytes;
-    if (round) atomicOr(S.changed + round, 1u);
+    if (store) {
+        S.s_start[sg] = start; S.s_exit[sg] = ex; S.s_nsym[sg] = nsym; S.s_nbytes[sg] = nbytes;
+        if (round) atomicOr(S.changed + round, 1u);
+    }
 }
 
 // ---------------------------------------------------------------------------------- verify + scan (CTA per block)
@@ -264,25 +281,30 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
     const uint32_t data_rel = S.blk_data_rel[b];
     const uint32_t k = (blockIdx.x - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
     const uint32_t k0 = data_rel / kSpecBits, e = S.blk_eob_seg[b];
-    if (k < k0 || k > e) return;
-    const uint32_t sg = S.blk_seg0[b] + k;
+    const bool mine = k >= k0 && k <= e;
+    const uint32_t sg = S.blk_seg0[b] + (mine ? k : k0);
     const uint32_t m = S.blk_member[b];
     const uint8_t *p0 = S.in + S.in_off[m];
     const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
     const uint64_t blk_abs = S.blk_bit[b] + 8ull * lead, blk_len = S.blk_end[b] - S.blk_bit[b];
     const uint32_t start = S.s_start[sg];
     const uint64_t seg_end = min((uint64_t)(k + 1) * kSpecBits, blk_len);
-    if (start >= seg_end) { S.s_min_src[sg] = INT64_MAX; return; }      // no symbol starts in this subsegment
+    const bool decode = mine && start < seg_end;
+    if (mine && !decode) S.s_min_src[sg] = INT64_MAX;                     // no symbol starts in this subsegment
     TBits t;
     t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
     t.nwords = (S.in_len[m] + lead + 3) >> 2;
-    tb_seek(t, blk_abs + start);
+    t.pos = 0; t.bb = 0; t.bc = 0; t.widx = 0;
+    if (decode) tb_seek(t, blk_abs + start);
     uint32_t nsym = 0, nbytes = 0;
     int32_t min_rel = INT32_MAX;
-    TokSink sink = { stage + threadIdx.x * 8, reinterpret_cast<uint4 *>(S.tokens + S.blk_tok0[b] + S.s_tok_rel[sg]), 0 };
-    spec_decode<true>(t, Ts, blk_abs + seg_end, nsym, nbytes, &sink, min_rel);
-    sink.finish();
-    S.s_min_src[sg] = min_rel == INT32_MAX ? INT64_MAX : (int64_t)S.s_out_rel[sg] + min_rel;
+    TokSink sink = { stage + threadIdx.x * 8, reinterpret_cast<uint4 *>(S.tokens + S.blk_tok0[b] + (decode ? S.s_tok_rel[sg] : 0)), 0 };
+    const uint32_t mask = __activemask();
+    spec_decode<true>(mask, decode, t, Ts, blk_abs + seg_end, nsym, nbytes, &sink, min_rel);
+    if (decode) {
+        sink.finish();
+        S.s_min_src[sg] = min_rel == INT32_MAX ? INT64_MAX : (int64_t)S.s_out_rel[sg] + min_rel;
+    }
 }
 
 // ---------------------------------------------------------------------------------- independent LZ77 units inside a block

@@ -111,13 +111,26 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *s, uint32_t off) {     
     const uint32_t *w = reinterpret_cast<const uint32_t *>(s + (off & ~3u));
     return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
-constexpr uint32_t kMatchSmem = kPTile + kLookback + 261 + 16 + 32;
+constexpr uint32_t kScanCap = 256 + 258;                          // a head scans at most this far; followers are < 256 positions behind it
+constexpr uint32_t kMatchBytes = (kPTile + kLookback + kScanCap + 16 + 32 + 15) & ~15u;
+constexpr uint32_t kMatchSmem = kMatchBytes + 3 * (kPTile + 8) * 2;
 
 // md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
 // the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
+//
+// Phase A finds the candidate distance of every position (chain walk, parse independent).  Consecutive positions with
+// the same distance form an alignment run: bytes keep matching at that alignment until one mismatch position E, so
+// length(p) = min(E - p, max_length) for every position of the run.  Only run HEADS scan for E (phase B, dense work
+// queue); followers derive their length (phase C).  A head is forced every 256 positions so that a head's scan of
+// 256 + 258 bytes is exact for all its followers.
 __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     extern __shared__ __align__(16) uint8_t sb[];
-    const uint32_t tid = threadIdx.x;
+    uint16_t *sdist = reinterpret_cast<uint16_t *>(sb + kMatchBytes);     // [kPTile + 8] candidate distance (0 = none)
+    uint16_t *send = sdist + kPTile + 8;                                    // [kPTile + 8] match end (tile relative) written at heads
+    uint16_t *queue = send + kPTile + 8;                                    // [kPTile + 8] head positions (tile relative)
+    __shared__ uint32_t nq;
+    __shared__ int32_t wcarry[16];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t pt = blockIdx.x;
     const uint32_t c = find_owner(E.pt0, E.n_chunks, pt);
     const ChunkDesc cd = E.chunks[c];
@@ -126,13 +139,14 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     const uint32_t ts = (pt - E.pt0[c]) * kPTile;
     const uint32_t te = min(ts + kPTile, n);
     const uint32_t lo = ts > kLookback ? ts - kLookback : 0;
-    const uint32_t hi = min(n, te + 261);
+    const uint32_t hi = min(n, te + kScanCap + 3);
     const uint64_t g_lo = cd.off + lo;
     const uint64_t g_al = g_lo & ~15ull;
     const uint32_t shift = (uint32_t)(g_lo - g_al);
     const uint32_t nvec = (hi - lo + shift + 15) >> 4;
     const uint4 *__restrict__ gsrc = reinterpret_cast<const uint4 *>(E.in + g_al);
     uint4 *sdst = reinterpret_cast<uint4 *>(sb);
+    if (tid == 0) nq = 0;
     for (uint32_t i = tid; i < nvec; i += 512) {
         const uint64_t off = g_al + 16ull * i;
         if (off + 16 <= E.in_size) sdst[i] = __ldg(gsrc + i);
@@ -142,6 +156,7 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     const uint16_t *__restrict__ lk = E.link + cd.off;
     uint32_t *__restrict__ md = E.md + cd.off;
     const uint32_t sbase = shift - lo;        // smem index of chunk position x is x + sbase (mod 2^32 arithmetic)
+    // ---- phase A: candidate distance per position
     for (uint32_t pos0 = ts + tid; pos0 < te; pos0 += 4 * 512) {
         uint32_t dpre[4];
 #pragma unroll
@@ -150,36 +165,91 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
         for (uint32_t u = 0; u < 4; u++) {
             const uint32_t pos = pos0 + u * 512;
             if (pos >= te) break;
-            uint32_t out = 0;
+            uint32_t dist = 0;
             if (pos < end) {
                 const uint32_t si = pos + sbase;
                 const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
                 uint32_t d = dpre[u], total = 0, j = pos;
-                bool found = false;
                 while (d) {
                     total += d;
                     if (total > E.window) break;
                     j -= d;
                     const uint32_t sj = j + sbase;
                     const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
-                    if (tj == t) { found = true; break; }
+                    if (tj == t) { dist = total; break; }
                     d = lk[j];
                 }
-                if (found) {
-                    const uint32_t a = si + 3, b = j + sbase + 3;
-                    const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
-                    uint32_t k = 0;
-                    while (k < limit) {
-                        const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
-                        if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                        k += 4;
-                    }
-                    if (k > limit) k = limit;
-                    out = ((3 + k) << 16) | total;
-                }
             }
-            md[pos] = out;
+            sdist[pos - ts] = (uint16_t)dist;
         }
+    }
+    __syncthreads();
+    // ---- phase B1: heads -> dense queue (warp-aggregated append)
+    for (uint32_t base = ts; base < te; base += 512) {
+        const uint32_t pos = base + tid;
+        bool head = false;
+        if (pos < te) {
+            const uint32_t d = sdist[pos - ts];
+            head = d != 0 && (pos == ts || sdist[pos - ts - 1] != d || ((pos - ts) & 255u) == 0);
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, head);
+        uint32_t wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&nq, (uint32_t)__popc(bal));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (head) queue[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(pos - ts);
+    }
+    __syncthreads();
+    // ---- phase B2: every head finds the end of its matching region (exclusive), scanning at most kScanCap bytes
+    const uint32_t nheads = nq;
+    for (uint32_t i = tid; i < nheads; i += 512) {
+        const uint32_t rel = queue[i], pos = ts + rel;
+        const uint32_t d = sdist[rel];
+        const uint32_t a = pos + sbase + 3, bsrc = a - d;
+        const uint32_t limit = min(kScanCap - 3, n - (pos + 3));          // bytes beyond the trigram that may be compared
+        uint32_t k = 0;
+        while (k < limit) {
+            const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, bsrc + k);
+            if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+            k += 4;
+        }
+        if (k > limit) k = limit;
+        send[rel] = (uint16_t)(rel + 3 + k);                               // tile-relative end of the matching region (<= kPTile + kScanCap)
+    }
+    __syncthreads();
+    // ---- phase C: each thread owns 16 consecutive positions (kPTile / 512); the head in force at its first position comes
+    // from a block-wide max-scan of "last head position"
+    constexpr uint32_t PER = kPTile / 512;
+    const uint32_t r0 = tid * PER;
+    int32_t last = -1;
+    for (uint32_t i = 0; i < PER; i++) {
+        const uint32_t rel = r0 + i;
+        if (ts + rel < te) {
+            const uint32_t d = sdist[rel];
+            if (d != 0 && (rel == 0 || sdist[rel - 1] != d || (rel & 255u) == 0)) last = (int32_t)rel;
+        }
+    }
+    int32_t inc = last;
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { const int32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, dlt); if ((int)lane >= dlt) inc = max(inc, v); }
+    if (lane == 31) wcarry[wid] = inc;
+    __syncthreads();
+    int32_t carry = -1;
+    for (uint32_t w = 0; w < wid; w++) carry = max(carry, wcarry[w]);
+    const int32_t prev_lane = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane > 0) carry = max(carry, prev_lane);
+    int32_t cur = carry;                                                  // head in force before this thread's first position
+    for (uint32_t i = 0; i < PER; i++) {
+        const uint32_t rel = r0 + i, pos = ts + rel;
+        if (pos >= te) break;
+        const uint32_t d = sdist[rel];
+        uint32_t out = 0;
+        if (d != 0) {
+            if (rel == 0 || sdist[rel - 1] != d || (rel & 255u) == 0) cur = (int32_t)rel;
+            const uint32_t e = send[cur];                                   // the run's match end
+            uint32_t len = e - rel;
+            if (len > E.max_len) len = E.max_len;
+            out = (len << 16) | d;
+        }
+        md[pos] = out;
     }
 }
 

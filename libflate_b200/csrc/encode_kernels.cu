@@ -113,7 +113,9 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *s, uint32_t off) {     
 }
 constexpr uint32_t kScanCap = 256 + 258;                          // a head scans at most this far; followers are < 256 positions behind it
 constexpr uint32_t kMatchBytes = (kPTile + kLookback + kScanCap + 16 + 32 + 15) & ~15u;
-constexpr uint32_t kMatchSmem = kMatchBytes + 3 * (kPTile + 8) * 2;
+constexpr uint32_t kMatchLinks = kPTile + kLookback + 16;           // link window staged next to the bytes
+constexpr uint32_t kMatchSmem = kMatchBytes + kMatchLinks * 2 + 3 * (kPTile + 8) * 2;
+constexpr uint32_t kMatchThreads = 1024;
 
 // md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
 // the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
@@ -123,13 +125,14 @@ constexpr uint32_t kMatchSmem = kMatchBytes + 3 * (kPTile + 8) * 2;
 // length(p) = min(E - p, max_length) for every position of the run.  Only run HEADS scan for E (phase B, dense work
 // queue); followers derive their length (phase C).  A head is forced every 256 positions so that a head's scan of
 // 256 + 258 bytes is exact for all its followers.
-__global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
+__global__ void __launch_bounds__(kMatchThreads) k_lz_match(EncDev E) {
     extern __shared__ __align__(16) uint8_t sb[];
-    uint16_t *sdist = reinterpret_cast<uint16_t *>(sb + kMatchBytes);     // [kPTile + 8] candidate distance (0 = none)
+    uint16_t *slk = reinterpret_cast<uint16_t *>(sb + kMatchBytes);       // [kMatchLinks] link[] of positions lo .. te-1 (index x - lo + lshift)
+    uint16_t *sdist = slk + kMatchLinks;                                    // [kPTile + 8] candidate distance (0 = none)
     uint16_t *send = sdist + kPTile + 8;                                    // [kPTile + 8] match end (tile relative) written at heads
     uint16_t *queue = send + kPTile + 8;                                    // [kPTile + 8] head positions (tile relative)
     __shared__ uint32_t nq;
-    __shared__ int32_t wcarry[16];
+    __shared__ int32_t wcarry[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t pt = blockIdx.x;
     const uint32_t c = find_owner(E.pt0, E.n_chunks, pt);
@@ -147,45 +150,42 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     const uint4 *__restrict__ gsrc = reinterpret_cast<const uint4 *>(E.in + g_al);
     uint4 *sdst = reinterpret_cast<uint4 *>(sb);
     if (tid == 0) nq = 0;
-    for (uint32_t i = tid; i < nvec; i += 512) {
+    for (uint32_t i = tid; i < nvec; i += kMatchThreads) {
         const uint64_t off = g_al + 16ull * i;
         if (off + 16 <= E.in_size) sdst[i] = __ldg(gsrc + i);
         else { uint4 v; v.x = ld_in32(E.in, off, E.in_size); v.y = ld_in32(E.in, off + 4, E.in_size); v.z = ld_in32(E.in, off + 8, E.in_size); v.w = ld_in32(E.in, off + 12, E.in_size); sdst[i] = v; }
     }
+    {   // stage link[lo .. te) (u16 each) with 16-byte loads: the E.link array is indexed like the input, so the same alignment trick applies
+        const uint64_t l_lo = (cd.off + lo) * 2, l_al = l_lo & ~15ull;
+        const uint32_t lshift_b = (uint32_t)(l_lo - l_al);
+        const uint32_t nlv = ((te - lo) * 2 + lshift_b + 15) >> 4;
+        const uint4 *__restrict__ lsrc = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(E.link) + l_al);
+        uint4 *ldst = reinterpret_cast<uint4 *>(slk);
+        for (uint32_t i = tid; i < nlv; i += kMatchThreads) ldst[i] = __ldg(lsrc + i);      // E.link is allocated with padding (b2f_api.cu)
+    }
     __syncthreads();
-    const uint16_t *__restrict__ lk = E.link + cd.off;
     uint32_t *__restrict__ md = E.md + cd.off;
     const uint32_t sbase = shift - lo;        // smem index of chunk position x is x + sbase (mod 2^32 arithmetic)
-    // ---- phase A: candidate distance per position
-    for (uint32_t pos0 = ts + tid; pos0 < te; pos0 += 4 * 512) {
-        uint32_t dpre[4];
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) { const uint32_t q = pos0 + u * 512; dpre[u] = (q < te && q < end) ? lk[q] : 0; }   // independent loads first
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) {
-            const uint32_t pos = pos0 + u * 512;
-            if (pos >= te) break;
-            uint32_t dist = 0;
-            if (pos < end) {
-                const uint32_t si = pos + sbase;
-                const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
-                uint32_t d = dpre[u], total = 0, j = pos;
-                while (d) {
-                    total += d;
-                    if (total > E.window) break;
-                    j -= d;
-                    const uint32_t sj = j + sbase;
-                    const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
-                    if (tj == t) { dist = total; break; }
-                    d = lk[j];
-                }
+    const uint32_t lbase = (uint32_t)((((cd.off + lo) * 2) & 15ull) >> 1) - lo;   // slk index of chunk position x is x + lbase
+    // ---- phase A: candidate distance per position (everything out of shared memory)
+    for (uint32_t pos = ts + tid; pos < te; pos += kMatchThreads) {
+        uint32_t dist = 0;
+        if (pos < end) {
+            const uint32_t t = ld32u(sb, pos + sbase) & 0xFFFFFFu;
+            uint32_t d = slk[pos + lbase], total = 0, j = pos;
+            while (d) {
+                total += d;
+                if (total > E.window) break;
+                j -= d;
+                if ((ld32u(sb, j + sbase) & 0xFFFFFFu) == t) { dist = total; break; }
+                d = slk[j + lbase];
             }
-            sdist[pos - ts] = (uint16_t)dist;
         }
+        sdist[pos - ts] = (uint16_t)dist;
     }
     __syncthreads();
     // ---- phase B1: heads -> dense queue (warp-aggregated append)
-    for (uint32_t base = ts; base < te; base += 512) {
+    for (uint32_t base = ts; base < te; base += kMatchThreads) {
         const uint32_t pos = base + tid;
         bool head = false;
         if (pos < te) {
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     __syncthreads();
     // ---- phase B2: every head finds the end of its matching region (exclusive), scanning at most kScanCap bytes
     const uint32_t nheads = nq;
-    for (uint32_t i = tid; i < nheads; i += 512) {
+    for (uint32_t i = tid; i < nheads; i += kMatchThreads) {
         const uint32_t rel = queue[i], pos = ts + rel;
         const uint32_t d = sdist[rel];
         const uint32_t a = pos + sbase + 3, bsrc = a - d;
@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
         send[rel] = (uint16_t)(rel + 3 + k);                               // tile-relative end of the matching region (<= kPTile + kScanCap)
     }
     __syncthreads();
-    // ---- phase C: each thread owns 16 consecutive positions (kPTile / 512); the head in force at its first position comes
+    // ---- phase C: each thread owns kPTile / kMatchThreads consecutive positions; the head in force at its first position comes
     // from a block-wide max-scan of "last head position"
-    constexpr uint32_t PER = kPTile / 512;
+    constexpr uint32_t PER = kPTile / kMatchThreads;
     const uint32_t r0 = tid * PER;
     int32_t last = -1;
     for (uint32_t i = 0; i < PER; i++) {
@@ -565,7 +565,7 @@ cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm) {
     if (tm) tm->mark(st, "lz_chain");
     k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 4, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "lz_match");
-    k_lz_match<<<E.n_ptiles, 512, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
+    k_lz_match<<<E.n_ptiles, kMatchThreads, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_exits");
     k_parse_exits<<<(E.n_tiles + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_stitch");

@@ -42,7 +42,10 @@ __device__ __forceinline__ uint32_t ld_in32(const uint8_t *__restrict__ in, uint
 // 14-bit hash (0 = none within 32768).  Every position < end is "inserted" exactly once in
 // increasing order (default.rs:78, 92-97), so this ordered chain is parse independent.
 __global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
-    extern __shared__ uint32_t head[];       // 1 << kHashBits entries: last position + 1
+    // 1 << kHashBits entries holding (last position + 1) mod 65536.  A stale or never-written entry can alias to a bogus
+    // distance <= 32768; that is harmless: lz_match verifies the trigram at every hop, and a position with the same trigram
+    // within the window would have refreshed the entry.
+    extern __shared__ uint16_t head[];
     const uint32_t lane = threadIdx.x;
     const uint32_t seg = blockIdx.x;
     const uint32_t c = find_owner(E.seg0, E.n_chunks, seg);
@@ -55,7 +58,6 @@ __global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
     const uint32_t ws = s_start > kLookback ? s_start - kLookback : 0;
     for (uint32_t i = lane; i < (1u << kHashBits); i += 32) head[i] = 0;
     __syncwarp();
-    const uint8_t *__restrict__ p = E.in + cd.off;
     uint16_t *__restrict__ lk = E.link + cd.off;
     for (uint32_t q = max(lim, s_start) + lane; q < s_end; q += 32) lk[q] = 0;   // tail without a trigram
     if (ws >= lim) return;
@@ -82,22 +84,23 @@ __global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
             const bool valid = pos64 >= (int64_t)ws && pos64 < (int64_t)lim;
             const uint32_t pos = (uint32_t)pos64;
             const uint32_t h = valid ? (t * 0x9E3779B1u) >> (32 - kHashBits) : 0;
+            const uint32_t mine = (pos + 1) & 0xFFFFu;
             const uint32_t old = valid ? head[h] : 0;
             __syncwarp();
-            if (valid) head[h] = pos + 1;                            // same-hash lanes: one of them wins
+            if (valid) head[h] = (uint16_t)mine;                     // same-hash lanes: one of them wins
             __syncwarp();
-            const bool lost = valid && head[h] != pos + 1;
-            uint32_t prev1 = old;
+            const bool lost = valid && head[h] != mine;
+            uint32_t d = (mine - old) & 0xFFFFu;                     // distance to the entry's position (modulo 65536)
+            if (d > pos) d = 0;                                      // would point before the chunk: empty / stale entry
             if (__any_sync(0xFFFFFFFFu, lost)) {                     // rare: two positions of this step share a hash -> exact ordered resolution
                 const uint32_t key = valid ? h : (0x80000000u | lane);
                 const uint32_t m = __match_any_sync(0xFFFFFFFFu, key);
                 const uint32_t lower = m & ((1u << lane) - 1u);
-                if (lower) prev1 = (uint32_t)(base + (31 - __clz((int)lower))) + 1;
-                if (valid && (m >> lane) == 1u) head[h] = pos + 1;   // highest lane of the group publishes
+                if (lower) d = lane - (31 - __clz((int)lower));
+                if (valid && (m >> lane) == 1u) head[h] = (uint16_t)mine;   // highest lane of the group publishes
                 __syncwarp();
             }
             if (valid && pos >= s_start) {
-                uint32_t d = prev1 ? pos + 1 - prev1 : 0;
                 if (d > kLookback) d = 0;
                 lk[pos] = (uint16_t)d;
             }
@@ -168,22 +171,47 @@ __global__ void __launch_bounds__(kMatchThreads) k_lz_match(EncDev E) {
     const uint32_t sbase = shift - lo;        // smem index of chunk position x is x + sbase (mod 2^32 arithmetic)
     const uint32_t lbase = (uint32_t)((((cd.off + lo) * 2) & 15ull) >> 1) - lo;   // slk index of chunk position x is x + lbase
     // ---- phase A: candidate distance per position (everything out of shared memory)
+    // The average walk is ~1 hop but a few positions (a rare trigram sharing a bucket with a frequent one) would walk hundreds
+    // of links and stall the whole CTA at the barrier: walks are capped and the leftovers go to a warp-cooperative scan.
+    constexpr uint32_t kMaxHops = 48;
     for (uint32_t pos = ts + tid; pos < te; pos += kMatchThreads) {
         uint32_t dist = 0;
         if (pos < end) {
             const uint32_t t = ld32u(sb, pos + sbase) & 0xFFFFFFu;
-            uint32_t d = slk[pos + lbase], total = 0, j = pos;
+            uint32_t d = slk[pos + lbase], total = 0, j = pos, hops = 0;
             while (d) {
                 total += d;
-                if (total > E.window) break;
+                if (total > E.window || total > pos) break;
                 j -= d;
                 if ((ld32u(sb, j + sbase) & 0xFFFFFFu) == t) { dist = total; break; }
+                if (++hops == kMaxHops) { queue[atomicAdd(&nq, 1u)] = (uint16_t)(pos - ts); break; }
                 d = slk[j + lbase];
             }
         }
         sdist[pos - ts] = (uint16_t)dist;
     }
     __syncthreads();
+    {   // leftovers: one warp per position scans the window backwards, 32 positions per step, for the most recent equal trigram
+        const uint32_t nlong = nq;
+        for (uint32_t i = wid; i < nlong; i += kMatchThreads / 32) {
+            const uint32_t pos = ts + queue[i];
+            const uint32_t t = ld32u(sb, pos + sbase) & 0xFFFFFFu;
+            const uint32_t first = pos > E.window ? pos - E.window : 0;     // oldest admissible candidate
+            uint32_t dist = 0;
+            for (uint32_t hi_pos = pos; hi_pos > first;) {
+                const uint32_t base = hi_pos >= 32 ? hi_pos - 32 : 0;        // candidates base .. hi_pos-1
+                const uint32_t j = base + lane;
+                const bool m = j < hi_pos && j >= first && (ld32u(sb, j + sbase) & 0xFFFFFFu) == t;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m);
+                if (bal) { dist = pos - (base + (31 - __clz((int)bal))); break; }
+                hi_pos = base;
+            }
+            if (lane == 0) sdist[pos - ts] = (uint16_t)dist;
+        }
+        __syncthreads();
+        if (tid == 0) nq = 0;
+        __syncthreads();
+    }
     // ---- phase B1: heads -> dense queue (warp-aggregated append)
     for (uint32_t base = ts; base < te; base += kMatchThreads) {
         const uint32_t pos = base + tid;
@@ -552,7 +580,7 @@ __global__ void __launch_bounds__(256) k_compact_syms(EncDev E, const uint64_t *
 
 cudaError_t enc_init_attributes() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_lz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << kHashBits) * 4));
+    e = cudaFuncSetAttribute(k_lz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << kHashBits) * 2));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_lz_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
@@ -563,7 +591,7 @@ cudaError_t enc_init_attributes() {
 cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm) {
     if (E.n_chunks == 0) return cudaSuccess;
     if (tm) tm->mark(st, "lz_chain");
-    k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 4, st>>>(E); B2F_LAUNCH_CHECK();
+    k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 2, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "lz_match");
     k_lz_match<<<E.n_ptiles, kMatchThreads, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_exits");

@@ -18,7 +18,7 @@ constexpr uint32_t kTile = 2048;        // greedy-parse tile (positions); must b
 constexpr uint32_t kExitW = 258;        // entry points per tile that a previous tile can exit into
 constexpr uint32_t kPTile = 8192;       // match-kernel tile (positions staged in shared memory)
 constexpr uint32_t kSeg = 131072;       // chain-build segment (one warp, sequential; segments after the first re-insert 32 KiB of warm-up)
-constexpr uint32_t kHashBits = 15;      // chain-build hash table = 2^15 u16 = 64 KiB per warp
+constexpr uint32_t kHashBits = 14;      // chain-build hash table = 2^14 u32 = 64 KiB per warp
 constexpr uint32_t kLookback = 32768;   // libflate_lz77::MAX_DISTANCE
 constexpr uint32_t kGrpTiles = 64;      // tiles per emit CTA (one chunk per CTA)
 constexpr uint32_t kHdrWords = 160;     // dynamic header bit buffer per block (<= 4495 bits)

@@ -42,10 +42,8 @@ __device__ __forceinline__ uint32_t ld_in32(const uint8_t *__restrict__ in, uint
 // 14-bit hash (0 = none within 32768).  Every position < end is "inserted" exactly once in
 // increasing order (default.rs:78, 92-97), so this ordered chain is parse independent.
 __global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
-    // 1 << kHashBits entries holding (last position + 1) mod 65536.  A stale or never-written entry can alias to a bogus
-    // distance <= 32768; that is harmless: lz_match verifies the trigram at every hop, and a position with the same trigram
-    // within the window would have refreshed the entry.
-    extern __shared__ uint16_t head[];
+    extern __shared__ uint32_t head[];       // 1 << kHashBits entries: last position + 1 (exact: a 16-bit modulo entry would alias
+                                             // stale buckets into bogus in-window links and send lz_match down unrelated chains)
     const uint32_t lane = threadIdx.x;
     const uint32_t seg = blockIdx.x;
     const uint32_t c = find_owner(E.seg0, E.n_chunks, seg);
@@ -84,20 +82,18 @@ __global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
             const bool valid = pos64 >= (int64_t)ws && pos64 < (int64_t)lim;
             const uint32_t pos = (uint32_t)pos64;
             const uint32_t h = valid ? (t * 0x9E3779B1u) >> (32 - kHashBits) : 0;
-            const uint32_t mine = (pos + 1) & 0xFFFFu;
             const uint32_t old = valid ? head[h] : 0;
             __syncwarp();
-            if (valid) head[h] = (uint16_t)mine;                     // same-hash lanes: one of them wins
+            if (valid) head[h] = pos + 1;                            // same-hash lanes: one of them wins
             __syncwarp();
-            const bool lost = valid && head[h] != mine;
-            uint32_t d = (mine - old) & 0xFFFFu;                     // distance to the entry's position (modulo 65536)
-            if (d > pos) d = 0;                                      // would point before the chunk: empty / stale entry
+            const bool lost = valid && head[h] != pos + 1;
+            uint32_t d = old ? pos + 1 - old : 0;
             if (__any_sync(0xFFFFFFFFu, lost)) {                     // rare: two positions of this step share a hash -> exact ordered resolution
                 const uint32_t key = valid ? h : (0x80000000u | lane);
                 const uint32_t m = __match_any_sync(0xFFFFFFFFu, key);
                 const uint32_t lower = m & ((1u << lane) - 1u);
                 if (lower) d = lane - (31 - __clz((int)lower));
-                if (valid && (m >> lane) == 1u) head[h] = (uint16_t)mine;   // highest lane of the group publishes
+                if (valid && (m >> lane) == 1u) head[h] = pos + 1;   // highest lane of the group publishes
                 __syncwarp();
             }
             if (valid && pos >= s_start) {
@@ -173,7 +169,7 @@ __global__ void __launch_bounds__(kMatchThreads) k_lz_match(EncDev E) {
     // ---- phase A: candidate distance per position (everything out of shared memory)
     // The average walk is ~1 hop but a few positions (a rare trigram sharing a bucket with a frequent one) would walk hundreds
     // of links and stall the whole CTA at the barrier: walks are capped and the leftovers go to a warp-cooperative scan.
-    constexpr uint32_t kMaxHops = 48;
+    constexpr uint32_t kMaxHops = 96;
     for (uint32_t pos = ts + tid; pos < te; pos += kMatchThreads) {
         uint32_t dist = 0;
         if (pos < end) {
@@ -580,7 +576,7 @@ __global__ void __launch_bounds__(256) k_compact_syms(EncDev E, const uint64_t *
 
 cudaError_t enc_init_attributes() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_lz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << kHashBits) * 2));
+    e = cudaFuncSetAttribute(k_lz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << kHashBits) * 4));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_lz_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
@@ -591,7 +587,7 @@ cudaError_t enc_init_attributes() {
 cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm) {
     if (E.n_chunks == 0) return cudaSuccess;
     if (tm) tm->mark(st, "lz_chain");
-    k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 2, st>>>(E); B2F_LAUNCH_CHECK();
+    k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 4, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "lz_match");
     k_lz_match<<<E.n_ptiles, kMatchThreads, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_exits");

@@ -110,29 +110,13 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *s, uint32_t off) {     
     const uint32_t *w = reinterpret_cast<const uint32_t *>(s + (off & ~3u));
     return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
-constexpr uint32_t kScanCap = 256 + 258;                          // a head scans at most this far; followers are < 256 positions behind it
-constexpr uint32_t kMatchBytes = (kPTile + kLookback + kScanCap + 16 + 32 + 15) & ~15u;
-constexpr uint32_t kMatchLinks = kPTile + kLookback + 16;           // link window staged next to the bytes
-constexpr uint32_t kMatchSmem = kMatchBytes + kMatchLinks * 2 + 3 * (kPTile + 8) * 2;
-constexpr uint32_t kMatchThreads = 1024;
+constexpr uint32_t kMatchSmem = kPTile + kLookback + 261 + 16 + 32;
 
 // md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
 // the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
-//
-// Phase A finds the candidate distance of every position (chain walk, parse independent).  Consecutive positions with
-// the same distance form an alignment run: bytes keep matching at that alignment until one mismatch position E, so
-// length(p) = min(E - p, max_length) for every position of the run.  Only run HEADS scan for E (phase B, dense work
-// queue); followers derive their length (phase C).  A head is forced every 256 positions so that a head's scan of
-// 256 + 258 bytes is exact for all its followers.
-__global__ void __launch_bounds__(kMatchThreads) k_lz_match(EncDev E) {
+__global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
     extern __shared__ __align__(16) uint8_t sb[];
-    uint16_t *slk = reinterpret_cast<uint16_t *>(sb + kMatchBytes);       // [kMatchLinks] link[] of positions lo .. te-1 (index x - lo + lshift)
-    uint16_t *sdist = slk + kMatchLinks;                                    // [kPTile + 8] candidate distance (0 = none)
-    uint16_t *send = sdist + kPTile + 8;                                    // [kPTile + 8] match end (tile relative) written at heads
-    uint16_t *queue = send + kPTile + 8;                                    // [kPTile + 8] head positions (tile relative)
-    __shared__ uint32_t nq;
-    __shared__ int32_t wcarry[32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t tid = threadIdx.x;
     const uint32_t pt = blockIdx.x;
     const uint32_t c = find_owner(E.pt0, E.n_chunks, pt);
     const ChunkDesc cd = E.chunks[c];
@@ -141,139 +125,60 @@ __global__ void __launch_bounds__(kMatchThreads) k_lz_match(EncDev E) {
     const uint32_t ts = (pt - E.pt0[c]) * kPTile;
     const uint32_t te = min(ts + kPTile, n);
     const uint32_t lo = ts > kLookback ? ts - kLookback : 0;
-    const uint32_t hi = min(n, te + kScanCap + 3);
+    const uint32_t hi = min(n, te + 261);
     const uint64_t g_lo = cd.off + lo;
     const uint64_t g_al = g_lo & ~15ull;
     const uint32_t shift = (uint32_t)(g_lo - g_al);
     const uint32_t nvec = (hi - lo + shift + 15) >> 4;
     const uint4 *__restrict__ gsrc = reinterpret_cast<const uint4 *>(E.in + g_al);
     uint4 *sdst = reinterpret_cast<uint4 *>(sb);
-    if (tid == 0) nq = 0;
-    for (uint32_t i = tid; i < nvec; i += kMatchThreads) {
+    for (uint32_t i = tid; i < nvec; i += 512) {
         const uint64_t off = g_al + 16ull * i;
         if (off + 16 <= E.in_size) sdst[i] = __ldg(gsrc + i);
         else { uint4 v; v.x = ld_in32(E.in, off, E.in_size); v.y = ld_in32(E.in, off + 4, E.in_size); v.z = ld_in32(E.in, off + 8, E.in_size); v.w = ld_in32(E.in, off + 12, E.in_size); sdst[i] = v; }
     }
-    {   // stage link[lo .. te) (u16 each) with 16-byte loads: the E.link array is indexed like the input, so the same alignment trick applies
-        const uint64_t l_lo = (cd.off + lo) * 2, l_al = l_lo & ~15ull;
-        const uint32_t lshift_b = (uint32_t)(l_lo - l_al);
-        const uint32_t nlv = ((te - lo) * 2 + lshift_b + 15) >> 4;
-        const uint4 *__restrict__ lsrc = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(E.link) + l_al);
-        uint4 *ldst = reinterpret_cast<uint4 *>(slk);
-        for (uint32_t i = tid; i < nlv; i += kMatchThreads) ldst[i] = __ldg(lsrc + i);      // E.link is allocated with padding (b2f_api.cu)
-    }
     __syncthreads();
+    const uint16_t *__restrict__ lk = E.link + cd.off;
     uint32_t *__restrict__ md = E.md + cd.off;
     const uint32_t sbase = shift - lo;        // smem index of chunk position x is x + sbase (mod 2^32 arithmetic)
-    const uint32_t lbase = (uint32_t)((((cd.off + lo) * 2) & 15ull) >> 1) - lo;   // slk index of chunk position x is x + lbase
-    // ---- phase A: candidate distance per position (everything out of shared memory)
-    // The average walk is ~1 hop but a few positions (a rare trigram sharing a bucket with a frequent one) would walk hundreds
-    // of links and stall the whole CTA at the barrier: walks are capped and the leftovers go to a warp-cooperative scan.
-    constexpr uint32_t kMaxHops = 96;
-    for (uint32_t pos = ts + tid; pos < te; pos += kMatchThreads) {
-        uint32_t dist = 0;
-        if (pos < end) {
-            const uint32_t t = ld32u(sb, pos + sbase) & 0xFFFFFFu;
-            uint32_t d = slk[pos + lbase], total = 0, j = pos, hops = 0;
-            while (d) {
-                total += d;
-                if (total > E.window || total > pos) break;
-                j -= d;
-                if ((ld32u(sb, j + sbase) & 0xFFFFFFu) == t) { dist = total; break; }
-                if (++hops == kMaxHops) { queue[atomicAdd(&nq, 1u)] = (uint16_t)(pos - ts); break; }
-                d = slk[j + lbase];
+    for (uint32_t pos0 = ts + tid; pos0 < te; pos0 += 4 * 512) {
+        uint32_t dpre[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) { const uint32_t q = pos0 + u * 512; dpre[u] = (q < te && q < end) ? lk[q] : 0; }   // independent loads first
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t pos = pos0 + u * 512;
+            if (pos >= te) break;
+            uint32_t out = 0;
+            if (pos < end) {
+                const uint32_t si = pos + sbase;
+                const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
+                uint32_t d = dpre[u], total = 0, j = pos;
+                bool found = false;
+                while (d) {
+                    total += d;
+                    if (total > E.window) break;
+                    j -= d;
+                    const uint32_t sj = j + sbase;
+                    const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
+                    if (tj == t) { found = true; break; }
+                    d = lk[j];
+                }
+                if (found) {
+                    const uint32_t a = si + 3, b = j + sbase + 3;
+                    const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
+                    uint32_t k = 0;
+                    while (k < limit) {
+                        const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
+                        if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        k += 4;
+                    }
+                    if (k > limit) k = limit;
+                    out = ((3 + k) << 16) | total;
+                }
             }
+            md[pos] = out;
         }
-        sdist[pos - ts] = (uint16_t)dist;
-    }
-    __syncthreads();
-    {   // leftovers: one warp per position scans the window backwards, 32 positions per step, for the most recent equal trigram
-        const uint32_t nlong = nq;
-        for (uint32_t i = wid; i < nlong; i += kMatchThreads / 32) {
-            const uint32_t pos = ts + queue[i];
-            const uint32_t t = ld32u(sb, pos + sbase) & 0xFFFFFFu;
-            const uint32_t first = pos > E.window ? pos - E.window : 0;     // oldest admissible candidate
-            uint32_t dist = 0;
-            for (uint32_t hi_pos = pos; hi_pos > first;) {
-                const uint32_t base = hi_pos >= 32 ? hi_pos - 32 : 0;        // candidates base .. hi_pos-1
-                const uint32_t j = base + lane;
-                const bool m = j < hi_pos && j >= first && (ld32u(sb, j + sbase) & 0xFFFFFFu) == t;
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m);
-                if (bal) { dist = pos - (base + (31 - __clz((int)bal))); break; }
-                hi_pos = base;
-            }
-            if (lane == 0) sdist[pos - ts] = (uint16_t)dist;
-        }
-        __syncthreads();
-        if (tid == 0) nq = 0;
-        __syncthreads();
-    }
-    // ---- phase B1: heads -> dense queue (warp-aggregated append)
-    for (uint32_t base = ts; base < te; base += kMatchThreads) {
-        const uint32_t pos = base + tid;
-        bool head = false;
-        if (pos < te) {
-            const uint32_t d = sdist[pos - ts];
-            head = d != 0 && (pos == ts || sdist[pos - ts - 1] != d || ((pos - ts) & 255u) == 0);
-        }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, head);
-        uint32_t wbase = 0;
-        if (lane == 0 && bal) wbase = atomicAdd(&nq, (uint32_t)__popc(bal));
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        if (head) queue[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(pos - ts);
-    }
-    __syncthreads();
-    // ---- phase B2: every head finds the end of its matching region (exclusive), scanning at most kScanCap bytes
-    const uint32_t nheads = nq;
-    for (uint32_t i = tid; i < nheads; i += kMatchThreads) {
-        const uint32_t rel = queue[i], pos = ts + rel;
-        const uint32_t d = sdist[rel];
-        const uint32_t a = pos + sbase + 3, bsrc = a - d;
-        const uint32_t limit = min(kScanCap - 3, n - (pos + 3));          // bytes beyond the trigram that may be compared
-        uint32_t k = 0;
-        while (k < limit) {
-            const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, bsrc + k);
-            if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-            k += 4;
-        }
-        if (k > limit) k = limit;
-        send[rel] = (uint16_t)(rel + 3 + k);                               // tile-relative end of the matching region (<= kPTile + kScanCap)
-    }
-    __syncthreads();
-    // ---- phase C: each thread owns kPTile / kMatchThreads consecutive positions; the head in force at its first position comes
-    // from a block-wide max-scan of "last head position"
-    constexpr uint32_t PER = kPTile / kMatchThreads;
-    const uint32_t r0 = tid * PER;
-    int32_t last = -1;
-    for (uint32_t i = 0; i < PER; i++) {
-        const uint32_t rel = r0 + i;
-        if (ts + rel < te) {
-            const uint32_t d = sdist[rel];
-            if (d != 0 && (rel == 0 || sdist[rel - 1] != d || (rel & 255u) == 0)) last = (int32_t)rel;
-        }
-    }
-    int32_t inc = last;
-    for (int dlt = 1; dlt < 32; dlt <<= 1) { const int32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, dlt); if ((int)lane >= dlt) inc = max(inc, v); }
-    if (lane == 31) wcarry[wid] = inc;
-    __syncthreads();
-    int32_t carry = -1;
-    for (uint32_t w = 0; w < wid; w++) carry = max(carry, wcarry[w]);
-    const int32_t prev_lane = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-    if (lane > 0) carry = max(carry, prev_lane);
-    int32_t cur = carry;                                                  // head in force before this thread's first position
-    for (uint32_t i = 0; i < PER; i++) {
-        const uint32_t rel = r0 + i, pos = ts + rel;
-        if (pos >= te) break;
-        const uint32_t d = sdist[rel];
-        uint32_t out = 0;
-        if (d != 0) {
-            if (rel == 0 || sdist[rel - 1] != d || (rel & 255u) == 0) cur = (int32_t)rel;
-            const uint32_t e = send[cur];                                   // the run's match end
-            uint32_t len = e - rel;
-            if (len > E.max_len) len = E.max_len;
-            out = (len << 16) | d;
-        }
-        md[pos] = out;
     }
 }
 
@@ -589,7 +494,7 @@ cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm) {
     if (tm) tm->mark(st, "lz_chain");
     k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 4, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "lz_match");
-    k_lz_match<<<E.n_ptiles, kMatchThreads, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
+    k_lz_match<<<E.n_ptiles, 512, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_exits");
     k_parse_exits<<<(E.n_tiles + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_stitch");

@@ -171,6 +171,9 @@ typedef struct b2f_stats {
 int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out);
 const char *b2f_stage_name(b2f_ctx *ctx, uint32_t stage);   /* name of stage i of the last call */
 void *b2f_ctx_stream(b2f_ctx *ctx);   /* cudaStream_t the ctx launches on */
+/* 1 (default): independent chunk slices of the LZ77 stage run concurrently on internal streams; 0: every kernel runs alone on
+ * the ctx stream, so that b2f_get_stats reports one duration per kernel (used for roofline measurements). */
+int b2f_ctx_set_overlap(b2f_ctx *ctx, int on);
 
 #ifdef __cplusplus
 }

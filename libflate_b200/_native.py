@@ -35,7 +35,7 @@ EXPORTS = [
     "b2f_adler32_batch", "b2f_crc32_batch", "b2f_encode_device", "b2f_decode_device", "b2f_header_len",
     "b2f_encoder_new", "b2f_encoder_write", "b2f_encoder_flush", "b2f_encoder_finish", "b2f_encoder_free",
     "b2f_decoder_new", "b2f_decoder_read", "b2f_decoder_unread", "b2f_decoder_consumed", "b2f_decoder_free",
-    "b2f_get_stats", "b2f_stage_name", "b2f_ctx_stream",
+    "b2f_get_stats", "b2f_stage_name", "b2f_ctx_stream", "b2f_ctx_set_overlap",
 ]
 
 _lib = None
@@ -86,6 +86,7 @@ def lib():
         L.b2f_stage_name.argtypes = [vp, C.c_uint32]
         L.b2f_ctx_stream.restype = vp
         L.b2f_ctx_stream.argtypes = [vp]
+        L.b2f_ctx_set_overlap.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -285,6 +286,9 @@ class Context:
 
     def adler32(self, datas, init=None):
         return self._cksum(lib().b2f_adler32_batch, datas, init)
+
+    def set_overlap(self, on):
+        self._check(lib().b2f_ctx_set_overlap(self._h, 1 if on else 0))
 
     # ---- stats
     def stats(self):

@@ -66,6 +66,9 @@ struct b2f_ctx {
     const char *stage_names[16];
     bool last_is_decode = false;
     uint64_t n_spec_members = 0, n_inorder_members = 0;
+    cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t aux_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    int overlap = 1;               // run independent chunk slices of the LZ77 stage on separate streams
 };
 
 static thread_local std::string g_create_err;
@@ -95,6 +98,9 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
         return B2F_ERR_CUDA;
     }
     ctx->tm.create();
+    for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+    for (auto &ev : ctx->aux_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (const char *o = getenv("B2F_OVERLAP")) ctx->overlap = atoi(o);
     *out = ctx;
     return B2F_OK;
 }
@@ -105,10 +111,13 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     for (auto &b : ctx->buf) b.release();
     ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release(); ctx->pin_cand.release(); ctx->pin_blk.release(); ctx->pin_ser.release(); ctx->pin_sel.release();
     ctx->tm.destroy();
+    for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
+    for (auto &ev : ctx->aux_ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 extern "C" const char *b2f_last_error(const b2f_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" int b2f_ctx_set_overlap(b2f_ctx *ctx, int on) { if (!ctx) return B2F_ERR_INVALID_ARG; ctx->overlap = on ? 1 : 0; return B2F_OK; }
 extern "C" void *b2f_ctx_stream(b2f_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out) { if (!ctx || !out) return B2F_ERR_INVALID_ARG; ctx->stats.decode_parallel_streams = ctx->n_spec_members; ctx->stats.decode_inorder_streams = ctx->n_inorder_members; *out = ctx->stats; return B2F_OK; }
 extern "C" const char *b2f_stage_name(b2f_ctx *ctx, uint32_t i) { return (ctx && i < 16 && ctx->stage_names[i]) ? ctx->stage_names[i] : ""; }
@@ -455,8 +464,8 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     ctx->tm.mark(ctx->stream, "clear");
     CK(cudaMemsetAsync(E.hist, 0, hist_bytes, ctx->stream));
     CK(cudaMemsetAsync(ctx->buf[NB_OUT].p, 0, out_total, ctx->stream));
-    CK(enc_launch_lz(E, ctx->stream, &ctx->tm));
-    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz();
+    CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u));
+    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz() * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
     CK(enc_launch_entropy(E, ctx->stream, &ctx->tm));
     ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0);
     // checksums over the inputs (C1/C2) -> trailers
@@ -661,7 +670,7 @@ extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, ui
     uint64_t *d_total = reinterpret_cast<uint64_t *>(tp);
     E.hist = ctx->buf[NB_BLK].as<uint32_t>();
     CK(cudaMemsetAsync(E.hist, 0, kHistStride * 4, ctx->stream));
-    CK(enc_launch_lz(E, ctx->stream, &ctx->tm));
+    CK(enc_launch_lz(E, pref, pref + 2, pref + 4, pref + 6, ctx->stream, &ctx->tm, nullptr, nullptr, 0));
     uint32_t *d_codes = ctx->buf[NB_OUT].as<uint32_t>();
     CK(enc_launch_compact(E, tile_symoff, d_total, d_codes, ctx->stream));
     ctx->stats.kernel_launches += enc_launch_count_lz() + 2;

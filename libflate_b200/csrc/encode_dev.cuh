@@ -56,7 +56,8 @@ struct StageTimer {
 };
 
 cudaError_t enc_init_attributes();
-cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm);
+cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
+                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux);
 cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm);
 cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t *total, uint32_t *dst, cudaStream_t st);
 uint32_t enc_launch_count_lz();

@@ -41,11 +41,11 @@ __device__ __forceinline__ uint32_t ld_in32(const uint8_t *__restrict__ in, uint
 // link[p] = distance to the nearest earlier position of the same chunk whose trigram has the same
 // 14-bit hash (0 = none within 32768).  Every position < end is "inserted" exactly once in
 // increasing order (default.rs:78, 92-97), so this ordered chain is parse independent.
-__global__ void __launch_bounds__(32) k_lz_chain(EncDev E) {
+__global__ void __launch_bounds__(32) k_lz_chain(EncDev E, uint32_t off) {
     extern __shared__ uint32_t head[];       // 1 << kHashBits entries: last position + 1 (exact: a 16-bit modulo entry would alias
                                              // stale buckets into bogus in-window links and send lz_match down unrelated chains)
     const uint32_t lane = threadIdx.x;
-    const uint32_t seg = blockIdx.x;
+    const uint32_t seg = blockIdx.x + off;
     const uint32_t c = find_owner(E.seg0, E.n_chunks, seg);
     const ChunkDesc cd = E.chunks[c];
     const uint32_t n = cd.len;
@@ -114,10 +114,10 @@ constexpr uint32_t kMatchSmem = kPTile + kLookback + 261 + 16 + 32;
 
 // md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
 // the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
-__global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
+__global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
     extern __shared__ __align__(16) uint8_t sb[];
     const uint32_t tid = threadIdx.x;
-    const uint32_t pt = blockIdx.x;
+    const uint32_t pt = blockIdx.x + off;
     const uint32_t c = find_owner(E.pt0, E.n_chunks, pt);
     const ChunkDesc cd = E.chunks[c];
     const uint32_t n = cd.len;
@@ -186,10 +186,10 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E) {
 // Greedy walk i -> i + step(i), step = match length or 1.  For a tile [ts,te) and each of the <= 258
 // positions a previous tile can jump into, exit = (first position >= te reached) - te  (SURVEY App. C).
 constexpr uint32_t kRing = 260;
-__global__ void __launch_bounds__(64) k_parse_exits(EncDev E) {
+__global__ void __launch_bounds__(64) k_parse_exits(EncDev E, uint32_t off, uint32_t lim) {
     __shared__ uint16_t ring[64 * kRing];
-    const uint32_t tile = blockIdx.x * 64 + threadIdx.x;
-    if (tile >= E.n_tiles) return;
+    const uint32_t tile = blockIdx.x * 64 + threadIdx.x + off;
+    if (tile >= lim) return;
     const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
     const ChunkDesc cd = E.chunks[c];
     const uint32_t n = cd.len;
@@ -209,9 +209,9 @@ __global__ void __launch_bounds__(64) k_parse_exits(EncDev E) {
 }
 
 // =============================================================================== K4 parse_stitch
-__global__ void __launch_bounds__(64) k_parse_stitch(EncDev E) {
-    const uint32_t c = blockIdx.x * 64 + threadIdx.x;
-    if (c >= E.n_chunks) return;
+__global__ void __launch_bounds__(64) k_parse_stitch(EncDev E, uint32_t off, uint32_t lim) {
+    const uint32_t c = blockIdx.x * 64 + threadIdx.x + off;
+    if (c >= lim) return;
     const uint32_t t0 = E.tile0[c], t1 = E.tile0[c + 1];
     uint32_t p = 0;
     for (uint32_t t = t0; t < t1; t++) {
@@ -221,9 +221,9 @@ __global__ void __launch_bounds__(64) k_parse_stitch(EncDev E) {
 }
 
 // =============================================================================== K5 parse_emit
-__global__ void __launch_bounds__(64) k_parse_emit(EncDev E) {
+__global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
     __shared__ uint32_t sh[kHistStride];
-    const uint32_t grp = blockIdx.x;
+    const uint32_t grp = blockIdx.x + off;
     const uint32_t c = find_owner(E.grp0, E.n_chunks, grp);
     const ChunkDesc cd = E.chunks[c];
     for (uint32_t i = threadIdx.x; i < kHistStride; i += 64) sh[i] = 0;
@@ -489,18 +489,45 @@ cudaError_t enc_init_attributes() {
     return e;
 }
 
-cudaError_t enc_launch_lz(const EncDev &E, cudaStream_t st, StageTimer *tm) {
-    if (E.n_chunks == 0) return cudaSuccess;
+// One slice = a contiguous range of chunks [c0, c1): chain -> match -> exits -> stitch -> emit, in order, on one stream.
+static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
+                                       uint32_t c0, uint32_t c1, cudaStream_t st, StageTimer *tm) {
+    if (c1 <= c0) return cudaSuccess;
+    const uint32_t nseg = h_seg0[c1] - h_seg0[c0], npt = h_pt0[c1] - h_pt0[c0], nt = h_tile0[c1] - h_tile0[c0], ng = h_grp0[c1] - h_grp0[c0];
     if (tm) tm->mark(st, "lz_chain");
-    k_lz_chain<<<E.n_segs, 32, (1u << kHashBits) * 4, st>>>(E); B2F_LAUNCH_CHECK();
+    k_lz_chain<<<nseg, 32, (1u << kHashBits) * 4, st>>>(E, h_seg0[c0]); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "lz_match");
-    k_lz_match<<<E.n_ptiles, 512, kMatchSmem, st>>>(E); B2F_LAUNCH_CHECK();
+    k_lz_match<<<npt, 512, kMatchSmem, st>>>(E, h_pt0[c0]); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_exits");
-    k_parse_exits<<<(E.n_tiles + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    k_parse_exits<<<(nt + 63) / 64, 64, 0, st>>>(E, h_tile0[c0], h_tile0[c1]); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_stitch");
-    k_parse_stitch<<<(E.n_chunks + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    k_parse_stitch<<<(c1 - c0 + 63) / 64, 64, 0, st>>>(E, c0, c1); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_emit");
-    k_parse_emit<<<E.n_grps, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    k_parse_emit<<<ng, 64, 0, st>>>(E, h_grp0[c0]); B2F_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+// LZ77 stage.  With aux streams the chunks are split into slices that run concurrently: the chain / exits kernels are
+// latency bound (one warp per segment / thread per tile) and leave most issue slots free for the match kernel of another slice.
+cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
+                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux) {
+    if (E.n_chunks == 0) return cudaSuccess;
+    if (n_aux < 2 || E.n_chunks < 2 * n_aux) return enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, 0, E.n_chunks, st, tm);
+    if (tm) tm->mark(st, "lz_pipeline");
+    cudaError_t e = cudaEventRecord(ev[0], st); if (e != cudaSuccess) return e;
+    // slices balanced by match tiles (proportional to bytes)
+    const uint32_t total = h_pt0[E.n_chunks];
+    uint32_t c0 = 0;
+    for (uint32_t g = 0; g < n_aux; g++) {
+        uint32_t c1 = c0;
+        const uint32_t want = (uint32_t)((uint64_t)total * (g + 1) / n_aux);
+        while (c1 < E.n_chunks && (h_pt0[c1] < want || g + 1 == n_aux)) c1++;
+        e = cudaStreamWaitEvent(aux[g], ev[0], 0); if (e != cudaSuccess) return e;
+        e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g], nullptr); if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ev[1 + g], aux[g]); if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(st, ev[1 + g], 0); if (e != cudaSuccess) return e;
+        c0 = c1;
+    }
     return cudaSuccess;
 }
 cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm) {

@@ -19,5 +19,10 @@ for it in range(3):
     sd = ctx.stats()
 assert st == 0 and out == d.tobytes()
 print(f"input {mib} MiB  ratio {len(enc)/d.size:.4f}  encode wall {te*1e3:.1f} ms  decode wall {td*1e3:.1f} ms")
+ctx.set_overlap(False)
+enc2 = ctx.encode(native.FMT_GZIP, d, sched, mtime=0); se2 = ctx.stats()
+assert enc2 == enc
+print("encode (overlap) :", " ".join(f"{n}={ms:.3f}" for n, ms in se["stages"]), f"| device {se['device_ms']:.3f}")
+se = se2
 print("encode stages (ms):", " ".join(f"{n}={ms:.3f}" for n, ms in se["stages"]), f"| device {se['device_ms']:.3f}")
 print("decode stages (ms):", " ".join(f"{n}={ms:.3f}" for n, ms in sd["stages"]), f"| device {sd['device_ms']:.3f}")

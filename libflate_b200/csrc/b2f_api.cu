@@ -380,6 +380,7 @@ __global__ void k_write_framing(uint8_t *out, const uint64_t *out_base, const ui
 struct EncodeJob {
     // device-resident inputs
     const uint8_t *d_in; std::vector<uint64_t> in_off; std::vector<uint64_t> in_len;
+    const uint8_t *const *h_in = nullptr;     // when set, the inputs still live on the host: encode_on_device copies them slice by slice
     // results
     std::vector<uint64_t> out_base; std::vector<uint64_t> out_len;   // in ctx->buf[NB_OUT]
 };
@@ -464,7 +465,18 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     ctx->tm.mark(ctx->stream, "clear");
     CK(cudaMemsetAsync(E.hist, 0, hist_bytes, ctx->stream));
     CK(cudaMemsetAsync(ctx->buf[NB_OUT].p, 0, out_total, ctx->stream));
-    CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u));
+    struct FeedCtx { b2f_ctx *ctx; const EncPlan *P; const EncodeJob *job; uint8_t *d_in; } fc = { ctx, &P, &job, const_cast<uint8_t *>(job.d_in) };
+    SliceFeed feed = { &fc, [](void *self, uint32_t c0, uint32_t c1, cudaStream_t st) -> cudaError_t {
+        FeedCtx *f = (FeedCtx *)self;
+        if (c1 <= c0) return cudaSuccess;
+        const uint64_t lo = f->P->chunks[c0].off, hi = f->P->chunks[c1 - 1].off + f->P->chunks[c1 - 1].len;   // device byte range of the slice
+        for (size_t s = 0; s < f->job->in_off.size(); s++) {     // streams are laid out in increasing in_off order
+            const uint64_t a = std::max<uint64_t>(lo, f->job->in_off[s]), b = std::min<uint64_t>(hi, f->job->in_off[s] + f->job->in_len[s]);
+            if (a < b) { cudaError_t e = cudaMemcpyAsync(f->d_in + a, f->job->h_in[s] + (a - f->job->in_off[s]), b - a, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e; }
+        }
+        return cudaSuccess; } };
+    CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u,
+                     job.h_in ? &feed : nullptr));
     if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz() * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
     CK(enc_launch_entropy(E, ctx->stream, &ctx->tm));
     ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0);
@@ -597,10 +609,10 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
     }
     CK(ctx->buf[NB_IN].ensure(total + 512));
     uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>();
-    ctx->tm.mark(ctx->stream, "h2d");
-    for (size_t s = 0; s < n_streams; s++) if (job.in_len[s]) CK(cudaMemcpyAsync(d_in + job.in_off[s], in[s], job.in_len[s], cudaMemcpyHostToDevice, ctx->stream));
     job.d_in = d_in;
     if (opts->mode == B2F_MODE_STORED) {
+        ctx->tm.mark(ctx->stream, "h2d");
+        for (size_t s = 0; s < n_streams; s++) if (job.in_len[s]) CK(cudaMemcpyAsync(d_in + job.in_off[s], in[s], job.in_len[s], cudaMemcpyHostToDevice, ctx->stream));
         std::vector<uint32_t> crc, adler;
         rc = run_checksums(ctx, d_in, job.in_off, job.in_len, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
         if (rc) return rc;
@@ -616,6 +628,7 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         collect_stats(ctx, false);
         return B2F_OK;
     }
+    job.h_in = in;                         // the H2D copies are issued per slice inside the LZ77 stage
     rc = encode_on_device(ctx, fmt, *opts, n_streams, sched, n_sched, job);
     if (rc) return rc;
     collect_stats(ctx, false);
@@ -670,7 +683,7 @@ extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, ui
     uint64_t *d_total = reinterpret_cast<uint64_t *>(tp);
     E.hist = ctx->buf[NB_BLK].as<uint32_t>();
     CK(cudaMemsetAsync(E.hist, 0, kHistStride * 4, ctx->stream));
-    CK(enc_launch_lz(E, pref, pref + 2, pref + 4, pref + 6, ctx->stream, &ctx->tm, nullptr, nullptr, 0));
+    CK(enc_launch_lz(E, pref, pref + 2, pref + 4, pref + 6, ctx->stream, &ctx->tm, nullptr, nullptr, 0, nullptr));
     uint32_t *d_codes = ctx->buf[NB_OUT].as<uint32_t>();
     CK(enc_launch_compact(E, tile_symoff, d_total, d_codes, ctx->stream));
     ctx->stats.kernel_launches += enc_launch_count_lz() + 2;

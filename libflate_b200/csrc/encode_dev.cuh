@@ -55,9 +55,12 @@ struct StageTimer {
     float total_ms() const { float ms = 0; if (n > 0) cudaEventElapsedTime(&ms, ev[0], ev[n]); return ms; }
 };
 
+// optional host->device feed of the input, one call per slice of chunks [c0, c1), on the stream that will process the slice
+struct SliceFeed { void *self; cudaError_t (*copy)(void *self, uint32_t c0, uint32_t c1, cudaStream_t st); };
+
 cudaError_t enc_init_attributes();
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
-                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux);
+                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed);
 cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm);
 cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t *total, uint32_t *dst, cudaStream_t st);
 uint32_t enc_launch_count_lz();

@@ -510,9 +510,12 @@ static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, 
 // LZ77 stage.  With aux streams the chunks are split into slices that run concurrently: the chain / exits kernels are
 // latency bound (one warp per segment / thread per tile) and leave most issue slots free for the match kernel of another slice.
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
-                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux) {
+                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed) {
     if (E.n_chunks == 0) return cudaSuccess;
-    if (n_aux < 2 || E.n_chunks < 2 * n_aux) return enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, 0, E.n_chunks, st, tm);
+    if (n_aux < 2 || E.n_chunks < 2 * n_aux) {
+        if (feed) { if (tm) tm->mark(st, "h2d"); cudaError_t fe = feed->copy(feed->self, 0, E.n_chunks, st); if (fe != cudaSuccess) return fe; }
+        return enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, 0, E.n_chunks, st, tm);
+    }
     if (tm) tm->mark(st, "lz_pipeline");
     cudaError_t e = cudaEventRecord(ev[0], st); if (e != cudaSuccess) return e;
     // slices balanced by match tiles (proportional to bytes)
@@ -523,6 +526,7 @@ cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_
         const uint32_t want = (uint32_t)((uint64_t)total * (g + 1) / n_aux);
         while (c1 < E.n_chunks && (h_pt0[c1] < want || g + 1 == n_aux)) c1++;
         e = cudaStreamWaitEvent(aux[g], ev[0], 0); if (e != cudaSuccess) return e;
+        if (feed) { e = feed->copy(feed->self, c0, c1, aux[g]); if (e != cudaSuccess) return e; }   // this slice's H2D overlaps the previous slices' kernels
         e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g], nullptr); if (e != cudaSuccess) return e;
         e = cudaEventRecord(ev[1 + g], aux[g]); if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st, ev[1 + g], 0); if (e != cudaSuccess) return e;

@@ -117,7 +117,7 @@ def cpu_baseline(cores, shard_mib, steps, warmup):
     return cores * shard / dt / GIB, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
@@ -133,7 +133,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": round(val, 4), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -147,8 +147,17 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout carries exactly ONE JSON line: libraries (NCCL's version banner, ...) that print to fd 1 are diverted to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -302,7 +311,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

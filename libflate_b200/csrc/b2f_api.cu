@@ -774,8 +774,8 @@ struct Packer {
 constexpr uint64_t kParallelMinBytes = 128 * 1024;    // smaller streams are decoded in order by one warp each
 
 // Decodes one "round": members[] are raw DEFLATE streams inside d_in; outputs to d_out.  Results to host vectors.
-//  - large members: block-boundary finder -> probe every candidate -> verify the chain of block ends from bit 0 ->
-//    decode all blocks of the chain in parallel (one warp per block, 64 KiB window in shared memory);
+//  - large members: block-boundary finder -> speculative sub-block parse of every candidate block -> verify the chain of
+//    block ends from bit 0 -> tokens -> independent LZ77 units resolved in parallel (spec_kernels.cu);
 //  - small members, and any member whose chain is not clean (non-dynamic blocks, cross-block back-references,
 //    errors, too-small output): in-order kernel, which reproduces libflate's error kinds and partial output.
 int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::vector<Member> &mem,

@@ -26,26 +26,7 @@ struct FindDev {
     uint32_t *q_member; uint64_t *q_bit; uint32_t *q_count; uint32_t q_cap;            // offsets that passed the cheap tests
     uint32_t *cand_member; uint64_t *cand_bit; uint32_t *cand_count; uint32_t cand_cap;   // fully validated candidates
 };
-// candidate probe (pass 1) and block decode (pass 2)
-struct BlockDev {
-    const uint8_t *in;
-    const uint64_t *in_off, *in_len;     // per member
-    uint32_t n_blocks;
-    const uint32_t *blk_member;          // [n_blocks]
-    const uint64_t *blk_bit;             // [n_blocks] start bit inside the member
-    const uint64_t *blk_stop;            // [n_blocks] probe stop bit (pass 1)
-    // pass 1 results
-    int32_t *p_status; uint64_t *p_end_bit; uint64_t *p_out_len; uint32_t *p_flags;   // flags: 1 final, 2 needs earlier history
-    // pass 2 inputs/results
-    uint8_t *out;
-    const uint64_t *blk_out;             // [n_blocks] absolute output offset of the block
-    const uint64_t *mem_out_off;         // per member: start of its output
-    const uint64_t *mem_out_end;         // per member: out_off + cap
-    int32_t *d_status; uint64_t *d_out_len;
-};
 cudaError_t dec_init_attributes();
 cudaError_t dec_launch_serial(const DecDev &D, cudaStream_t st);
 cudaError_t dec_launch_find(const FindDev &F, cudaStream_t st);
-cudaError_t dec_launch_probe(const BlockDev &B, cudaStream_t st);
-cudaError_t dec_launch_blocks(const BlockDev &B, cudaStream_t st);
 }

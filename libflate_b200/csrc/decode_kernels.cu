@@ -1,8 +1,7 @@
 // decode_kernels.cu -- DEFLATE decode hot path (sm_100a).
 //   k_find_blocks      every bit offset of a stream is tested for a plausible dynamic-block header
 //                      (CTA-local two-level compaction: 17-bit precheck -> code-length-code Kraft test -> full validation)
-//   k_probe_blocks     warp per candidate: Huffman-decodes ONE block without producing output -> end bit, size, flags
-//   k_inflate_blocks   warp per verified block: full decode, 64 KiB output window in shared memory, coalesced flushes
+//   (the candidates feed the sub-block parallel inflate in spec_kernels.cu)
 //   k_inflate_streams  warp per stream, blocks in order (small streams, foreign streams with cross-block references,
 //                      streams with stored/fixed blocks, and every error path -- it reproduces the reference's error
 //                      kinds and partial output exactly)
@@ -67,18 +66,6 @@ struct WindowOut {
     __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
     __device__ __forceinline__ int fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base);
 };
-
-// pass 1: no output, only sizes; notes back-references that reach before the block's own start
-struct CountOut {
-    uint32_t far;
-    __device__ __forceinline__ uint64_t cap() const { return ~0ull; }
-    __device__ __forceinline__ void lit(uint64_t, uint8_t) {}
-    __device__ __forceinline__ void copy(uint64_t pos, uint32_t, uint32_t dist) { if (dist > pos) far = 1; }
-    __device__ __forceinline__ void raw(uint64_t, const uint8_t *, uint64_t) {}
-    __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
-    __device__ __forceinline__ int fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base);
-};
-
 
 // ---------------------------------------------------------------------------------- fast symbol loop (device only)
 // Register-resident bit buffer with a prefetched input word, explicit 32-bit shared-memory addresses for the decode tables
@@ -168,7 +155,6 @@ __device__ __forceinline__ int fast_symbols(BitIn &b, const InflateTables &T, ui
 }
 
 __device__ __forceinline__ int WindowOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { uint32_t f = 0; return fast_symbols<false>(b, T, out_pos, hist_base, capacity, ring, flushed, g, lane, f); }
-__device__ __forceinline__ int CountOut::fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base) { uint64_t fl = 0; return fast_symbols<true>(b, T, out_pos, hist_base, ~0ull, nullptr, fl, nullptr, 0, far); }
 
 constexpr uint32_t kWinSmem = kRingBytes + (uint32_t)sizeof(InflateTables) + 64;
 
@@ -262,55 +248,8 @@ __global__ void __launch_bounds__(128) k_validate_candidates(FindDev F) {
     }
 }
 
-// ---------------------------------------------------------------------------------- pass 1: probe
-constexpr uint32_t kProbeWarps = 4;
-__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_blocks(BlockDev B) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    InflateTables *tabs = reinterpret_cast<InflateTables *>(smem_raw);
-    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t i = blockIdx.x * kProbeWarps + wid;
-    if (i >= B.n_blocks) return;
-    const uint32_t m = B.blk_member[i];
-    BitIn b;
-    const uint8_t *p0 = B.in + B.in_off[m];
-    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
-    bi_init(b, p0 - lead, B.in_len[m] + lead, B.blk_bit[i] + 8ull * lead);
-    b.stop = B.blk_stop[i] > ~0ull - 64 ? ~0ull : B.blk_stop[i] + 8ull * lead;
-    CountOut out = { 0 };
-    InflateResult R;
-    inflate_blocks(b, tabs[wid], out, 0, 1ull << 60, 1, (int)lane, 32, WarpSync(), R);
-    if (lane == 0) {
-        B.p_status[i] = R.status; B.p_end_bit[i] = R.end_bit - 8ull * lead; B.p_out_len[i] = R.out_len;
-        B.p_flags[i] = (R.final_seen ? 1u : 0u) | (out.far ? 2u : 0u);
-    }
-}
-
-// ---------------------------------------------------------------------------------- pass 2: block-parallel decode
-__global__ void __launch_bounds__(32) k_inflate_blocks(BlockDev B) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t *ring = smem_raw;
-    InflateTables &T = *reinterpret_cast<InflateTables *>(smem_raw + kRingBytes);
-    const uint32_t lane = threadIdx.x, i = blockIdx.x;
-    if (i >= B.n_blocks) return;
-    const uint32_t m = B.blk_member[i];
-    BitIn b;
-    const uint8_t *p0 = B.in + B.in_off[m];
-    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);
-    bi_init(b, p0 - lead, B.in_len[m] + lead, B.blk_bit[i] + 8ull * lead);
-    const uint64_t o0 = B.blk_out[i];
-    WindowOut out = { ring, B.out, B.mem_out_end[m], o0, lane };
-    InflateResult R;
-    inflate_blocks(b, T, out, o0, 0ull - B.mem_out_off[m], 1, (int)lane, 32, WarpSync(), R);
-    out.flush_to(R.out_len);
-    if (lane == 0) { B.d_status[i] = R.status; B.d_out_len[i] = R.out_len - o0; }
-}
-
 cudaError_t dec_init_attributes() {
-    cudaError_t e = cudaFuncSetAttribute(k_inflate_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_inflate_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_probe_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kProbeWarps * sizeof(InflateTables)));
+    return cudaFuncSetAttribute(k_inflate_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);
 }
 cudaError_t dec_launch_serial(const DecDev &D, cudaStream_t st) {
     if (D.n == 0) return cudaSuccess;
@@ -324,15 +263,4 @@ cudaError_t dec_launch_find(const FindDev &F, cudaStream_t st) {
     k_validate_candidates<<<(F.q_cap + 127) / 128, 128, 0, st>>>(F);      // grid sized for the queue capacity; idle threads exit at once
     return cudaGetLastError();
 }
-cudaError_t dec_launch_probe(const BlockDev &B, cudaStream_t st) {
-    if (B.n_blocks == 0) return cudaSuccess;
-    k_probe_blocks<<<(B.n_blocks + kProbeWarps - 1) / kProbeWarps, kProbeWarps * 32, kProbeWarps * sizeof(InflateTables), st>>>(B);
-    return cudaGetLastError();
-}
-cudaError_t dec_launch_blocks(const BlockDev &B, cudaStream_t st) {
-    if (B.n_blocks == 0) return cudaSuccess;
-    k_inflate_blocks<<<B.n_blocks, 32, kWinSmem, st>>>(B);
-    return cudaGetLastError();
-}
-
 }  // namespace b2f

@@ -363,7 +363,6 @@ __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volati
 // The ring keeps the most recent kResRing bytes; every step is written through to HBM, so sources older than the ring are
 // read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
 constexpr uint32_t kResRing = 24576;
-__device__ __forceinline__ uint32_t rix(uint32_t a) { return a % kResRing; }
 
 __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
     extern __shared__ __align__(16) uint8_t ring[];
@@ -377,8 +376,12 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
     const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
     uint8_t *__restrict__ g = S.out;
     uint64_t pos = out0;
+    uint32_t rpos = (uint32_t)(out0 % kResRing);                 // ring index of `pos` (kept incrementally: no modulo in the loop)
     uint32_t err = 0;
     uint32_t tnext = lane < ntok ? __ldg(tok + lane) : 0u;
+    // ring index of the byte `off` bytes after the step start (off < kResRing) / `back` bytes before index i (back <= kResRing)
+    #define RFWD(off) ((rpos + (off)) >= kResRing ? (rpos + (off)) - kResRing : (rpos + (off)))
+    #define RBACK(i, back) ((i) >= (back) ? (i) - (back) : (i) + kResRing - (back))
     for (uint64_t i0 = 0; i0 < ntok; i0 += 32) {
         const uint32_t tk = tnext;
         const uint64_t in = i0 + 32 + lane;
@@ -389,41 +392,51 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
         uint32_t incl = len;
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const uint64_t dst = pos + incl - len;
-        const uint32_t dst32 = (uint32_t)dst;
-        if (live && !is_m) ring[rix(dst32)] = (uint8_t)tk;
+        const uint32_t off = incl - len;                          // offset of this token's output inside the step
+        if (live && !is_m) ring[RFWD(off)] = (uint8_t)tk;
         const uint32_t dist = tk & 0xFFFFu;
+        const uint64_t dst = pos + off;
         if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
-        const uint32_t step_end = (uint32_t)pos + total;
         __syncwarp();
         // matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on the
-        // bytes written just before them, so resolving them independently buys nothing)
+        // bytes written just before them, so resolving them independently buys nothing).  The parameters of the next match
+        // are fetched (shuffles) while the current one is being copied.
         uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m);
+        uint32_t j = pending ? __ffs((int)pending) - 1 : 0;
+        uint32_t n_off = __shfl_sync(0xFFFFFFFFu, off, j), n_tk = __shfl_sync(0xFFFFFFFFu, tk, j);
         while (pending) {
-            const uint32_t j = __ffs((int)pending) - 1;
+            const uint32_t moff = n_off, mtk = n_tk;
             pending &= pending - 1;
-            const uint32_t mdst = __shfl_sync(0xFFFFFFFFu, dst32, j);
-            const uint32_t mtk = __shfl_sync(0xFFFFFFFFu, tk, j);
+            if (pending) { j = __ffs((int)pending) - 1; n_off = __shfl_sync(0xFFFFFFFFu, off, j); n_tk = __shfl_sync(0xFFFFFFFFu, tk, j); }
             const uint32_t mlen = (mtk >> 16) & 0x1FFu, mdist = mtk & 0xFFFFu;
-            const uint32_t msrc = mdst - mdist;
-            if ((int32_t)(step_end - msrc) > (int32_t)kResRing) {   // source older than the ring: it was written through to HBM (never overlaps: dist > len)
-                const uint8_t *gs = g + (pos + (uint32_t)(mdst - (uint32_t)pos)) - mdist;   // exact 64-bit source address
-                for (uint32_t k = lane; k < mlen; k += 32) ring[rix(mdst + k)] = __ldcg(gs + k);
-            } else if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) ring[rix(mdst + k)] = ring[rix(msrc + k)]; }
-            else if (mdist >= 32) {                                 // overlapping, but each 32-byte slice only reads bytes of earlier slices
-                for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
-                    const uint32_t k = k0 + lane;
-                    if (k < mlen) ring[rix(mdst + k)] = ring[rix(msrc + k)];
-                    __syncwarp();
+            const uint32_t d0 = RFWD(moff);                         // ring index of the match's first output byte
+            if (mdist + (total - moff) > kResRing) {                // source older than the ring: it was written through to HBM (never overlaps: dist > len)
+                const uint8_t *gs = g + (pos + moff) - mdist;
+                for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k; if (di >= kResRing) di -= kResRing; ring[di] = __ldcg(gs + k); }
+            } else {
+                const uint32_t s0i = RBACK(d0, mdist);              // ring index of the first source byte
+                if (mdist >= mlen) {
+                    for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k, si = s0i + k; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }
+                } else if (mdist >= 32) {                           // overlapping, but each 32-byte slice only reads bytes of earlier slices
+                    for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        if (k < mlen) { uint32_t di = d0 + k, si = s0i + k; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }
+                        __syncwarp();
+                    }
+                } else {
+                    for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k, si = s0i + k % mdist; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }
                 }
-            } else { for (uint32_t k = lane; k < mlen; k += 32) ring[rix(mdst + k)] = ring[rix(msrc + k % mdist)]; }
+            }
             __syncwarp();
         }
         // write the step through to HBM
-        for (uint32_t k = lane; k < total; k += 32) g[pos + k] = ring[rix((uint32_t)pos + k)];
+        for (uint32_t k = lane; k < total; k += 32) g[pos + k] = ring[RFWD(k)];
         pos += total;
+        rpos += total; if (rpos >= kResRing) rpos -= kResRing;
         __syncwarp();
     }
+    #undef RFWD
+    #undef RBACK
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) { S.res_err[u] = err; S.res_len[u] = pos - out0; }
 }

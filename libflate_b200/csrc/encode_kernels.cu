@@ -110,33 +110,12 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *s, uint32_t off) {     
     const uint32_t *w = reinterpret_cast<const uint32_t *>(s + (off & ~3u));
     return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
-constexpr uint32_t kMatchBytes = (kPTile + kLookback + 261 + 16 + 32 + 15) & ~15u;
-constexpr uint32_t kMatchQueue = 1024;                             // deferred long walks per tile (overflow is handled inline)
-constexpr uint32_t kMatchSmem = kMatchBytes + kMatchQueue * 4;
-constexpr uint32_t kMatchHops = 8;                                 // hops walked inline; the ~1 % of positions needing more are deferred
-
-// LCP of the bytes after the trigram + md word (shared by the inline and the deferred path)
-__device__ __forceinline__ uint32_t match_word(const uint8_t *sb, uint32_t si, uint32_t sj, uint32_t limit, uint32_t total) {
-    const uint32_t a = si + 3, b = sj + 3;
-    uint32_t k = 0;
-    while (k < limit) {
-        const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
-        if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-        k += 4;
-    }
-    if (k > limit) k = limit;
-    return ((3 + k) << 16) | total;
-}
+constexpr uint32_t kMatchSmem = kPTile + kLookback + 261 + 16 + 32;
 
 // md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
 // the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
-// The chain walk averages ~1.2 hops but has a heavy tail (a rare trigram sharing a bucket with a frequent one walks
-// hundreds of links); a warp would wait for its slowest lane at every position, so walks are cut at kMatchHops and
-// the leftovers are finished afterwards by dense warps from a shared-memory queue.
 __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
     extern __shared__ __align__(16) uint8_t sb[];
-    uint32_t *queue = reinterpret_cast<uint32_t *>(sb + kMatchBytes);     // (pos - ts) << 16 | distance walked so far
-    __shared__ uint32_t nq;
     const uint32_t tid = threadIdx.x;
     const uint32_t pt = blockIdx.x + off;
     const uint32_t c = find_owner(E.pt0, E.n_chunks, pt);
@@ -153,11 +132,10 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
     const uint32_t nvec = (hi - lo + shift + 15) >> 4;
     const uint4 *__restrict__ gsrc = reinterpret_cast<const uint4 *>(E.in + g_al);
     uint4 *sdst = reinterpret_cast<uint4 *>(sb);
-    if (tid == 0) nq = 0;
     for (uint32_t i = tid; i < nvec; i += 512) {
-        const uint64_t off16 = g_al + 16ull * i;
-        if (off16 + 16 <= E.in_size) sdst[i] = __ldg(gsrc + i);
-        else { uint4 v; v.x = ld_in32(E.in, off16, E.in_size); v.y = ld_in32(E.in, off16 + 4, E.in_size); v.z = ld_in32(E.in, off16 + 8, E.in_size); v.w = ld_in32(E.in, off16 + 12, E.in_size); sdst[i] = v; }
+        const uint64_t off = g_al + 16ull * i;
+        if (off + 16 <= E.in_size) sdst[i] = __ldg(gsrc + i);
+        else { uint4 v; v.x = ld_in32(E.in, off, E.in_size); v.y = ld_in32(E.in, off + 4, E.in_size); v.z = ld_in32(E.in, off + 8, E.in_size); v.w = ld_in32(E.in, off + 12, E.in_size); sdst[i] = v; }
     }
     __syncthreads();
     const uint16_t *__restrict__ lk = E.link + cd.off;
@@ -172,46 +150,35 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
             const uint32_t pos = pos0 + u * 512;
             if (pos >= te) break;
             uint32_t out = 0;
-            bool deferred = false;
             if (pos < end) {
                 const uint32_t si = pos + sbase;
-                const uint32_t t = ld32u(sb, si) & 0xFFFFFFu;
-                uint32_t d = dpre[u], total = 0, j = pos, hops = 0;
+                const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
+                uint32_t d = dpre[u], total = 0, j = pos;
                 bool found = false;
                 while (d) {
                     total += d;
                     if (total > E.window) break;
                     j -= d;
-                    if ((ld32u(sb, j + sbase) & 0xFFFFFFu) == t) { found = true; break; }
-                    if (++hops == kMatchHops) {
-                        const uint32_t slot = atomicAdd(&nq, 1u);
-                        if (slot < kMatchQueue) { queue[slot] = ((pos - ts) << 16) | total; deferred = true; break; }
-                        hops = 0x80000000u;                          // queue full: keep walking inline
-                    }
+                    const uint32_t sj = j + sbase;
+                    const uint32_t tj = (uint32_t)sb[sj] | ((uint32_t)sb[sj + 1] << 8) | ((uint32_t)sb[sj + 2] << 16);
+                    if (tj == t) { found = true; break; }
                     d = lk[j];
                 }
-                if (found) out = match_word(sb, si, j + sbase, min(E.max_len - 3, n - (pos + 3)), total);
+                if (found) {
+                    const uint32_t a = si + 3, b = j + sbase + 3;
+                    const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
+                    uint32_t k = 0;
+                    while (k < limit) {
+                        const uint32_t x = ld32u(sb, a + k) ^ ld32u(sb, b + k);
+                        if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        k += 4;
+                    }
+                    if (k > limit) k = limit;
+                    out = ((3 + k) << 16) | total;
+                }
             }
-            if (!deferred) md[pos] = out;
+            md[pos] = out;
         }
-    }
-    __syncthreads();
-    const uint32_t nlong = min(nq, kMatchQueue);
-    for (uint32_t i = tid; i < nlong; i += 512) {                    // dense: every lane finishes one long walk
-        const uint32_t q = queue[i];
-        const uint32_t pos = ts + (q >> 16);
-        uint32_t total = q & 0xFFFFu, j = pos - total;
-        const uint32_t si = pos + sbase;
-        const uint32_t t = ld32u(sb, si) & 0xFFFFFFu;
-        uint32_t d = lk[j], out = 0;
-        while (d) {
-            total += d;
-            if (total > E.window) break;
-            j -= d;
-            if ((ld32u(sb, j + sbase) & 0xFFFFFFu) == t) { out = match_word(sb, si, j + sbase, min(E.max_len - 3, n - (pos + 3)), total); break; }
-            d = lk[j];
-        }
-        md[pos] = out;
     }
 }
 

@@ -129,9 +129,16 @@ extern "C" void b2f_encode_opts_default(b2f_encode_opts *o) {
 
 static void collect_stats(b2f_ctx *ctx, bool is_decode) {
     ctx->last_is_decode = is_decode;
-    uint32_t n = (uint32_t)std::min(ctx->tm.n, 16);
+    // stages that ran several times (retries, sync points) are summed under one name, in order of first appearance
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < 16; i++) { ctx->stats.last_kernel_ms[i] = 0.f; ctx->stage_names[i] = nullptr; }
+    for (int i = 0; i < ctx->tm.n; i++) {
+        uint32_t k = 0;
+        while (k < n && strcmp(ctx->stage_names[k], ctx->tm.name[i]) != 0) k++;
+        if (k == n) { if (n == 16) continue; ctx->stage_names[n++] = ctx->tm.name[i]; }
+        ctx->stats.last_kernel_ms[k] += ctx->tm.stage_ms(i);
+    }
     ctx->stats.last_n_stages = n;
-    for (uint32_t i = 0; i < 16; i++) { ctx->stats.last_kernel_ms[i] = i < n ? ctx->tm.stage_ms((int)i) : 0.f; ctx->stage_names[i] = i < n ? ctx->tm.name[i] : nullptr; }
     ctx->stats.last_device_ms = ctx->tm.total_ms();
 }
 
@@ -938,13 +945,31 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     auto it = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, pos));
                     if (it != cands.end() && it->first == m && it->second == pos && (it + 1) != cands.end() && (it + 1)->first == m && out <= out_cap[m]) {
                         drop.push_back(*(it + 1)); retry = true;
+                        // Keep walking to collect the other false positives of this member in the same attempt: a block whose chain is
+                        // consistent but hits the end of its extent without EndOfBlock (status 2) was cut by the candidate after it; the
+                        // candidate after THAT one is presumed true again, and verified blocks (status 0) are followed exactly.
+                        size_t idx = (size_t)(it - cands.begin());
+                        while (idx < ncand && cands[idx].first == m) {
+                            if (h_st[idx] == 2) {
+                                if (idx + 1 >= ncand || cands[idx + 1].first != m) break;
+                                drop.push_back(cands[idx + 1]);
+                                idx += 2;
+                            } else if (h_st[idx] == 0 && !(h_fl[idx] & 1u)) {
+                                auto nx = std::lower_bound(cands.begin(), cands.end(), std::make_pair(m, cands[idx].second + h_ee[idx]));
+                                if (nx == cands.end() || nx->first != m || nx->second != cands[idx].second + h_ee[idx]) break;
+                                idx = (size_t)(nx - cands.begin());
+                            } else break;
+                        }
                     }
                     continue;
                 }
                 is_par[m] = 1; st[m] = kInfOk; olen[m] = out; cons[m] = (pos + 7) >> 3;
             }
             if (retry && attempt + 1 < 12) {
-                for (auto &d : drop) cands.erase(std::remove(cands.begin(), cands.end(), d), cands.end());
+                std::sort(drop.begin(), drop.end()); drop.erase(std::unique(drop.begin(), drop.end()), drop.end());
+                std::vector<std::pair<uint32_t, uint64_t>> kept;
+                for (auto &cnd : cands) if (!std::binary_search(drop.begin(), drop.end(), cnd)) kept.push_back(cnd);
+                cands.swap(kept);
                 for (uint32_t m : big) is_par[m] = 0;
                 ctx->tm.mark(ctx->stream, "spec_retry");
                 continue;

@@ -40,7 +40,7 @@ struct EncDev {
 };
 
 struct StageTimer {
-    enum { kMax = 24 };
+    enum { kMax = 96 };
     cudaEvent_t ev[kMax + 1];
     const char *name[kMax];
     int n = 0;

@@ -231,20 +231,26 @@ __global__ void __launch_bounds__(256) k_spec_verify(SpecDev S) {
             }
         }
         __syncthreads();
-        const uint32_t e = eob_seg;
-        if (e == 0xFFFFFFFFu) { if (tid == 0) bad = 1; }
+        uint32_t e = eob_seg;
+        bool truncated = false;
+        if (e == 0xFFFFFFFFu) {
+            // no EndOfBlock before the end of the block's extent: if the chain is consistent all the way, the extent was cut
+            // short by a false-positive candidate -> status 2 tells the host to drop the candidate that follows this block
+            truncated = true; e = nseg - 1;
+        }
         __syncthreads();
-        if (!bad) {
+        {
             for (uint32_t base = k0; base <= e; base += 256) {
                 const uint32_t k = base + tid;
                 if (k <= e) {
                     const uint32_t st = S.s_start[s0 + k], ex = ex_final[s0 + k];
                     const uint32_t want = k == k0 ? data_rel : ex_final[s0 + k - 1];
-                    if (st != want || st >= kExitDead || (k < e && ex >= kExitDead)) atomicOr(&bad, 1u);
+                    if (st != want || st >= kExitDead || ((k < e || truncated) && ex >= kExitDead)) atomicOr(&bad, 1u);
                 }
             }
         }
         __syncthreads();
+        if (truncated) { if (tid == 0) { S.blk_status[b] = bad ? 1u : 2u; S.blk_nout[b] = 0; S.blk_ntok[b] = 0; S.blk_eob_end[b] = 0; } return; }
     }
     if (bad) { if (tid == 0) { S.blk_status[b] = 1; S.blk_nout[b] = 0; S.blk_ntok[b] = 0; S.blk_eob_end[b] = 0; } return; }
     const uint32_t e = eob_seg;

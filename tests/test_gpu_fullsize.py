@@ -86,8 +86,10 @@ def test_config5_many_block_gzip_decode(ctx, titles256):
     m = ctx.encode_into(native.FMT_GZIP, d, enc, sched, mtime=0)
     assert int.from_bytes(bytes(enc[m - 4:m]), "little") == n % (1 << 32)
     dec = np.empty(n + 64, dtype=np.uint8)
+    before = ctx.stats()
     dl, used, st = ctx.decode_into(native.FMT_GZIP, enc, m, dec)
+    after = ctx.stats()
     assert st == 0 and dl == n and used == m
     assert np.array_equal(dec[:n], d)
-    s = ctx.stats()
-    assert s["stages"] and any(name == "lz_resolve" for name, _ in s["stages"])         # block-parallel path, not the in-order kernel
+    assert after["decode_parallel_streams"] - before["decode_parallel_streams"] == 1     # block-parallel path, not the in-order kernel
+    assert dict(after["stages"]).get("lz_resolve", 0) > 0

@@ -759,7 +759,7 @@ int parse_zlib_header(HostReader &r) {          // zlib::Header::read_from (zlib
 }
 int map_inf_status(int s) { return s == kInfOk ? B2F_OK : s == kInfInvalid ? B2F_ERR_INVALID_DATA : s == kInfEof ? B2F_ERR_UNEXPECTED_EOF : B2F_ERR_OUTPUT_TOO_SMALL; }
 
-struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_off; uint64_t out_cap; };
+struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_off; uint64_t out_cap; uint8_t *h_out; };   // h_out: pinned host destination of this member's output (or NULL)
 
 // Packs several host arrays into one pinned staging area + one H2D copy; returns device pointers.
 struct Packer {
@@ -786,9 +786,9 @@ constexpr uint64_t kParallelMinBytes = 128 * 1024;    // smaller streams are dec
 //  - small members, and any member whose chain is not clean (non-dynamic blocks, cross-block back-references,
 //    errors, too-small output): in-order kernel, which reproduces libflate's error kinds and partial output.
 int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::vector<Member> &mem,
-                  std::vector<int> &st, std::vector<uint64_t> &olen, std::vector<uint64_t> &cons) {
+                  std::vector<int> &st, std::vector<uint64_t> &olen, std::vector<uint64_t> &cons, std::vector<char> &copied) {
     const size_t n = mem.size();
-    st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0);
+    st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0); copied.assign(n, 0);
     if (!n) return B2F_OK;
     std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_cap(n), out_end(n);
     for (size_t i = 0; i < n; i++) { in_off[i] = mem[i].def_off; in_len[i] = mem[i].def_len; out_off[i] = mem[i].out_off; out_cap[i] = mem[i].out_cap; out_end[i] = mem[i].out_off + mem[i].out_cap; }
@@ -999,8 +999,35 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 ctx->tm.mark(ctx->stream, "spec_tokens");
                 CK(spec_launch_tokens(S, (uint32_t)nsel, ctx->stream));
                 ctx->tm.mark(ctx->stream, "lz_resolve");
-                CK(spec_launch_resolve(S, (uint32_t)nsel, nunits, ctx->stream));
-                ctx->stats.kernel_launches += 3;
+                CK(spec_launch_units(S, (uint32_t)nsel, ctx->stream));
+                // The resolve runs in up to 4 parts (by output bytes); the output of a finished part is copied to pinned host memory
+                // on a side stream while the next part resolves.
+                {
+                    uint64_t total_len = 0; for (size_t k = 0; k < nsel; k++) total_len += k_len[k];
+                    const uint32_t nparts = (total_len >= (64ull << 20) && ctx->overlap) ? 4 : 1;
+                    size_t b0 = 0; uint64_t acc = 0;
+                    for (uint32_t part = 0; part < nparts; part++) {
+                        size_t b1 = b0;
+                        const uint64_t want = total_len * (part + 1) / nparts;
+                        while (b1 < nsel && (acc < want || part + 1 == nparts)) { acc += k_len[b1]; b1++; }
+                        CK(spec_launch_resolve(S, unit0[b0], unit0[b1], ctx->stream));
+                        ctx->stats.kernel_launches += 1;
+                        bool any_host = false;
+                        for (size_t k = b0; k < b1; k++) if (mem[cands[sel_blocks[k]].first].h_out) { any_host = true; break; }
+                        if (any_host) {
+                            CK(cudaEventRecord(ctx->aux_ev[part], ctx->stream));
+                            CK(cudaStreamWaitEvent(ctx->aux[0], ctx->aux_ev[part], 0));
+                            for (size_t k = b0; k < b1; k++) {
+                                const uint32_t m = cands[sel_blocks[k]].first;
+                                if (mem[m].h_out && k_len[k])
+                                    CK(cudaMemcpyAsync(mem[m].h_out + (k_out[k] - out_off[m]), d_out + k_out[k], k_len[k], cudaMemcpyDeviceToHost, ctx->aux[0]));
+                            }
+                        }
+                        b0 = b1;
+                    }
+                    for (uint32_t m : big) if (is_par[m] && mem[m].h_out) copied[m] = 1;
+                }
+                ctx->stats.kernel_launches += 2;
                 ctx->tm.mark(ctx->stream, "sync");
                 const size_t rb = s_end - s_ub;                      // unit_nout | unit_blk | res_err | res_len
                 CK(ctx->pin_res.ensure(rb + 64));
@@ -1017,7 +1044,9 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     for (uint32_t u = unit0[k]; u < unit0[k + 1]; u++) if (h_ub[u] != 0xFFFFFFFFu) { sum += h_len[u]; if (h_err[u] || h_len[u] != h_un[u]) bad = true; }
                     if (bad || sum != k_len[k]) redo[cands[sel_blocks[k]].first] = 1;
                 }
-                for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; serial_spec.push_back(m); }
+                bool any_redo = false;
+                for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; copied[m] = 0; serial_spec.push_back(m); any_redo = true; }
+                if (any_redo) CK(cudaStreamSynchronize(ctx->aux[0]));     // early copies of a redone member must not land after its final copy
             }
         }
     }
@@ -1098,7 +1127,8 @@ struct InputAccess {
 
 // Shared decode driver: container framing on the host (a few bytes per stream), DEFLATE + checksums on the device.
 int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const uint8_t *d_in, const uint64_t *in_off, const size_t *in_len,
-                uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status) {
+                uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status,
+                uint8_t *const *h_out = nullptr, std::vector<uint64_t> *h_copied = nullptr) {
     std::vector<size_t> pos(n_streams, 0);            // reader position per stream
     std::vector<uint64_t> produced(n_streams, 0);
     std::vector<char> done(n_streams, 0);
@@ -1137,13 +1167,16 @@ int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const 
         std::vector<Member> mem;
         for (size_t s : act) {
             if (done[s]) continue;
-            Member m = { s, in_off[s] + pos[s], in_len[s] - pos[s], out_off[s] + produced[s], out_cap[s] > produced[s] ? out_cap[s] - produced[s] : 0 };
+            Member m = { s, in_off[s] + pos[s], in_len[s] - pos[s], out_off[s] + produced[s], out_cap[s] > produced[s] ? out_cap[s] - produced[s] : 0,
+                         (h_out && h_out[s]) ? h_out[s] + produced[s] : nullptr };
             mem.push_back(m);
         }
         if (mem.empty()) break;
-        std::vector<int> st; std::vector<uint64_t> olen, cons;
-        int rc = inflate_round(ctx, d_in, d_out, mem, st, olen, cons);
+        std::vector<int> st; std::vector<uint64_t> olen, cons; std::vector<char> copied;
+        int rc = inflate_round(ctx, d_in, d_out, mem, st, olen, cons, copied);
         if (rc) return rc;
+        // bytes of each stream that are already on the host (a prefix: members are decoded in order)
+        if (h_copied) for (size_t i = 0; i < mem.size(); i++) if (copied[i] && (*h_copied)[mem[i].stream] == produced[mem[i].stream]) (*h_copied)[mem[i].stream] += std::min<uint64_t>(olen[i], mem[i].out_cap);
         // ---- trailers + checksums of what was produced in this round
         std::vector<uint64_t> ck_off, ck_len; std::vector<size_t> ck_idx, ck_streams, ck_pos;
         for (size_t i = 0; i < mem.size(); i++) {
@@ -1202,16 +1235,25 @@ extern "C" int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams, const u
     ctx->tm.mark(ctx->stream, "h2d");
     for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(cudaMemcpyAsync(d_in + in_off[s], in[s], in_len[s], cudaMemcpyHostToDevice, ctx->stream));
     InputAccess IA = { ctx, in, d_in, in_off.data(), in_len };
-    int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status);
+    // early (overlapped) copies only into pinned destinations: a pageable cudaMemcpyAsync would block the launching thread
+    std::vector<uint8_t *> h_out(n_streams, nullptr);
+    for (size_t s = 0; s < n_streams; s++) {
+        cudaPointerAttributes pa;
+        if (out[s] && cudaPointerGetAttributes(&pa, out[s]) == cudaSuccess && pa.type == cudaMemoryTypeHost) h_out[s] = out[s];
+    }
+    cudaGetLastError();
+    std::vector<uint64_t> h_copied(n_streams, 0);
+    int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status, h_out.data(), &h_copied);
     if (rc) return rc;
     ctx->tm.finish(ctx->stream);
     CK(cudaStreamSynchronize(ctx->stream));
     collect_stats(ctx, true);
     for (size_t s = 0; s < n_streams; s++) {
-        size_t w = std::min(out_len[s], out_cap[s]);
-        if (w) CK(cudaMemcpyAsync(out[s], d_out + out_off[s], w, cudaMemcpyDeviceToHost, ctx->stream));
+        const size_t w = std::min(out_len[s], out_cap[s]), have = (size_t)std::min<uint64_t>(h_copied[s], w);
+        if (w > have) CK(cudaMemcpyAsync(out[s] + have, d_out + out_off[s] + have, w - have, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->aux[0]));
     return B2F_OK;
 }
 

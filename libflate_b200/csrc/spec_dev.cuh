@@ -30,5 +30,6 @@ struct SpecDev {
 cudaError_t spec_init_attributes();
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st);
 cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
-cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t n_sel, uint32_t n_units, cudaStream_t st);
+cudaError_t spec_launch_units(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
+cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t u0, uint32_t u1, cudaStream_t st);
 }

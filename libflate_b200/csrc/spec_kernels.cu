@@ -370,10 +370,10 @@ __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volati
 // read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
 constexpr uint32_t kResRing = 24576;
 
-__global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S) {
+__global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
     extern __shared__ __align__(16) uint8_t ring[];
     const uint32_t lane = threadIdx.x;
-    const uint32_t u = blockIdx.x;
+    const uint32_t u = blockIdx.x + uoff;
     const uint32_t b = S.unit_blk[u];
     if (b == 0xFFFFFFFFu) return;                                // unused slot
     const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b] + S.unit_tok[u];
@@ -473,11 +473,15 @@ cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st
     k_spec_tokens<<<S.n_ctas, kSpecCta, 0, st>>>(S);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t n_sel, uint32_t n_units, cudaStream_t st) {
+cudaError_t spec_launch_units(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
     if (!n_sel) return cudaSuccess;
     k_spec_units<<<n_sel, 32, 0, st>>>(S);
-    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
-    k_spec_resolve<<<n_units, 32, kResRing, st>>>(S);
+    return cudaGetLastError();
+}
+// resolves the unit slots [u0, u1)
+cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t u0, uint32_t u1, cudaStream_t st) {
+    if (u1 <= u0) return cudaSuccess;
+    k_spec_resolve<<<u1 - u0, 32, kResRing, st>>>(S, u0);
     return cudaGetLastError();
 }
 

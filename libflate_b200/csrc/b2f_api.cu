@@ -1000,11 +1000,12 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 CK(spec_launch_tokens(S, (uint32_t)nsel, ctx->stream));
                 ctx->tm.mark(ctx->stream, "lz_resolve");
                 CK(spec_launch_units(S, (uint32_t)nsel, ctx->stream));
-                // The resolve runs in up to 4 parts (by output bytes); the output of a finished part is copied to pinned host memory
-                // on a side stream while the next part resolves.
+                // The output is copied to pinned host memory on a side stream as soon as the resolve has finished.
                 {
                     uint64_t total_len = 0; for (size_t k = 0; k < nsel; k++) total_len += k_len[k];
-                    const uint32_t nparts = (total_len >= (64ull << 20) && ctx->overlap) ? 4 : 1;
+                    // (splitting the resolve itself does not pay: every unit is one latency-bound warp, so each part would take as long
+                    // as the whole; the copy of the output still overlaps the checksum kernel and the host-side trailer checks)
+                    const uint32_t nparts = 1;
                     size_t b0 = 0; uint64_t acc = 0;
                     for (uint32_t part = 0; part < nparts; part++) {
                         size_t b1 = b0;

@@ -403,11 +403,19 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         const uint32_t dist = tk & 0xFFFFu;
         const uint64_t dst = pos + off;
         if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
+        // Matches whose source is older than the ring read final data from HBM and never depend on this step's output: every
+        // lane resolves its own one now, all in parallel (their ~800-cycle loads overlap instead of queueing up one per match).
+        const bool is_far = is_m && dist + (total - off) > kResRing;
+        if (is_far) {
+            const uint8_t *gs = g + dst - dist;
+            const uint32_t d0 = RFWD(off);
+            for (uint32_t k = 0; k < len; k++) { uint32_t di = d0 + k; if (di >= kResRing) di -= kResRing; ring[di] = __ldcg(gs + k); }
+        }
         __syncwarp();
-        // matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on the
-        // bytes written just before them, so resolving them independently buys nothing).  The parameters of the next match
+        // remaining matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on
+        // the bytes written just before them, so resolving them independently buys nothing).  The parameters of the next match
         // are fetched (shuffles) while the current one is being copied.
-        uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m);
+        uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m && !is_far);
         uint32_t j = pending ? __ffs((int)pending) - 1 : 0;
         uint32_t n_off = __shfl_sync(0xFFFFFFFFu, off, j), n_tk = __shfl_sync(0xFFFFFFFFu, tk, j);
         while (pending) {
@@ -416,10 +424,7 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
             if (pending) { j = __ffs((int)pending) - 1; n_off = __shfl_sync(0xFFFFFFFFu, off, j); n_tk = __shfl_sync(0xFFFFFFFFu, tk, j); }
             const uint32_t mlen = (mtk >> 16) & 0x1FFu, mdist = mtk & 0xFFFFu;
             const uint32_t d0 = RFWD(moff);                         // ring index of the match's first output byte
-            if (mdist + (total - moff) > kResRing) {                // source older than the ring: it was written through to HBM (never overlaps: dist > len)
-                const uint8_t *gs = g + (pos + moff) - mdist;
-                for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k; if (di >= kResRing) di -= kResRing; ring[di] = __ldcg(gs + k); }
-            } else {
+            {
                 const uint32_t s0i = RBACK(d0, mdist);              // ring index of the first source byte
                 if (mdist >= mlen) {
                     for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k, si = s0i + k; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }

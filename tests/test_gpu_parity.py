@@ -346,3 +346,26 @@ def test_config4_shape_zlib_streams(ctx):
     for d, e in zip(datas, encs):
         assert e == orc.encode(1, d)
         assert e[-4:] == pyzlib.adler32(d).to_bytes(4, "big")
+
+
+@pytest.mark.gpu
+def test_cli_mirror_of_examples_flate(tmp_path):
+    """examples/flate.rs:84-111: gzip-encode / gzip-decode / gzip-decode-multi / zlib-encode / zlib-decode over files.  The
+    encoders are fed by an 8 KiB copy loop, so the bytes equal the oracle's with schedule [8192]*k."""
+    from libflate_b200 import flate, titles
+    d = titles.generate(700_001, seed=77).tobytes()
+    src = tmp_path / "in.txt"
+    src.write_bytes(d)
+    sched = [8192] * (len(d) // 8192) + ([len(d) % 8192] if len(d) % 8192 else [])
+    gz, zz, back = tmp_path / "o.gz", tmp_path / "o.z", tmp_path / "back"
+    assert flate.main(["-i", str(src), "-o", str(gz), "--mtime", "0", "gzip-encode"]) == 0
+    assert gz.read_bytes() == orc.encode(orc.FMT_GZIP, d, sched, mtime=0)
+    assert flate.main(["-i", str(src), "-o", str(zz), "zlib-encode"]) == 0
+    assert zz.read_bytes() == orc.encode(orc.FMT_ZLIB, d, sched)
+    assert pyzlib.decompress(zz.read_bytes()) == d
+    assert flate.main(["-i", str(gz), "-o", str(back), "-v", "gzip-decode"]) == 0 and back.read_bytes() == d
+    assert flate.main(["-i", str(zz), "-o", str(back), "zlib-decode"]) == 0 and back.read_bytes() == d
+    two = tmp_path / "two.gz"
+    two.write_bytes(gz.read_bytes() + pygzip.compress(b"second member"))
+    assert flate.main(["-i", str(two), "-o", str(back), "gzip-decode-multi"]) == 0 and back.read_bytes() == d + b"second member"
+    assert flate.main(["-i", str(two), "-o", str(back), "gzip-decode"]) == 0 and back.read_bytes() == d

@@ -7,6 +7,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libb2f.so")
+if os.environ.get("B2F_LIB"):          # developer switch: load another build of the same library (kernel experiments)
+    SO_PATH = os.path.abspath(os.environ["B2F_LIB"])
 
 OK, ERR_INVALID_DATA, ERR_UNEXPECTED_EOF, ERR_OUTPUT_TOO_SMALL, ERR_NOMEM, ERR_CUDA, ERR_INVALID_ARG = 0, -1, -2, -3, -4, -5, -6
 FMT_DEFLATE, FMT_ZLIB, FMT_GZIP, FMT_GZIP_MULTI = 0, 1, 2, 3

@@ -59,49 +59,76 @@ __global__ void __launch_bounds__(32) k_lz_chain(EncDev E, uint32_t off) {
     uint16_t *__restrict__ lk = E.link + cd.off;
     for (uint32_t q = max(lim, s_start) + lane; q < s_end; q += 32) lk[q] = 0;   // tail without a trigram
     if (ws >= lim) return;
-    // The input is consumed as 128-byte blocks: lane L holds the aligned word at block + 4L; the next block is prefetched
-    // one block (4 steps) ahead, so no load sits on the critical path.  Positions are int64 relative to the chunk because the
+    // The input is consumed as 128-byte blocks: lane L holds the aligned word at block + 4L; blocks are prefetched
+    // several iterations ahead, so no load sits on the critical path.  Positions are int64 relative to the chunk because the
     // aligned start can lie up to 3 bytes before position `ws` (those lanes are masked off).
     const int64_t a0 = (int64_t)ws - (int64_t)((cd.off + ws) & 3u);
     const uint64_t g0 = (uint64_t)((int64_t)cd.off + a0);          // 4-byte aligned offset into E.in
-    uint32_t cur = ld_in32(E.in, g0 + 4ull * lane, E.in_size);
+    // One shared-memory atomicMax per position publishes pos+1 and returns the previous head.  Positions grow monotonically, so
+    // the table always ends up with the most recent position; lanes of one step that share a bucket are serialised by the
+    // hardware and, when that happens in ascending lane order, each one receives exactly its predecessor.  Any other order makes
+    // some lane see a value above its own position: that is detected once per 128-byte block and repaired exactly (below).
+    // The four steps of a block are independent instructions, so their atomics are in flight together.
+    // Input blocks are prefetched kChainAhead iterations ahead (a cold HBM read costs about two block iterations of this warp).
+    constexpr uint32_t kChainAhead = 4;
+    uint32_t pre[kChainAhead];
+#pragma unroll
+    for (uint32_t k = 0; k < kChainAhead; k++) pre[k] = ld_in32(E.in, g0 + 128ull * k + 4ull * lane, E.in_size);
     uint32_t blk = 0;
     for (int64_t bpos = a0; bpos < (int64_t)lim; bpos += 128, blk++) {
-        const uint32_t nxt = ld_in32(E.in, g0 + 128ull * (blk + 1) + 4ull * lane, E.in_size);
+        const uint32_t cur = pre[0], nxt = pre[1];
+#pragma unroll
+        for (uint32_t k = 0; k + 1 < kChainAhead; k++) pre[k] = pre[k + 1];
+        pre[kChainAhead - 1] = ld_in32(E.in, g0 + 128ull * (blk + kChainAhead) + 4ull * lane, E.in_size);
+        const uint32_t hn = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+        uint32_t hh[4], oo[4];
+        bool vv[4];
+        bool bad = false;
 #pragma unroll
         for (uint32_t s4 = 0; s4 < 4; s4++) {
             const int64_t base = bpos + 32 * s4;
-            if (base >= (int64_t)lim) break;
             const uint32_t wi = (32 * s4 + lane) >> 2, bo = lane & 3u;
             const uint32_t lo = __shfl_sync(0xFFFFFFFFu, cur, wi);
             const uint32_t hc = __shfl_sync(0xFFFFFFFFu, cur, (wi + 1) & 31u);
-            const uint32_t hn = __shfl_sync(0xFFFFFFFFu, nxt, 0);
             const uint32_t hi = wi == 31 ? hn : hc;
             const uint32_t t = __funnelshift_r(lo, hi, bo * 8u) & 0xFFFFFFu;
             const int64_t pos64 = base + lane;
-            const bool valid = pos64 >= (int64_t)ws && pos64 < (int64_t)lim;
-            const uint32_t pos = (uint32_t)pos64;
-            const uint32_t h = valid ? (t * 0x9E3779B1u) >> (32 - kHashBits) : 0;
-            const uint32_t old = valid ? head[h] : 0;
-            __syncwarp();
-            if (valid) head[h] = pos + 1;                            // same-hash lanes: one of them wins
-            __syncwarp();
-            const bool lost = valid && head[h] != pos + 1;
-            uint32_t d = old ? pos + 1 - old : 0;
-            if (__any_sync(0xFFFFFFFFu, lost)) {                     // rare: two positions of this step share a hash -> exact ordered resolution
-                const uint32_t key = valid ? h : (0x80000000u | lane);
+            vv[s4] = pos64 >= (int64_t)ws && pos64 < (int64_t)lim;
+            hh[s4] = (t * 0x9E3779B1u) >> (32 - kHashBits);
+            oo[s4] = vv[s4] ? atomicMax(&head[hh[s4]], (uint32_t)pos64 + 1u) : 0u;
+#ifdef B2F_CHAIN_FORCE_REPAIR                                    /* test build: always take the repair path */
+            bad = true;
+#else
+            bad |= vv[s4] && oo[s4] > (uint32_t)pos64;
+#endif
+        }
+        if (__any_sync(0xFFFFFFFFu, bad)) {
+            // exact repair: within a step the predecessor of a lane is the nearest lower lane of its bucket; the lowest lane of a
+            // bucket gets the head from before the step = the smallest value any lane of the bucket received
+#pragma unroll
+            for (uint32_t s4 = 0; s4 < 4; s4++) {
+                const uint32_t pos = (uint32_t)(bpos + 32 * s4 + lane);
+                const uint32_t key = vv[s4] ? hh[s4] : (0x80000000u | lane);
                 const uint32_t m = __match_any_sync(0xFFFFFFFFu, key);
                 const uint32_t lower = m & ((1u << lane) - 1u);
-                if (lower) d = lane - (31 - __clz((int)lower));
-                if (valid && (m >> lane) == 1u) head[h] = pos + 1;   // highest lane of the group publishes
-                __syncwarp();
+                uint32_t mn = oo[s4], mm = m & ~(1u << lane);
+                while (__any_sync(0xFFFFFFFFu, mm != 0)) {
+                    const uint32_t src = mm ? (uint32_t)__ffs((int)mm) - 1u : lane;
+                    const uint32_t v = __shfl_sync(0xFFFFFFFFu, oo[s4], src);
+                    if (mm) { mn = min(mn, v); mm &= mm - 1u; }
+                }
+                oo[s4] = lower ? pos + 1u - (lane - (31u - (uint32_t)__clz((int)lower))) : mn;
             }
-            if (valid && pos >= s_start) {
+        }
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) {
+            const uint32_t pos = (uint32_t)(bpos + 32 * s4 + lane);
+            if (vv[s4] && pos >= s_start) {
+                uint32_t d = oo[s4] ? pos + 1u - oo[s4] : 0u;
                 if (d > kLookback) d = 0;
                 lk[pos] = (uint16_t)d;
             }
         }
-        cur = nxt;
     }
 }
 

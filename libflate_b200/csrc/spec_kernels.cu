@@ -409,7 +409,14 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         if (is_far) {
             const uint8_t *gs = g + dst - dist;
             const uint32_t d0 = RFWD(off);
-            for (uint32_t k = 0; k < len; k++) { uint32_t di = d0 + k; if (di >= kResRing) di -= kResRing; ring[di] = __ldcg(gs + k); }
+            for (uint32_t k0 = 0; k0 < len; k0 += 16) {           // 16 loads in flight, then the stores (a byte-by-byte loop would
+                uint32_t v[16];                                   // serialise on load latency: ring[] and g[] may alias for the compiler)
+#pragma unroll
+                for (uint32_t t = 0; t < 16; t++) v[t] = k0 + t < len ? (uint32_t)__ldcg(gs + k0 + t) : 0u;
+#pragma unroll
+                for (uint32_t t = 0; t < 16; t++)
+                    if (k0 + t < len) { uint32_t di = d0 + k0 + t; if (di >= kResRing) di -= kResRing; ring[di] = (uint8_t)v[t]; }
+            }
         }
         __syncwarp();
         // remaining matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on

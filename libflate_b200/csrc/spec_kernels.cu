@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(32) k_spec_units(SpecDev S) {
 }
 
 // ---------------------------------------------------------------------------------- LZ77 resolution (warp per block)
-__device__ __forceinline__ uint32_t r_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t r_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void r_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
@@ -381,13 +381,20 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
     const uint64_t out0 = S.blk_out0[b] + S.unit_out[u];        // absolute offset in S.out of the unit's first byte
     const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
     uint8_t *__restrict__ g = S.out;
+    const uint32_t galign = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
+    const uint32_t rb = (uint32_t)__cvta_generic_to_shared(ring);    // 32-bit shared address of the ring (hot loop uses ld/st.shared directly)
     uint64_t pos = out0;
-    uint32_t rpos = (uint32_t)(out0 % kResRing);                 // ring index of `pos` (kept incrementally: no modulo in the loop)
+    // ring index of `pos`, kept incrementally (no modulo in the loop) and congruent to the global ADDRESS mod 4, so that aligned
+    // words of the ring are aligned words of the output
+    uint32_t rpos = (uint32_t)((out0 + galign) % kResRing);
+    uint64_t flushed = out0;                                     // bytes before this offset are in HBM
+    bool words = false;                                          // write-through by aligned words once `flushed` is word aligned
     uint32_t err = 0;
     uint32_t tnext = lane < ntok ? __ldg(tok + lane) : 0u;
     // ring index of the byte `off` bytes after the step start (off < kResRing) / `back` bytes before index i (back <= kResRing)
     #define RFWD(off) ((rpos + (off)) >= kResRing ? (rpos + (off)) - kResRing : (rpos + (off)))
     #define RBACK(i, back) ((i) >= (back) ? (i) - (back) : (i) + kResRing - (back))
+    #define RWRAP(i) ((i) >= kResRing ? (i) - kResRing : (i))
     for (uint64_t i0 = 0; i0 < ntok; i0 += 32) {
         const uint32_t tk = tnext;
         const uint64_t in = i0 + 32 + lane;
@@ -399,62 +406,78 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const uint32_t off = incl - len;                          // offset of this token's output inside the step
-        if (live && !is_m) ring[RFWD(off)] = (uint8_t)tk;
+        const uint32_t d0 = RFWD(off);                            // ring index of this token's first output byte
+        if (live && !is_m) ring[d0] = (uint8_t)tk;
         const uint32_t dist = tk & 0xFFFFu;
         const uint64_t dst = pos + off;
         if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
         // Matches whose source is older than the ring read final data from HBM and never depend on this step's output: every
-        // lane resolves its own one now, all in parallel (their ~800-cycle loads overlap instead of queueing up one per match).
+        // lane resolves its own one now, all in parallel (their loads overlap instead of queueing up one per match).
         const bool is_far = is_m && dist + (total - off) > kResRing;
         if (is_far) {
             const uint8_t *gs = g + dst - dist;
-            const uint32_t d0 = RFWD(off);
             for (uint32_t k0 = 0; k0 < len; k0 += 16) {           // 16 loads in flight, then the stores (a byte-by-byte loop would
                 uint32_t v[16];                                   // serialise on load latency: ring[] and g[] may alias for the compiler)
 #pragma unroll
                 for (uint32_t t = 0; t < 16; t++) v[t] = k0 + t < len ? (uint32_t)__ldcg(gs + k0 + t) : 0u;
 #pragma unroll
                 for (uint32_t t = 0; t < 16; t++)
-                    if (k0 + t < len) { uint32_t di = d0 + k0 + t; if (di >= kResRing) di -= kResRing; ring[di] = (uint8_t)v[t]; }
+                    if (k0 + t < len) { const uint32_t di = RWRAP(d0 + k0 + t); ring[di] = (uint8_t)v[t]; }
             }
         }
-        __syncwarp();
         // remaining matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on
-        // the bytes written just before them, so resolving them independently buys nothing).  The parameters of the next match
-        // are fetched (shuffles) while the current one is being copied.
+        // the bytes written just before them, so resolving them independently buys nothing).  Each lane packs the parameters of
+        // its own match once; the loop only shuffles them (the next match's while the current one is being copied).
+        const uint32_t p1 = d0 | (len << 16);                                           // ring index of the first output byte | length
+        const uint32_t p2 = (is_m && !is_far ? RBACK(d0, dist) : 0u) | (dist << 16);    // ring index of the first source byte | distance
+        __syncwarp();
         uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m && !is_far);
         uint32_t j = pending ? __ffs((int)pending) - 1 : 0;
-        uint32_t n_off = __shfl_sync(0xFFFFFFFFu, off, j), n_tk = __shfl_sync(0xFFFFFFFFu, tk, j);
+        uint32_t n1 = __shfl_sync(0xFFFFFFFFu, p1, j), n2 = __shfl_sync(0xFFFFFFFFu, p2, j);
         while (pending) {
-            const uint32_t moff = n_off, mtk = n_tk;
+            const uint32_t c1 = n1, c2 = n2;
             pending &= pending - 1;
-            if (pending) { j = __ffs((int)pending) - 1; n_off = __shfl_sync(0xFFFFFFFFu, off, j); n_tk = __shfl_sync(0xFFFFFFFFu, tk, j); }
-            const uint32_t mlen = (mtk >> 16) & 0x1FFu, mdist = mtk & 0xFFFFu;
-            const uint32_t d0 = RFWD(moff);                         // ring index of the match's first output byte
-            {
-                const uint32_t s0i = RBACK(d0, mdist);              // ring index of the first source byte
-                if (mdist >= mlen) {
-                    for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k, si = s0i + k; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }
-                } else if (mdist >= 32) {                           // overlapping, but each 32-byte slice only reads bytes of earlier slices
-                    for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
-                        const uint32_t k = k0 + lane;
-                        if (k < mlen) { uint32_t di = d0 + k, si = s0i + k; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }
-                        __syncwarp();
-                    }
-                } else {
-                    for (uint32_t k = lane; k < mlen; k += 32) { uint32_t di = d0 + k, si = s0i + k % mdist; if (di >= kResRing) di -= kResRing; if (si >= kResRing) si -= kResRing; ring[di] = ring[si]; }
+            if (pending) { j = __ffs((int)pending) - 1; n1 = __shfl_sync(0xFFFFFFFFu, p1, j); n2 = __shfl_sync(0xFFFFFFFFu, p2, j); }
+            const uint32_t mlen = c1 >> 16, mdist = c2 >> 16;
+            const uint32_t md = (c1 & 0xFFFFu) + lane, ms = (c2 & 0xFFFFu) + lane;      // this lane's byte of the first 32-byte slice
+            if (mdist >= mlen && mlen <= 32) {                      // the common case: one slice, source entirely older than the output
+                if (lane < mlen) r_sts8(rb + RWRAP(md), r_lds8(rb + RWRAP(ms)));
+            } else if (mdist >= 32) {                               // each 32-byte slice only reads bytes of earlier slices
+                for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
+                    if (k0 + lane < mlen) r_sts8(rb + RWRAP(md + k0), r_lds8(rb + RWRAP(ms + k0)));
+                    __syncwarp();
                 }
+            } else {                                                // short period: byte k repeats byte k mod dist of the source
+                for (uint32_t k = lane; k < mlen; k += 32) ring[RWRAP(md - lane + k)] = ring[RWRAP(ms - lane + k % mdist)];
             }
             __syncwarp();
         }
         // write the step through to HBM
-        for (uint32_t k = lane; k < total; k += 32) g[pos + k] = ring[RFWD(k)];
-        pos += total;
-        rpos += total; if (rpos >= kResRing) rpos -= kResRing;
+        const uint64_t new_end = pos + total;
+        if (words) {
+            const uint64_t fe = new_end - ((new_end + galign) & 3u);        // last word boundary at or below new_end
+            if (fe > flushed) {
+                const uint32_t nw = (uint32_t)(fe - flushed) >> 2;
+                const uint32_t r0 = RBACK(rpos, (uint32_t)(pos - flushed));  // pos - flushed <= 3
+                uint32_t *gw = reinterpret_cast<uint32_t *>(g + flushed);
+                for (uint32_t k = lane; k < nw; k += 32) gw[k] = *reinterpret_cast<const uint32_t *>(ring + RWRAP(r0 + 4 * k));
+                flushed = fe;
+            }
+        } else {
+            for (uint32_t k = lane; k < total; k += 32) g[pos + k] = ring[RFWD(k)];
+            if (new_end - out0 >= 8) { words = true; flushed = new_end - ((new_end + galign) & 3u); }
+        }
+        pos = new_end;
+        rpos = RFWD(total);
         __syncwarp();
+    }
+    if (words) {                                                 // the bytes after the last whole word
+        const uint32_t nt = (uint32_t)(pos - flushed), r0 = RBACK(rpos, nt);
+        if (lane < nt) g[flushed + lane] = ring[RWRAP(r0 + lane)];
     }
     #undef RFWD
     #undef RBACK
+    #undef RWRAP
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) { S.res_err[u] = err; S.res_len[u] = pos - out0; }
 }

@@ -369,3 +369,39 @@ def test_cli_mirror_of_examples_flate(tmp_path):
     two.write_bytes(gz.read_bytes() + pygzip.compress(b"second member"))
     assert flate.main(["-i", str(two), "-o", str(back), "gzip-decode-multi"]) == 0 and back.read_bytes() == d + b"second member"
     assert flate.main(["-i", str(two), "-o", str(back), "gzip-decode"]) == 0 and back.read_bytes() == d
+
+
+@pytest.mark.gpu
+def test_device_api_unaligned_offsets(ctx):
+    """b2f_encode_device / b2f_decode_device with odd byte offsets on both sides (the resolve kernel writes aligned words only
+    where a word is wholly owned by one unit)."""
+    import torch
+    from libflate_b200 import native, titles
+    datas = [titles.generate(n, seed=s).tobytes() for n, s in ((1_500_001, 5), (1_200_003, 6), (70_001, 7))]
+    scheds = [[8192] * (len(d) // 8192 + 1) for d in datas]
+    want = [orc.encode(orc.FMT_ZLIB, d, sc) for d, sc in zip(datas, scheds)]
+    in_off, pos = [], 1
+    for d in datas:
+        in_off.append(pos); pos += len(d) + 3
+    d_in = torch.zeros(pos + 64, dtype=torch.uint8, device="cuda")
+    for o, d in zip(in_off, datas):
+        d_in[o:o + len(d)] = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+    caps = [len(d) + len(d) // 8 + 4096 for d in datas]
+    e_off, pos = [], 3
+    for c in caps:
+        e_off.append(pos); pos += c + 1
+    d_enc = torch.zeros(pos + 64, dtype=torch.uint8, device="cuda")
+    ol, st = ctx.encode_device(native.FMT_ZLIB, d_in.data_ptr(), in_off, [len(d) for d in datas], d_enc.data_ptr(), e_off, caps, scheds)
+    assert st == [0, 0, 0]
+    for o, n, w in zip(e_off, ol, want):
+        assert bytes(d_enc[o:o + n].cpu().numpy()) == w
+    o_off, pos = [], 1
+    for d in datas:
+        o_off.append(pos); pos += len(d) + 65 + 2
+    d_out = torch.full((pos + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    dl, used, st = ctx.decode_device(native.FMT_ZLIB, d_enc.data_ptr() + 0, e_off, ol, d_out.data_ptr() + 1, [o - 1 for o in o_off], [len(d) + 65 for d in datas])
+    assert st == [0, 0, 0] and used == ol and dl == [len(d) for d in datas]
+    host = d_out.cpu().numpy()
+    for o, d in zip(o_off, datas):
+        assert bytes(host[o:o + len(d)]) == d
+        assert host[o - 1] == 0xEE and host[o + len(d)] == 0xEE          # nothing written outside the streams

@@ -364,11 +364,18 @@ __global__ void __launch_bounds__(32) k_spec_units(SpecDev S) {
 // ---------------------------------------------------------------------------------- LZ77 resolution (warp per block)
 __device__ __forceinline__ uint32_t r_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void r_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 r_lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void r_sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+// ring[dst] = ring[src] for the lanes with on != 0, as predicated instructions (no divergent branch)
+__device__ __forceinline__ void r_copy8_if(uint32_t on, uint32_t src, uint32_t dst) {
+    asm volatile("{ .reg .pred p; .reg .u32 v; setp.ne.u32 p, %0, 0; @p ld.shared.u8 v, [%1]; @p st.shared.u8 [%2], v; }" :: "r"(on), "r"(src), "r"(dst) : "memory");
+}
 __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // The ring keeps the most recent kResRing bytes; every step is written through to HBM, so sources older than the ring are
 // read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
 constexpr uint32_t kResRing = 24576;
+constexpr uint32_t kResSmem = kResRing + 34 * 8 + 32;            // + the per-step queue of match parameters + 32 write-only dummy bytes
 
 __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
     extern __shared__ __align__(16) uint8_t ring[];
@@ -382,7 +389,13 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
     const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
     uint8_t *__restrict__ g = S.out;
     const uint32_t galign = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
-    const uint32_t rb = (uint32_t)__cvta_generic_to_shared(ring);    // 32-bit shared address of the ring (hot loop uses ld/st.shared directly)
+    uint32_t rb;                                                 // 32-bit shared address of the ring, pinned in a register (the
+    {                                                            // compiler would otherwise rebuild it from %cluster_ctaid per access)
+        const uint64_t ga = reinterpret_cast<uint64_t>(ring);
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(rb) : "l"(ga));
+    }
+    const uint32_t qb = rb + kResRing;                           // queue of (p1, p2) pairs of the step's in-order matches
+    const uint32_t dummy = qb + 34 * 8 + lane;
     uint64_t pos = out0;
     // ring index of `pos`, kept incrementally (no modulo in the loop) and congruent to the global ADDRESS mod 4, so that aligned
     // words of the ring are aligned words of the output
@@ -430,21 +443,21 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         // its own match once; the loop only shuffles them (the next match's while the current one is being copied).
         const uint32_t p1 = d0 | (len << 16);                                           // ring index of the first output byte | length
         const uint32_t p2 = (is_m && !is_far ? RBACK(d0, dist) : 0u) | (dist << 16);    // ring index of the first source byte | distance
+        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, is_m && !is_far);
+        const uint32_t nm = __popc(mmask);
+        if (is_m && !is_far) r_sts64(qb + 8u * __popc(mmask & ((1u << lane) - 1u)), p1, p2);   // compacted, in token order
         __syncwarp();
-        uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_m && !is_far);
-        uint32_t j = pending ? __ffs((int)pending) - 1 : 0;
-        uint32_t n1 = __shfl_sync(0xFFFFFFFFu, p1, j), n2 = __shfl_sync(0xFFFFFFFFu, p2, j);
-        while (pending) {
-            const uint32_t c1 = n1, c2 = n2;
-            pending &= pending - 1;
-            if (pending) { j = __ffs((int)pending) - 1; n1 = __shfl_sync(0xFFFFFFFFu, p1, j); n2 = __shfl_sync(0xFFFFFFFFu, p2, j); }
-            const uint32_t mlen = c1 >> 16, mdist = c2 >> 16;
-            const uint32_t md = (c1 & 0xFFFFu) + lane, ms = (c2 & 0xFFFFu) + lane;      // this lane's byte of the first 32-byte slice
+        uint2 nx = r_lds64(qb);
+        for (uint32_t i = 0; i < nm; i++) {
+            const uint2 c = nx;
+            nx = r_lds64(qb + 8u * (i + 1));                        // next match's parameters (slot nm is never used)
+            const uint32_t mlen = c.x >> 16, mdist = c.y >> 16;
+            const uint32_t md = (c.x & 0xFFFFu) + lane, ms = (c.y & 0xFFFFu) + lane;    // this lane's byte of the first 32-byte slice
             if (mdist >= mlen && mlen <= 32) {                      // the common case: one slice, source entirely older than the output
-                if (lane < mlen) r_sts8(rb + RWRAP(md), r_lds8(rb + RWRAP(ms)));
+                r_sts8(lane < mlen ? rb + RWRAP(md) : dummy, r_lds8(rb + RWRAP(ms)));   // idle lanes store into their dummy byte: no branch
             } else if (mdist >= 32) {                               // each 32-byte slice only reads bytes of earlier slices
                 for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
-                    if (k0 + lane < mlen) r_sts8(rb + RWRAP(md + k0), r_lds8(rb + RWRAP(ms + k0)));
+                    r_copy8_if(k0 + lane < mlen, rb + RWRAP(ms + k0), rb + RWRAP(md + k0));
                     __syncwarp();
                 }
             } else {                                                // short period: byte k repeats byte k mod dist of the source
@@ -486,7 +499,7 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
 cudaError_t spec_init_attributes() {
     cudaError_t e = cudaFuncSetAttribute(k_spec_headers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(InflateTables)));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_spec_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResRing);
+    return cudaFuncSetAttribute(k_spec_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmem);
 }
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st) {
     if (!S.n_blocks) return cudaSuccess;
@@ -516,7 +529,7 @@ cudaError_t spec_launch_units(const SpecDev &S, uint32_t n_sel, cudaStream_t st)
 // resolves the unit slots [u0, u1)
 cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t u0, uint32_t u1, cudaStream_t st) {
     if (u1 <= u0) return cudaSuccess;
-    k_spec_resolve<<<u1 - u0, 32, kResRing, st>>>(S, u0);
+    k_spec_resolve<<<u1 - u0, 32, kResSmem, st>>>(S, u0);
     return cudaGetLastError();
 }
 

@@ -375,6 +375,8 @@ __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volati
 // The ring keeps the most recent kResRing bytes; every step is written through to HBM, so sources older than the ring are
 // read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
 constexpr uint32_t kResRing = 24576;
+// ceil(65536 / p): k mod p == k - p * ((k * inv) >> 16) for p < 32, k < 400 (run-length matches; avoids a division per match)
+__constant__ uint32_t kInvPeriod[32] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
 constexpr uint32_t kResSmem = kResRing + 34 * 8 + 32;            // + the per-step queue of match parameters + 32 write-only dummy bytes
 
 __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
@@ -423,10 +425,11 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         if (live && !is_m) ring[d0] = (uint8_t)tk;
         const uint32_t dist = tk & 0xFFFFu;
         const uint64_t dst = pos + off;
-        if (is_m && (uint64_t)dist > dst - out0) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
+        const bool ok = is_m && (uint64_t)dist <= dst - out0;     // source inside the unit; anything else is flagged and never dereferenced
+        if (is_m && !ok) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
         // Matches whose source is older than the ring read final data from HBM and never depend on this step's output: every
         // lane resolves its own one now, all in parallel (their loads overlap instead of queueing up one per match).
-        const bool is_far = is_m && dist + (total - off) > kResRing;
+        const bool is_far = ok && dist + (total - off) > kResRing;
         if (is_far) {
             const uint8_t *gs = g + dst - dist;
             for (uint32_t k0 = 0; k0 < len; k0 += 16) {           // 16 loads in flight, then the stores (a byte-by-byte loop would
@@ -442,15 +445,17 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         // the bytes written just before them, so resolving them independently buys nothing).  Each lane packs the parameters of
         // its own match once; the loop only shuffles them (the next match's while the current one is being copied).
         const uint32_t p1 = d0 | (len << 16);                                           // ring index of the first output byte | length
-        const uint32_t p2 = (is_m && !is_far ? RBACK(d0, dist) : 0u) | (dist << 16);    // ring index of the first source byte | distance
-        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, is_m && !is_far);
+        const bool inorder = ok && !is_far;
+        const uint32_t p2 = (inorder ? RBACK(d0, dist) : 0u) | (dist << 16);            // ring index of the first source byte | distance
+        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, inorder);
         const uint32_t nm = __popc(mmask);
-        if (is_m && !is_far) r_sts64(qb + 8u * __popc(mmask & ((1u << lane) - 1u)), p1, p2);   // compacted, in token order
+        if (inorder) r_sts64(qb + 8u * __popc(mmask & ((1u << lane) - 1u)), p1, p2);   // compacted, in token order
         __syncwarp();
-        uint2 nx = r_lds64(qb);
+        uint2 nx = r_lds64(qb), nx2 = r_lds64(qb + 8u);
         for (uint32_t i = 0; i < nm; i++) {
             const uint2 c = nx;
-            nx = r_lds64(qb + 8u * (i + 1));                        // next match's parameters (slot nm is never used)
+            nx = nx2;
+            nx2 = r_lds64(qb + 8u * (i + 2));                       // parameters two matches ahead (slots >= nm are read but never used)
             const uint32_t mlen = c.x >> 16, mdist = c.y >> 16;
             const uint32_t md = (c.x & 0xFFFFu) + lane, ms = (c.y & 0xFFFFu) + lane;    // this lane's byte of the first 32-byte slice
             if (mdist >= mlen && mlen <= 32) {                      // the common case: one slice, source entirely older than the output
@@ -461,7 +466,11 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
                     __syncwarp();
                 }
             } else {                                                // short period: byte k repeats byte k mod dist of the source
-                for (uint32_t k = lane; k < mlen; k += 32) ring[RWRAP(md - lane + k)] = ring[RWRAP(ms - lane + k % mdist)];
+                const uint32_t inv = kInvPeriod[mdist];
+                for (uint32_t k = lane; k < mlen; k += 32) {
+                    const uint32_t r = k - mdist * ((k * inv) >> 16);
+                    r_sts8(rb + RWRAP(md - lane + k), r_lds8(rb + RWRAP(ms - lane + r)));
+                }
             }
             __syncwarp();
         }

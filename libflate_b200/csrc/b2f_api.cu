@@ -416,7 +416,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     uint64_t in_span = 0;
     for (size_t s = 0; s < n_streams; s++) in_span = std::max<uint64_t>(in_span, job.in_off[s] + job.in_len[s]);
 
-    CK(ctx->buf[NB_LINK].ensure(in_span * 2 + 256));
+    CK(ctx->buf[NB_LINK].ensure(enc_link_bytes(in_span)));
     CK(ctx->buf[NB_MD].ensure(in_span * 4 + 256));
     CK(ctx->buf[NB_SYM].ensure(in_span * 4 + 256));
     CK(ctx->buf[NB_EXIT].ensure((size_t)n_tiles * kExitW * 2 + 256));
@@ -455,6 +455,8 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     const uint8_t *d_hdr = put(hdr.data(), hdr.size());
     CK(cudaMemcpyAsync(dp0, hp0, (size_t)(hp - hp0), cudaMemcpyHostToDevice, ctx->stream));
     E.link = ctx->buf[NB_LINK].as<uint16_t>(); E.md = ctx->buf[NB_MD].as<uint32_t>(); E.sym = ctx->buf[NB_SYM].as<uint32_t>();
+    enc_set_fix(E, in_span);
+    CK(cudaMemsetAsync(E.fix_count, 0, 256, ctx->stream));
     E.exit_tab = ctx->buf[NB_EXIT].as<uint16_t>();
     uint8_t *tp = ctx->buf[NB_TILE].as<uint8_t>();
     E.tile_entry = carve<uint16_t>(tp, n_tiles); E.tile_nsym = carve<uint32_t>(tp, n_tiles); E.tile_bits = carve<uint32_t>(tp, n_tiles); E.tile_bitrel = carve<uint64_t>(tp, n_tiles);
@@ -664,7 +666,7 @@ extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, ui
     const uint32_t n_tiles = (uint32_t)((len + kTile - 1) / kTile);
     ChunkDesc cd; cd.off = 0; cd.len = (uint32_t)len; cd.block = 0;
     uint32_t pref[8] = { 0, (uint32_t)((len + kSeg - 1) / kSeg), 0, (uint32_t)((len + kPTile - 1) / kPTile), 0, n_tiles, 0, (n_tiles + kGrpTiles - 1) / kGrpTiles };
-    CK(ctx->buf[NB_LINK].ensure(len * 2 + 256)); CK(ctx->buf[NB_MD].ensure(len * 4 + 256)); CK(ctx->buf[NB_SYM].ensure(len * 4 + 256));
+    CK(ctx->buf[NB_LINK].ensure(enc_link_bytes(len))); CK(ctx->buf[NB_MD].ensure(len * 4 + 256)); CK(ctx->buf[NB_SYM].ensure(len * 4 + 256));
     CK(ctx->buf[NB_EXIT].ensure((size_t)n_tiles * kExitW * 2 + 256));
     size_t tile_bytes = carve_size<uint16_t>(n_tiles) + carve_size<uint32_t>(n_tiles) + carve_size<uint64_t>(n_tiles) + 512;
     CK(ctx->buf[NB_TILE].ensure(tile_bytes));
@@ -683,6 +685,8 @@ extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, ui
     E.n_segs = pref[1]; E.n_ptiles = pref[3]; E.n_tiles = n_tiles; E.n_grps = pref[7];
     E.window = window_size > 32768 ? 32768 : window_size; E.max_len = max_length > 258 ? 258 : max_length;
     E.link = ctx->buf[NB_LINK].as<uint16_t>(); E.md = ctx->buf[NB_MD].as<uint32_t>(); E.sym = ctx->buf[NB_SYM].as<uint32_t>();
+    enc_set_fix(E, len);
+    CK(cudaMemsetAsync(E.fix_count, 0, 256, ctx->stream));
     E.exit_tab = ctx->buf[NB_EXIT].as<uint16_t>();
     uint8_t *tp = ctx->buf[NB_TILE].as<uint8_t>();
     E.tile_entry = carve<uint16_t>(tp, n_tiles); E.tile_nsym = carve<uint32_t>(tp, n_tiles);

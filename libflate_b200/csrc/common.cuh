@@ -17,7 +17,7 @@ namespace b2f {
 constexpr uint32_t kTile = 1024;        // greedy-parse tile (positions); must be >= 259
 constexpr uint32_t kExitW = 258;        // entry points per tile that a previous tile can exit into
 constexpr uint32_t kPTile = 16384;      // match-kernel tile (positions staged in shared memory)
-constexpr uint32_t kSeg = 131072;       // chain-build segment (one warp, sequential; segments after the first re-insert 32 KiB of warm-up)
+constexpr uint32_t kSeg = 262144;       // chain-build segment (segments after the first of a chunk re-insert 32 KiB of warm-up)
 constexpr uint32_t kHashBits = 14;      // chain-build hash table = 2^14 u32 = 64 KiB per warp
 constexpr uint32_t kLookback = 32768;   // libflate_lz77::MAX_DISTANCE
 constexpr uint32_t kGrpTiles = 64;      // tiles per emit CTA (one chunk per CTA)

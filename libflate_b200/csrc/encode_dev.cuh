@@ -17,6 +17,11 @@ struct EncDev {
     // LZ77 stage
     uint16_t *link;               // [N]  distance to previous same-hash position
     uint32_t *md;                 // [N]  0 | len<<16 | dist  (candidate at every position)
+    uint64_t *fix_pos;            // [kFixSlices * fix_cap] global offsets of the positions k_lz_find left to k_lz_fixup
+    uint64_t *fix2_pos;           // [kFixSlices * fix_cap] ... that k_lz_fixup left to k_lz_fixup2
+    uint32_t *fix2_j;             // [kFixSlices * fix_cap] chunk position the level-1 walk stopped at
+    uint32_t *fix_count, *fix2_count;   // [kFixSlices] each
+    uint32_t fix_cap;             // queue entries per slice
     uint16_t *exit_tab;           // [n_tiles * 258]
     uint16_t *tile_entry;         // [n_tiles]
     uint32_t *sym;                // [N]  tile-slotted symbol words
@@ -38,6 +43,18 @@ struct EncDev {
     uint64_t *stream_end_bits;    // [n_streams] end of the deflate bits, relative to out_base*8
     uint32_t *out_words;          // output buffer viewed as u32 (zero-filled before the entropy stage)
 };
+
+constexpr uint32_t kFixSlices = 8;
+// bytes of the link[] scratch buffer for an input span of `span` bytes: the links, then the fix-up counters and queues
+inline size_t enc_fix_cap(uint64_t span) { return (size_t)(span / 256 + 4096); }
+inline size_t enc_link_bytes(uint64_t span) { return (size_t)(((span * 2 + 511) & ~(uint64_t)255) + 256 + (size_t)kFixSlices * enc_fix_cap(span) * 20); }
+inline void enc_set_fix(EncDev &E, uint64_t span) {
+    uint8_t *base = reinterpret_cast<uint8_t *>(E.link) + ((span * 2 + 511) & ~(uint64_t)255);
+    const size_t q = (size_t)kFixSlices * enc_fix_cap(span);
+    E.fix_count = reinterpret_cast<uint32_t *>(base); E.fix2_count = E.fix_count + kFixSlices;
+    E.fix_pos = reinterpret_cast<uint64_t *>(base + 256); E.fix2_pos = E.fix_pos + q; E.fix2_j = reinterpret_cast<uint32_t *>(E.fix2_pos + q);
+    E.fix_cap = (uint32_t)enc_fix_cap(span);
+}
 
 struct StageTimer {
     enum { kMax = 96 };

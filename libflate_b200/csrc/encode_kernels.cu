@@ -13,6 +13,7 @@
 //   K10 bitpack      warp per tile: LSB-first packing in shared memory, coalesced store         (B1)
 // Reference behaviour: libflate_lz77/src/default.rs:59-183, src/deflate/encode.rs:261-426,
 // src/deflate/symbol.rs:95-183,321-386,486-540, src/huffman.rs:35-55,192-363, src/bit.rs:25-49.
+#include <stdlib.h>
 #include "common.cuh"
 #include "huff_build.cuh"
 #include "encode_dev.cuh"
@@ -209,6 +210,437 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
     }
 }
 
+// =============================================================================== K1+K2 fused: lz_find
+// One CTA per chain segment does what k_lz_chain + k_lz_match do, with every intermediate in shared memory:
+//   * the bytes and the hash-chain links of the last 32 KiB (+ kFindCap blocks of slack) live in two rings, so a chain hop is
+//     a shared-memory read instead of a dependent L2 load (47 % of k_lz_match's stall samples);
+//   * one loader warp streams the segment into the byte ring, 128-byte blocks, several loads in flight;
+//   * the worker warps claim blocks dynamically (atomic counter).  Only the hash-table update is ordered: a worker runs its
+//     four atomicMax steps when the turn (an mbarrier per block slot) reaches its block -- then every earlier position has been
+//     inserted and no later one, exactly the single-warp invariant of k_lz_chain -- publishes the block's links and passes the
+//     turn on.  Walking the chains, the LCP and the md[] store run outside the ordered section, concurrently on all workers;
+//     because blocks are claimed by whichever warp is free, a slow block delays nobody else until the ring slack is used up.
+//   * the tails are cut so that no block is slow: a chain walk stops after kFindHops hops (0.3 % of the positions of
+//     titles-shaped text, but they were half of the walk time) and the position goes to a queue that k_lz_fixup finishes from
+//     HBM (link[] is written through for it); a match longer than 19 bytes is extended by the whole warp, 128 bytes per round,
+//     once per run of consecutive positions that share the same distance (their lengths differ by one each).
+// Ring safety: a worker publishes the block it is working on; it only reads positions >= 128 b - 32768.  The loader does not
+// overwrite a ring slot before every published block (and hence every future one) is past the slot's old content:
+// block x may be staged once min(cur_blk) >= x + 1 - kFindCap.  The link writes of block b reuse older slots than the bytes
+// of block b + 3 staged before it, so the same test covers them.
+#ifndef B2F_FIND_WARPS
+#define B2F_FIND_WARPS 31
+#endif
+#ifndef B2F_FIND_CAP
+#define B2F_FIND_CAP 64
+#endif
+#ifndef B2F_FIND_HOPS
+#define B2F_FIND_HOPS 16
+#endif
+#ifndef B2F_FIND_UNROLL
+#define B2F_FIND_UNROLL 1
+#endif
+#ifndef B2F_FIND_WAIT_NS
+#define B2F_FIND_WAIT_NS 20000u
+#endif
+constexpr int kFindUnroll = B2F_FIND_UNROLL;                          // 1: one copy of the match code, 4: one per step of a block
+constexpr uint32_t kFindWarps = B2F_FIND_WARPS;                    // worker warps; one more warp loads
+constexpr uint32_t kFindCap = B2F_FIND_CAP;
+constexpr uint32_t kFindHops = B2F_FIND_HOPS;                      // chain hops per position before it is deferred to k_lz_fixup
+constexpr uint32_t kFindSlots = 32;                                // turn mbarriers (> kFindWarps: at most kFindWarps blocks wait for their turn)
+constexpr uint32_t kFindRing = kLookback + 128 * kFindCap;
+constexpr uint32_t kFindRingBlocks = kFindRing / 128;
+constexpr uint32_t kFindMirror = 384;                              // the first bytes of the ring repeated after its end: forward reads never wrap
+constexpr uint32_t kFindLoadDepth = 8;                             // blocks per loader step (two steps in flight)
+constexpr uint32_t kFindLane = 16;                                 // bytes of a match compared by its own lane before the warp takes over
+constexpr uint32_t kFindCtrl = (4u << kHashBits) + 2 * kFindRing + kFindRing + kFindMirror;   // offset of the control words
+constexpr uint32_t kFindSmem = kFindCtrl + 16 + 4 * 32 + 8 * 2 * kFindSlots + 4 * 32;   // ctrl | cur_blk | turn + publication barriers | dummies
+static_assert(kFindWarps >= 1 && kFindWarps < kFindSlots && kFindCap >= 16 && kFindMirror >= 3 + 258 + 31 + 8 && kFindMirror % 128 == 0, "lz_find geometry");
+
+__device__ __forceinline__ uint32_t lds_acquire(uint32_t saddr) {
+    uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_release(uint32_t saddr, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+// explicit shared-space loads with 32-bit addresses (generic pointers make the compiler rebuild the window base in the loops)
+__device__ __forceinline__ uint32_t s_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t s_ld16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t s_ld32u(uint32_t base_a, uint32_t off) {     // unaligned 4-byte read at base + off
+    const uint32_t a = base_a + (off & ~3u);
+    return __funnelshift_r(s_ld32(a), s_ld32(a + 4u), (off & 3u) * 8u);
+}
+// mbarrier hand-off of the turn: slot b mod kFindSlots completes one phase per block; the warp that finished the ordered section
+// of block b-1 arrives on it (release), the owner of block b waits for it in hardware (acquire) instead of polling.
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    do {
+        // the suspend-time hint parks the warp in hardware; without it the waiters poll and take the issue slots the turn holder needs
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity), "r"(B2F_FIND_WAIT_NS) : "memory");
+    } while (!ok);
+}
+
+__global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uint32_t off, uint32_t slice) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    uint32_t *head = reinterpret_cast<uint32_t *>(fsm);                            // last position + 1 per hash bucket
+    uint16_t *lring = reinterpret_cast<uint16_t *>(fsm + (4u << kHashBits));       // link of position q at q mod kFindRing
+    uint8_t *bring = fsm + (4u << kHashBits) + 2 * kFindRing;                      // byte of position q at q mod kFindRing (+ mirror)
+    uint32_t *ctrl = reinterpret_cast<uint32_t *>(fsm + kFindCtrl);                // [0] next block to claim, [1] blocks staged, [4..36) cur_blk
+    const uint32_t ctrl_a = (uint32_t)__cvta_generic_to_shared(ctrl);
+    const uint32_t staged_a = ctrl_a + 4, cur_a = ctrl_a + 16, mb_a = ctrl_a + 16 + 4 * 32, dummy_a = mb_a + 8 * 2 * kFindSlots;
+    const uint32_t head_a = (uint32_t)__cvta_generic_to_shared(head);
+    const uint32_t lring_a = (uint32_t)__cvta_generic_to_shared(lring), bring_a = (uint32_t)__cvta_generic_to_shared(bring);
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x + off;
+    const uint32_t c = find_owner(E.seg0, E.n_chunks, seg);
+    const ChunkDesc cd = E.chunks[c];
+    const uint32_t n = cd.len;
+    const uint32_t end = (n > 3 ? n : 3) - 3;
+    const uint32_t s_start = (seg - E.seg0[c]) * kSeg;
+    const uint32_t s_end = min(s_start + kSeg, n);
+    const uint32_t lim = min(s_end, end);
+    const uint32_t ws = s_start > kLookback ? s_start - kLookback : 0;
+    // ring coordinates: q = position - a0, a0 = warm-up start rounded down so that block loads are 4-byte aligned words
+    const int64_t a0 = (int64_t)ws - (int64_t)((cd.off + ws) & 3u);
+    const uint64_t g0 = (uint64_t)((int64_t)cd.off + a0);
+    const uint32_t nblk = (uint32_t)(((int64_t)s_end - a0 + 127) >> 7);
+    for (uint32_t i = threadIdx.x; i < (1u << kHashBits); i += (kFindWarps + 1) * 32) head[i] = 0;
+    if (threadIdx.x < 36) ctrl[threadIdx.x] = 0;
+    if (threadIdx.x < 32) ctrl[36 + 4 * kFindSlots + threadIdx.x] = 0;             // dummy words
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < 2 * kFindSlots; i++) mbar_init(mb_a + 8u * i, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { mbar_arrive(mb_a); mbar_arrive(mb_a + 8u * kFindSlots); }   // block 0 may start / publish
+
+    if (w == kFindWarps) {
+        // ------------------------------------------------------------------ loader warp
+        const uint32_t nstage = nblk + 3;                                          // the LCP of the last block reads up to 300 bytes ahead
+        uint32_t cur[kFindLoadDepth], nxt[kFindLoadDepth];
+#pragma unroll
+        for (uint32_t k = 0; k < kFindLoadDepth; k++) cur[k] = ld_in32(E.in, g0 + 128ull * k + 4ull * lane, E.in_size);
+        uint32_t rb = 0;                                                           // ring index of block x
+        for (uint32_t x = 0; x < nstage; x += kFindLoadDepth) {
+#pragma unroll
+            for (uint32_t k = 0; k < kFindLoadDepth; k++) nxt[k] = ld_in32(E.in, g0 + 128ull * (x + kFindLoadDepth + k) + 4ull * lane, E.in_size);
+            const uint32_t last = x + kFindLoadDepth;                              // blocks [x, last) are staged by this step
+            if (last > kFindCap) {                                                 // wait until nobody needs the slots about to be reused
+                const uint32_t need = last - kFindCap;
+                for (;;) {
+                    const uint32_t v = lane < kFindWarps ? lds_acquire(cur_a + 4u * lane) : 0xFFFFFFFFu;
+                    if (__reduce_min_sync(0xFFFFFFFFu, v) >= need) break;
+                    __nanosleep(200);
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < kFindLoadDepth; k++) {
+                *reinterpret_cast<uint32_t *>(bring + rb + 4u * lane) = cur[k];
+                if (rb < kFindMirror) *reinterpret_cast<uint32_t *>(bring + kFindRing + rb + 4u * lane) = cur[k];
+                rb += 128u; if (rb >= kFindRing) rb = 0;
+            }
+            __syncwarp();
+            if (lane == 0) sts_release(staged_a, last);
+#pragma unroll
+            for (uint32_t k = 0; k < kFindLoadDepth; k++) cur[k] = nxt[k];
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- worker warps
+    uint32_t *__restrict__ md = E.md + cd.off;
+    uint16_t *__restrict__ glk = E.link + cd.off;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(&ctrl[0], 1u);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (b >= nblk) break;
+        if (lane == 0) sts_release(cur_a + 4u * w, b);                             // from now on this warp reads positions >= 128 b - 32768 only
+        const int32_t bpos = (int32_t)a0 + (int32_t)(128u * b);                    // chunk position of the block's first byte (>= -3)
+        const uint32_t rb = (b % kFindRingBlocks) * 128u;                          // ring index of the block
+        while (lds_acquire(staged_a) < b + 4u) { }                                 // blocks <= b+3 are in the ring
+        // Everything the ordered section needs is prepared first: bucket address and pos+1 per position.  Positions that are not
+        // inserted (alignment lead-in, the last three bytes of the chunk, beyond the segment) go to a per-lane dummy word with
+        // value 0, so the section is four unconditional shared-memory atomics.
+        uint32_t t[4], hh[4], ha[4], p1[4], oo[4], dd[4];
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) {
+            const int32_t pos = bpos + (int32_t)(32 * s4 + lane);
+            t[s4] = s_ld32u(bring_a, rb + 32 * s4 + lane) & 0xFFFFFFu;
+            const bool v = pos >= (int32_t)ws && pos < (int32_t)lim;
+            hh[s4] = (t[s4] * 0x9E3779B1u) >> (32 - kHashBits);
+            ha[s4] = v ? head_a + 4u * hh[s4] : dummy_a + 4u * lane;
+            p1[s4] = v ? (uint32_t)pos + 1u : 0u;
+        }
+        asm volatile("" :: "r"(ha[0]), "r"(ha[1]), "r"(ha[2]), "r"(ha[3]), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]));
+        // ---- stage A, ordered: the table update.  The turn is passed on as soon as the atomics are issued (the arrive is a release,
+        // so they are performed before the next owner's); everything that only consumes their results comes after.
+        mbar_wait(mb_a + 8u * (b & (kFindSlots - 1)), (b / kFindSlots) & 1u);
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) asm volatile("atom.shared.max.u32 %0, [%1], %2;" : "=r"(oo[s4]) : "r"(ha[s4]), "r"(p1[s4]) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mb_a + 8u * ((b + 1) & (kFindSlots - 1)));
+        // ---- stage B: links from the returned heads
+        bool bad = false;
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) {
+#ifdef B2F_CHAIN_FORCE_REPAIR
+            bad = true;
+#else
+            bad |= p1[s4] != 0u && oo[s4] >= p1[s4];                               // saw a later position of its own step: out-of-order serialisation
+#endif
+        }
+        if (__any_sync(0xFFFFFFFFu, bad)) {                                        // exact repair, see k_lz_chain
+#pragma unroll
+            for (uint32_t s4 = 0; s4 < 4; s4++) {
+                const uint32_t key = p1[s4] ? hh[s4] : (0x80000000u | lane);
+                const uint32_t m = __match_any_sync(0xFFFFFFFFu, key);
+                const uint32_t lower = m & ((1u << lane) - 1u);
+                uint32_t mn = oo[s4], mm = m & ~(1u << lane);
+                while (__any_sync(0xFFFFFFFFu, mm != 0)) {
+                    const uint32_t src = mm ? (uint32_t)__ffs((int)mm) - 1u : lane;
+                    const uint32_t v = __shfl_sync(0xFFFFFFFFu, oo[s4], src);
+                    if (mm) { mn = min(mn, v); mm &= mm - 1u; }
+                }
+                oo[s4] = lower ? p1[s4] - (lane - (31u - (uint32_t)__clz((int)lower))) : mn;
+            }
+        }
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) {
+            uint32_t d = (p1[s4] && oo[s4]) ? p1[s4] - oo[s4] : 0u;
+            if (d > kLookback) d = 0;
+            dd[s4] = d;
+            lring[rb + 32 * s4 + lane] = (uint16_t)d;
+        }
+        __syncwarp();
+        // links are published in block order (second, much shorter hand-off chain): once this warp holds the publication turn, the
+        // links of every earlier block are in the ring
+        mbar_wait(mb_a + 8u * (kFindSlots + (b & (kFindSlots - 1))), (b / kFindSlots) & 1u);
+        if (lane == 0) mbar_arrive(mb_a + 8u * (kFindSlots + ((b + 1) & (kFindSlots - 1))));
+        // ---- unordered part: the matches of this block's positions that belong to the segment (warp-uniform control flow)
+        if (bpos + 127 < (int32_t)s_start) continue;
+#pragma unroll kFindUnroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) {
+            const int32_t posi = bpos + (int32_t)(32 * s4 + lane);
+            const bool valid = posi >= (int32_t)s_start && posi < (int32_t)s_end;
+            if (!__any_sync(0xFFFFFFFFu, valid)) continue;
+            const uint32_t pos = (uint32_t)posi;
+            const uint32_t ri = rb + 32 * s4 + lane;
+            const uint32_t tt = s4 == 0 ? t[0] : s4 == 1 ? t[1] : s4 == 2 ? t[2] : t[3];
+            const uint32_t d0 = s4 == 0 ? dd[0] : s4 == 1 ? dd[1] : s4 == 2 ? dd[2] : dd[3];
+            if (valid) glk[pos] = (uint16_t)d0;                                    // written through for k_lz_fixup
+            // chain walk, at most kFindHops hops.  res: 0 no match, 1 found at ring index jx (distance total), 2 deferred
+            uint32_t d = valid ? d0 : 0u, total = 0, hops = kFindHops, jx = ri, res = 0;
+            while (d) {
+                total += d;
+                if (total > E.window) break;
+                jx = jx >= d ? jx - d : jx + kFindRing - d;
+                const uint32_t dn = s_ld16(lring_a + 2u * jx);
+                const uint32_t tj = s_ld32u(bring_a, jx) & 0xFFFFFFu;
+                if (tj == tt) { res = 1; break; }
+                d = dn;
+                if (--hops == 0) { if (d) res = 2; break; }
+            }
+            const bool found = res == 1;
+            // the first kFindLane bytes of every match by its own lane
+            const uint32_t limit = found ? min(E.max_len - 3, n - (pos + 3)) : 0u;
+            const uint32_t a = ri + 3, s = jx + 3;                                 // forward reads run into the mirror instead of wrapping
+            uint32_t k = 0;
+            bool open = found && limit != 0;
+#pragma unroll
+            for (uint32_t it = 0; it < kFindLane / 4; it++) {
+                if (open) {
+                    const uint32_t x = s_ld32u(bring_a, a + k) ^ s_ld32u(bring_a, s + k);
+                    if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; open = false; }
+                    else { k += 4; if (k >= limit) open = false; }
+                }
+            }
+            // longer matches: one cooperative extension per run of consecutive lanes with the same distance
+            const uint32_t U = __ballot_sync(0xFFFFFFFFu, open);
+            if (U) {
+                const uint32_t pd = __shfl_up_sync(0xFFFFFFFFu, total, 1);
+                const bool follower = open && lane > 0 && ((U >> (lane - 1)) & 1u) && pd == total;
+                const uint32_t F = __ballot_sync(0xFFFFFFFFu, follower);
+                const uint32_t H = U & ~F;
+                uint32_t ext = 0;                                                  // head lanes: matching bytes from their a (not capped by max_len)
+                for (uint32_t hm = H; hm; hm &= hm - 1u) {
+                    const uint32_t h = (uint32_t)__ffs((int)hm) - 1u;
+                    const uint32_t ah = __shfl_sync(0xFFFFFFFFu, a, h), sh = __shfl_sync(0xFFFFFFFFu, s, h), ph = __shfl_sync(0xFFFFFFFFu, pos, h);
+                    const uint32_t fr = ~((F >> h) >> 1);                          // followers directly after h
+                    const uint32_t run = h == 31 ? 0u : (fr ? (uint32_t)__ffs((int)fr) - 1u : 31u - h);
+                    const uint32_t lim_ext = min(E.max_len - 3 + run, n - (ph + 3));
+                    uint32_t e = kFindLane, eh;
+                    for (;;) {
+                        const uint32_t o = e + 4u * lane;
+                        const uint32_t x = o < lim_ext ? (s_ld32u(bring_a, ah + o) ^ s_ld32u(bring_a, sh + o)) : 1u;
+                        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, x != 0);
+                        if (mm) {
+                            const uint32_t l0 = (uint32_t)__ffs((int)mm) - 1u;
+                            const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, x, l0);
+                            const uint32_t o0 = e + 4u * l0;
+                            eh = o0 >= lim_ext ? lim_ext : min(lim_ext, o0 + ((uint32_t)(__ffs((int)x0) - 1) >> 3));
+                            break;
+                        }
+                        e += 128u;
+                    }
+                    if (lane == h) ext = eh;
+                }
+                const uint32_t below = H & (0xFFFFFFFFu >> (31u - lane));
+                const uint32_t hl = (open && below) ? 31u - (uint32_t)__clz((int)below) : lane;
+                const uint32_t eh = __shfl_sync(0xFFFFFFFFu, ext, hl);
+                if (open) k = eh - (lane - hl);
+            }
+            uint32_t out = 0;
+            if (found) { if (k > limit) k = limit; out = ((3 + k) << 16) | total; }
+            // deferred positions go to the fix-up queue of this slice (or, should it be full, are finished here)
+            bool deferred = res == 2;
+            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, deferred);
+            if (dm) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(E.fix_count + slice, (uint32_t)__popc(dm));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const uint32_t slot = base + (uint32_t)__popc(dm & ((1u << lane) - 1u));
+                if (deferred) {
+                    if (slot < E.fix_cap) E.fix_pos[(uint64_t)slice * E.fix_cap + slot] = cd.off + pos;
+                    else {
+                        bool f2 = false;
+                        while (d) {
+                            total += d;
+                            if (total > E.window) break;
+                            jx = jx >= d ? jx - d : jx + kFindRing - d;
+                            const uint32_t dn = s_ld16(lring_a + 2u * jx);
+                            const uint32_t tj = s_ld32u(bring_a, jx) & 0xFFFFFFu;
+                            if (tj == tt) { f2 = true; break; }
+                            d = dn;
+                        }
+                        if (f2) {
+                            const uint32_t lim2 = min(E.max_len - 3, n - (pos + 3));
+                            const uint32_t s2 = jx + 3;
+                            uint32_t k2 = 0;
+                            while (k2 < lim2) {
+                                const uint32_t x = s_ld32u(bring_a, a + k2) ^ s_ld32u(bring_a, s2 + k2);
+                                if (x) { k2 += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                                k2 += 4;
+                            }
+                            if (k2 > lim2) k2 = lim2;
+                            out = ((3 + k2) << 16) | total;
+                        }
+                        deferred = false;
+                    }
+                }
+            }
+            if (valid && !deferred) md[pos] = out;
+        }
+    }
+    if (lane == 0) sts_release(cur_a + 4u * w, 0xFFFFFFFFu);
+}
+
+// Finishes the positions whose chain walk k_lz_find cut short.  Level 1: one thread per position repeats the walk from HBM
+// (link[], input bytes) for at most kFixHops hops.  What is still open then sits behind a very long chain -- thousands of
+// entries when a run of identical lines filled a bucket -- and goes to level 2, which no longer follows the chain: a warp scans
+// the rest of the window for the trigram itself, 128 positions per step.
+#ifndef B2F_FIX_HOPS
+#define B2F_FIX_HOPS 160
+#endif
+constexpr uint32_t kFixHops = B2F_FIX_HOPS;
+__device__ __forceinline__ uint32_t fix_chunk(const EncDev &E, uint64_t g) {       // chunk containing g (chunks lie in increasing offset order)
+    uint32_t lo = 0, hi = E.n_chunks;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (E.chunks[mid].off <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256) k_lz_fixup(EncDev E, uint32_t slice) {
+    const uint32_t cnt = min(E.fix_count[slice], E.fix_cap);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < cnt; i += gridDim.x * 256) {
+        const uint64_t g = E.fix_pos[(uint64_t)slice * E.fix_cap + i];
+        const ChunkDesc cd = E.chunks[fix_chunk(E, g)];
+        const uint8_t *__restrict__ p = E.in + cd.off;
+        const uint16_t *__restrict__ lk = E.link + cd.off;
+        const uint32_t n = cd.len, pos = (uint32_t)(g - cd.off);
+        const uint32_t t = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
+        uint32_t d = lk[pos], total = 0, j = pos, out = 0, hops = 0;
+        bool found = false, pushed = false;
+        while (d) {
+            total += d;
+            if (total > E.window) break;
+            j -= d;
+            const uint32_t tj = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) | ((uint32_t)p[j + 2] << 16);
+            if (tj == t) { found = true; break; }
+            d = lk[j];
+            if (++hops == kFixHops && d) {
+                const uint32_t slot = atomicAdd(E.fix2_count + slice, 1u);
+                if (slot < E.fix_cap) { E.fix2_pos[(uint64_t)slice * E.fix_cap + slot] = g; E.fix2_j[(uint64_t)slice * E.fix_cap + slot] = j; pushed = true; break; }
+            }
+        }
+        if (pushed) continue;
+        if (found) {
+            const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
+            uint32_t k = 0;
+            while (k < limit && p[pos + 3 + k] == p[j + 3 + k]) k++;
+            out = ((3 + k) << 16) | total;
+        }
+        E.md[g] = out;
+    }
+}
+// 32-bit little-endian load at any byte offset, aligned words only, zero fill at and beyond in_size
+__device__ __forceinline__ uint32_t ld_in32_any(const uint8_t *__restrict__ in, uint64_t off, uint64_t in_size) {
+    const uint64_t a = off & ~3ull;
+    const uint32_t lo = ld_in32(in, a, in_size), hi = ld_in32(in, a + 4, in_size);
+    return __funnelshift_r(lo, hi, ((uint32_t)off & 3u) * 8u);
+}
+__global__ void __launch_bounds__(256) k_lz_fixup2(EncDev E, uint32_t slice) {
+    const uint32_t cnt = min(E.fix2_count[slice], E.fix_cap);
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i = (blockIdx.x * 256 + threadIdx.x) >> 5; i < cnt; i += gridDim.x * 8) {
+        const uint64_t g = E.fix2_pos[(uint64_t)slice * E.fix_cap + i];
+        const ChunkDesc cd = E.chunks[fix_chunk(E, g)];
+        const uint8_t *__restrict__ p = E.in + cd.off;
+        const uint32_t n = cd.len, pos = (uint32_t)(g - cd.off);
+        const uint32_t t = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
+        const uint32_t lowest = pos > E.window ? pos - E.window : 0u;             // candidates: lowest <= q < hi
+        const uint32_t hi = E.fix2_j[(uint64_t)slice * E.fix_cap + i];            // the chain showed that (hi, pos) holds no occurrence; hi itself is another trigram
+        // Scan downwards, 512 aligned bytes per step: lane L compares the trigram at each of the 16 positions of its 16 bytes
+        // (byte-wise SIMD compares of the words shifted by 0, 1 and 2 bytes), the highest hit inside [lowest, hi) wins.
+        const uint32_t T0 = (t & 0xFFu) * 0x01010101u, T1 = ((t >> 8) & 0xFFu) * 0x01010101u, T2 = (t >> 16) * 0x01010101u;
+        const int64_t glow = (int64_t)cd.off + lowest, ghi = (int64_t)cd.off + hi;
+        int32_t best = -1;
+        for (int64_t S = (ghi - 1) & ~511ll; hi > lowest && S + 512 > glow; S -= 512) {
+            const int64_t g0 = S + 16 * (int64_t)lane;
+            uint32_t wv[5];
+#pragma unroll
+            for (uint32_t u = 0; u < 5; u++) wv[u] = g0 + 4 * u >= 0 ? ld_in32(E.in, (uint64_t)(g0 + 4 * u), E.in_size) : 0u;
+            uint32_t m16 = 0;
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+                const uint32_t x1 = __funnelshift_r(wv[u], wv[u + 1], 8), x2 = __funnelshift_r(wv[u], wv[u + 1], 16);
+                const uint32_t m = __vcmpeq4(wv[u], T0) & __vcmpeq4(x1, T1) & __vcmpeq4(x2, T2);      // 0xFF per matching position
+                m16 |= (((m & 0x80808080u) * 0x00204081u) >> 28) << (4 * u);
+            }
+            const int64_t lo_cut = glow - g0, hi_cut = ghi - g0;                  // valid bits: lo_cut <= bit < hi_cut
+            if (lo_cut > 0) m16 &= lo_cut >= 16 ? 0u : ~((1u << (uint32_t)lo_cut) - 1u);
+            if (hi_cut < 16) m16 &= hi_cut <= 0 ? 0u : (1u << (uint32_t)hi_cut) - 1u;
+            const int32_t mine = m16 ? (int32_t)(g0 - (int64_t)cd.off) + 31 - __clz((int)m16) : -1;
+            best = __reduce_max_sync(0xFFFFFFFFu, mine);
+            if (best >= 0) break;
+        }
+        uint32_t out = 0;
+        if (best >= 0) {                                                           // uniform
+            const uint32_t q = (uint32_t)best;
+            const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
+            uint32_t k = limit;
+            for (uint32_t r = 0; r < limit; r += 32) {
+                const uint32_t kk = r + lane;
+                const bool ne = kk < limit ? p[pos + 3 + kk] != p[q + 3 + kk] : true;
+                const uint32_t mm = __ballot_sync(0xFFFFFFFFu, ne);
+                if (mm) { k = min(limit, r + (uint32_t)__ffs((int)mm) - 1u); break; }
+            }
+            out = ((3 + k) << 16) | (pos - q);
+        }
+        if (lane == 0) E.md[g] = out;
+    }
+}
+
 // =============================================================================== K3 parse_exits
 // Greedy walk i -> i + step(i), step = match length or 1.  For a tile [ts,te) and each of the <= 258
 // positions a previous tile can jump into, exit = (first position >= te reached) - te  (SURVEY App. C).
@@ -225,13 +657,32 @@ __global__ void __launch_bounds__(64) k_parse_exits(EncDev E, uint32_t off, uint
     uint16_t *r = ring + threadIdx.x * kRing;
     const uint32_t *__restrict__ m = E.md + cd.off;
     uint16_t *__restrict__ xt = E.exit_tab + (uint64_t)tile * kExitW;
-    for (uint32_t i = te; i-- > ts;) {
-        const uint32_t v = m[i];
-        const uint32_t nx = i + (v ? (v >> 16) : 1u);
-        uint32_t ex;
-        if (nx >= te) ex = nx - te; else ex = r[(nx - ts) % kRing];
-        r[(i - ts) % kRing] = (uint16_t)ex;
-        if (i - ts < kExitW) xt[i - ts] = (uint16_t)ex;
+    // right to left in groups of 8 positions (one 32-byte sector of md per thread); the next group is loaded before the
+    // current one is processed, so the DP never waits for HBM (the loads were 67 % of this kernel's stall samples)
+    uint32_t cur[8], nxt[8];
+    uint32_t i = te;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) cur[k] = (i >= ts + 1 + k) ? m[i - 1 - k] : 0u;
+    while (i > ts) {
+        const uint32_t g = min(8u, i - ts);
+        const uint32_t i2 = i - g;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) nxt[k] = (i2 >= ts + 1 + k) ? m[i2 - 1 - k] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) {
+            if (k < g) {
+                const uint32_t p = i - 1 - k;
+                const uint32_t v = cur[k];
+                const uint32_t nx = p + (v ? (v >> 16) : 1u);
+                uint32_t ex;
+                if (nx >= te) ex = nx - te; else ex = r[(nx - ts) % kRing];
+                r[(p - ts) % kRing] = (uint16_t)ex;
+                if (p - ts < kExitW) xt[p - ts] = (uint16_t)ex;
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) cur[k] = nxt[k];
+        i = i2;
     }
 }
 
@@ -506,25 +957,36 @@ __global__ void __launch_bounds__(256) k_compact_syms(EncDev E, const uint64_t *
 // =============================================================================== launchers
 #define B2F_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return e__; } while (0)
 
+static bool g_lz_fused = true;
 cudaError_t enc_init_attributes() {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_lz_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << kHashBits) * 4));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_lz_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_lz_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmem);
+    if (e != cudaSuccess) return e;
+    if (const char *v = getenv("B2F_LZ_FUSED")) g_lz_fused = atoi(v) != 0;          // 0 = k_lz_chain + k_lz_match (A/B and fallback)
     e = cudaFuncSetAttribute(k_bitpack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kPackWords * 4));
     return e;
 }
 
 // One slice = a contiguous range of chunks [c0, c1): chain -> match -> exits -> stitch -> emit, in order, on one stream.
 static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
-                                       uint32_t c0, uint32_t c1, cudaStream_t st, StageTimer *tm) {
+                                       uint32_t c0, uint32_t c1, cudaStream_t st, StageTimer *tm, uint32_t slice) {
     if (c1 <= c0) return cudaSuccess;
     const uint32_t nseg = h_seg0[c1] - h_seg0[c0], npt = h_pt0[c1] - h_pt0[c0], nt = h_tile0[c1] - h_tile0[c0], ng = h_grp0[c1] - h_grp0[c0];
-    if (tm) tm->mark(st, "lz_chain");
-    k_lz_chain<<<nseg, 32, (1u << kHashBits) * 4, st>>>(E, h_seg0[c0]); B2F_LAUNCH_CHECK();
-    if (tm) tm->mark(st, "lz_match");
-    k_lz_match<<<npt, 512, kMatchSmem, st>>>(E, h_pt0[c0]); B2F_LAUNCH_CHECK();
+    if (g_lz_fused) {
+        if (tm) tm->mark(st, "lz_find");
+        k_lz_find<<<nseg, (kFindWarps + 1) * 32, kFindSmem, st>>>(E, h_seg0[c0], slice); B2F_LAUNCH_CHECK();
+        k_lz_fixup<<<592, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
+        k_lz_fixup2<<<1184, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
+    } else {
+        if (tm) tm->mark(st, "lz_chain");
+        k_lz_chain<<<nseg, 32, (1u << kHashBits) * 4, st>>>(E, h_seg0[c0]); B2F_LAUNCH_CHECK();
+        if (tm) tm->mark(st, "lz_match");
+        k_lz_match<<<npt, 512, kMatchSmem, st>>>(E, h_pt0[c0]); B2F_LAUNCH_CHECK();
+    }
     if (tm) tm->mark(st, "parse_exits");
     k_parse_exits<<<(nt + 63) / 64, 64, 0, st>>>(E, h_tile0[c0], h_tile0[c1]); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_stitch");
@@ -541,7 +1003,7 @@ cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_
     if (E.n_chunks == 0) return cudaSuccess;
     if (n_aux < 2 || E.n_chunks < 2 * n_aux) {
         if (feed) { if (tm) tm->mark(st, "h2d"); cudaError_t fe = feed->copy(feed->self, 0, E.n_chunks, st); if (fe != cudaSuccess) return fe; }
-        return enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, 0, E.n_chunks, st, tm);
+        return enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, 0, E.n_chunks, st, tm, 0);
     }
     if (tm) tm->mark(st, "lz_pipeline");
     cudaError_t e = cudaEventRecord(ev[0], st); if (e != cudaSuccess) return e;
@@ -554,7 +1016,7 @@ cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_
         while (c1 < E.n_chunks && (h_pt0[c1] < want || g + 1 == n_aux)) c1++;
         e = cudaStreamWaitEvent(aux[g], ev[0], 0); if (e != cudaSuccess) return e;
         if (feed) { e = feed->copy(feed->self, c0, c1, aux[g]); if (e != cudaSuccess) return e; }   // this slice's H2D overlaps the previous slices' kernels
-        e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g], nullptr); if (e != cudaSuccess) return e;
+        e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g], nullptr, g); if (e != cudaSuccess) return e;
         e = cudaEventRecord(ev[1 + g], aux[g]); if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st, ev[1 + g], 0); if (e != cudaSuccess) return e;
         c0 = c1;
@@ -584,7 +1046,7 @@ cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t 
     k_compact_syms<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E, tile_symoff, dst); B2F_LAUNCH_CHECK();
     return cudaSuccess;
 }
-uint32_t enc_launch_count_lz() { return 5; }
+uint32_t enc_launch_count_lz() { return g_lz_fused ? 6 : 5; }
 uint32_t enc_launch_count_entropy(bool has_tiles) { return has_tiles ? 6 : 4; }
 
 }  // namespace b2f

@@ -1,0 +1,12 @@
+set -x
+mkdir -p gpurun_out
+timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3 > gpurun_out/I_test_main.log
+cat gpurun_out/I_test_main.log
+for v in "" _w15 _w23; do
+  B2F_LIB=libflate_b200/libb2f$v.so timeout -s KILL 120 python tools/stage_times.py 265 A > gpurun_out/I_stage$v.log 2>&1
+  echo "== variant '$v'"; grep "encode stages" gpurun_out/I_stage$v.log
+done
+B2F_LIB=libflate_b200/libb2f_fr.so timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3 > gpurun_out/I_test_fr.log
+cat gpurun_out/I_test_fr.log
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:"k_lz_find" -c 2 -f -o gpurun_out/prof_I python tools/stage_times.py 64 A > gpurun_out/I_ncu.log 2>&1
+tail -2 gpurun_out/I_ncu.log

@@ -4,13 +4,15 @@
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
-tmp=/tmp/b2f_variant_$name; mkdir -p $tmp
+tmp=/tmp/b2f_variant_$name; rm -rf $tmp; mkdir -p $tmp
+rm -f libflate_b200/libb2f_$name.so
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -cudart static"
-objs=""
+objs=""; pids=""
 for s in b2f_api encode_kernels decode_kernels spec_kernels checksum_kernels; do
   /usr/local/cuda/bin/nvcc $F "$@" -c libflate_b200/csrc/$s.cu -o $tmp/$s.o &
+  pids="$pids $!"
   objs="$objs $tmp/$s.o"
 done
-wait
+for p in $pids; do wait $p; done
 /usr/local/cuda/bin/nvcc $F -shared -o libflate_b200/libb2f_$name.so $objs
 echo libflate_b200/libb2f_$name.so

@@ -487,9 +487,8 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u,
                      job.h_in ? &feed : nullptr));
     if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz() * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
-    CK(enc_launch_entropy(E, ctx->stream, &ctx->tm));
-    ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0);
     // checksums over the inputs (C1/C2) -> trailers
+    const bool ck_async = ctx->overlap && ctx->aux[0] != nullptr;
     const uint32_t *d_crc = nullptr, *d_adler = nullptr;
     if (fmt == B2F_FMT_GZIP || fmt == B2F_FMT_ZLIB) {
         std::vector<uint64_t> piece0(n_streams + 1, 0);
@@ -508,11 +507,23 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         C.n_pieces = piece0[n]; C.n_streams = (uint32_t)n;
         C.acc_a = (uint64_t *)(dm + o_a); C.acc_b = (uint64_t *)(dm + o_b); C.acc_crc = (uint32_t *)(dm + o_c);
         C.out_crc = (uint32_t *)(dm + o_oc); C.out_adler = (uint32_t *)(dm + o_oa);
-        ctx->tm.mark(ctx->stream, "checksum");
-        CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->stream));
+        // The checksum only needs the input: with overlap on it runs on an aux stream next to the entropy stage (huff_build, the scans
+        // and write_headers are a few hundred threads each and leave the GPU idle); framing waits for it.
+        if (ck_async) {
+            CK(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->aux[0], ctx->aux_ev[0], 0));
+            CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->aux[0]));
+            CK(cudaEventRecord(ctx->aux_ev[1], ctx->aux[0]));
+        } else {
+            ctx->tm.mark(ctx->stream, "checksum");
+            CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->stream));
+        }
         ctx->stats.kernel_launches += (C.n_pieces ? 1 : 0) + 1;
         d_crc = C.out_crc; d_adler = C.out_adler;
     }
+    CK(enc_launch_entropy(E, ctx->stream, &ctx->tm));
+    ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0);
+    if (ck_async && (fmt == B2F_FMT_GZIP || fmt == B2F_FMT_ZLIB)) CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
     ctx->tm.mark(ctx->stream, "framing");
     k_write_framing<<<(unsigned)((n_streams + 63) / 64), 64, 0, ctx->stream>>>(ctx->buf[NB_OUT].as<uint8_t>(), E.out_base, E.stream_end_bits, d_hdr,
                                                                              (uint32_t)hdr.size(), fmt, d_crc, d_adler, d_in_len, d_out_len, (uint32_t)n_streams);

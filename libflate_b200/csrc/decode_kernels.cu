@@ -211,9 +211,7 @@ __global__ void __launch_bounds__(256) k_find_blocks(FindDev F) {
     const uint32_t lane = tid & 31;
     {   // step A: thread t tests the 32 bit offsets of word t with one sliding 64-bit window
         const uint64_t win = smem_bits64(sw, tid * 32);
-        uint32_t pass = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 32; j++) if (hdr_precheck((uint32_t)(win >> j))) pass |= 1u << j;
+        uint32_t pass = hdr_precheck_mask32(win);
         const uint64_t q0 = b0 * 8 + tid * 32;
         if (q0 + 32 + 17 > limit) {                 // tail of the stream: drop offsets whose 17 header bits do not fit
             for (uint32_t j = 0; j < 32; j++) if (q0 + j + 17 > limit) pass &= ~(1u << j);

@@ -979,6 +979,7 @@ static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, 
     if (g_lz_fused) {
         if (tm) tm->mark(st, "lz_find");
         k_lz_find<<<nseg, (kFindWarps + 1) * 32, kFindSmem, st>>>(E, h_seg0[c0], slice); B2F_LAUNCH_CHECK();
+        if (tm) tm->mark(st, "lz_fixup");
         k_lz_fixup<<<592, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
         k_lz_fixup2<<<1184, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
     } else {

@@ -16,16 +16,52 @@ B2F_HD bool hdr_precheck(uint32_t w) {            // w = 32 stream bits starting
     return ((w >> 1) & 3u) == 2u && ((w >> 3) & 31u) <= 29u && ((w >> 8) & 31u) <= 29u;
 }
 
-// w0 = bits [0,64), w1 = bits [64,128) from the candidate
+// bit j of the result = hdr_precheck(w >> j) for j < 32 (uses bits [0, 45) of w): BTYPE is "bit 1 clear, bit 2 set";
+// a 5-bit field read LSB first is >= 30 exactly when its upper four bits are all set
+B2F_HD uint32_t hdr_precheck_mask32(uint64_t w) {
+    const uint64_t btype = ~(w >> 1) & (w >> 2);
+    const uint64_t hlit_bad = (w >> 4) & (w >> 5) & (w >> 6) & (w >> 7);
+    const uint64_t hdist_bad = (w >> 9) & (w >> 10) & (w >> 11) & (w >> 12);
+    return (uint32_t)(btype & ~hlit_bad & ~hdist_bad);
+}
+
+// Kraft sum and non-zero count of four packed 3-bit widths (12-bit index): kraft | count << 12
+static const uint16_t kKraft4Host[4096] = {
+#include "kraft4_table.inc"
+};
+#if defined(__CUDACC__)
+static __device__ const uint16_t kKraft4Dev[4096] = {
+#include "kraft4_table.inc"
+};
+#endif
+B2F_HD uint32_t kraft4(uint32_t idx) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&kKraft4Dev[idx]);
+#else
+    return kKraft4Host[idx];
+#endif
+}
+
+// w0 = bits [0,64), w1 = bits [64,128) from the candidate.  The code-length code must be complete (or a single 1-bit code).
 B2F_HD bool precode_check(uint64_t w0, uint64_t w1) {
     const uint32_t hclen = (uint32_t)((w0 >> 13) & 15u) + 4u;
-    // the 19 three-bit fields start at bit 17: fields 0..9 -> f0 (30 bits), fields 10..18 -> f1 (27 bits)
-    const uint32_t f0 = (uint32_t)(w0 >> 17) & 0x3FFFFFFFu;
-    const uint32_t f1 = (uint32_t)((w0 >> 47) | (w1 << 17)) & 0x7FFFFFFu;
-    uint32_t kraft = 0, nz = 0;
+    // the 19 three-bit fields start at bit 17; only the first hclen of them are present in the stream
+    uint64_t f = (w0 >> 17) | (w1 << 47);
+    f &= (1ull << (3u * hclen)) - 1ull;
+    uint32_t acc = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
+    for (uint32_t k = 0; k < 5; k++) acc += kraft4((uint32_t)(f >> (12 * k)) & 4095u);
+    const uint32_t kraft = acc & 4095u, nz = acc >> 12;
+    return kraft == 128u || (nz == 1 && kraft == 64u);
+}
+// the same test written out field by field (reference for the table version; used by the host checks)
+B2F_HD bool precode_check_loop(uint64_t w0, uint64_t w1) {
+    const uint32_t hclen = (uint32_t)((w0 >> 13) & 15u) + 4u;
+    const uint32_t f0 = (uint32_t)(w0 >> 17) & 0x3FFFFFFFu;
+    const uint32_t f1 = (uint32_t)((w0 >> 47) | (w1 << 17)) & 0x7FFFFFFu;
+    uint32_t kraft = 0, nz = 0;
     for (uint32_t i = 0; i < 19; i++) {
         const uint32_t len = i < 10 ? (f0 >> (3 * i)) & 7u : (f1 >> (3 * (i - 10))) & 7u;
         if (i < hclen && len) { kraft += 128u >> len; nz++; }

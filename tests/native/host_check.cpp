@@ -87,4 +87,19 @@ uint32_t hc_find_candidates(const uint8_t *in, uint64_t n, uint64_t *cands, uint
     }
     return k;
 }
+// equivalence of the finder's fast tests with their written-out forms on pseudo-random windows; returns the mismatch count
+uint32_t hc_finder_selftest(uint64_t seed, uint32_t n) {
+    uint32_t bad = 0;
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t w0 = next(), w1 = next();
+        if (i & 1) { w0 &= next(); w1 &= next(); }                 // sparser patterns: more zero widths, more passes
+        if ((i & 7) == 3) w0 = (w0 & ~(0x7ull << 0)) | 4;         // BTYPE = 10
+        if (precode_check(w0, w1) != precode_check_loop(w0, w1)) bad++;
+        const uint32_t m = hdr_precheck_mask32(w0);
+        for (uint32_t j = 0; j < 32; j++) if (((m >> j) & 1u) != (hdr_precheck((uint32_t)(w0 >> j)) ? 1u : 0u)) bad++;
+    }
+    return bad;
+}
 }

@@ -39,3 +39,12 @@ def test_false_positive_rate_on_random_bytes():
     blob = bytes(rng.getrandbits(8) for _ in range(300000))
     n, _ = hc.find_candidates(blob)
     assert n <= 2, n
+
+
+def test_fast_header_tests_equal_their_written_out_forms():
+    """table-driven Kraft test and 32-offsets-at-once precheck (what k_find_blocks runs) against the field-by-field forms"""
+    import ctypes as C
+    L = hc.lib()
+    L.hc_finder_selftest.restype = C.c_uint32
+    for seed in (1, 2, 3):
+        assert L.hc_finder_selftest(C.c_uint64(seed), C.c_uint32(400000)) == 0

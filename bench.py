@@ -279,7 +279,8 @@ def main():
     traffic = None
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")          # filled from an `ncu --set full` capture (see profiles/README.md)
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get(dom)
+        per_byte = json.load(open(prof)).get("per_input_byte", {}).get(dom)       # measured DRAM bytes per uncompressed byte of that kernel
+        traffic = int(per_byte * size) if per_byte is not None else None
     r = roof(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": r["achieved"], "peak": peak, "unit": "GB/s", "frac": r["frac"], "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": r["ms"], "algorithmic_bytes_per_launch": r["algorithmic_bytes"],

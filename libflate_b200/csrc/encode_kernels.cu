@@ -980,8 +980,10 @@ static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, 
         if (tm) tm->mark(st, "lz_find");
         k_lz_find<<<nseg, (kFindWarps + 1) * 32, kFindSmem, st>>>(E, h_seg0[c0], slice); B2F_LAUNCH_CHECK();
         if (tm) tm->mark(st, "lz_fixup");
-        k_lz_fixup<<<592, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
-        k_lz_fixup2<<<1184, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
+        // grids sized for the usual share of deferred positions (0.3 % / 0.03 %); both kernels stride over whatever was queued
+        const uint32_t gfix = min(4736u, max(148u, nseg * 4u));
+        k_lz_fixup<<<gfix, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
+        k_lz_fixup2<<<gfix, 256, 0, st>>>(E, slice); B2F_LAUNCH_CHECK();
     } else {
         if (tm) tm->mark(st, "lz_chain");
         k_lz_chain<<<nseg, 32, (1u << kHashBits) * 4, st>>>(E, h_seg0[c0]); B2F_LAUNCH_CHECK();

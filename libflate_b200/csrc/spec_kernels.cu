@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_round(SpecDev S, uint32_t rou
     const uint32_t b = owner_u32(S.blk_cta0, S.n_blocks, blockIdx.x);
     const uint32_t data_rel = S.blk_data_rel[b];
     if (data_rel == 0xFFFFFFFFu) return;                         // unusable header: the block never enters the chain
-    load_tables_smem(Ts, S.tabs + b);
     const uint32_t nseg = S.blk_seg0[b + 1] - S.blk_seg0[b];
     const uint32_t k = (blockIdx.x - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
     const uint32_t sg = S.blk_seg0[b] + min(k, nseg - 1);
@@ -189,6 +188,12 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_round(SpecDev S, uint32_t rou
         }
         if (store) { if (start >= seg_end) ex = start; else decode = true; }     // neighbour's last symbol may already cover this subsegment
     }
+    // confirmation rounds mostly carry results over: a CTA without a subsegment to decode skips the 11.6 KiB table load
+    if (!__syncthreads_or(decode ? 1 : 0)) {
+        if (store) { S.s_start[sg] = start; S.s_exit[sg] = ex; S.s_nsym[sg] = 0; S.s_nbytes[sg] = 0; if (round) atomicOr(S.changed + round, 1u); }
+        return;
+    }
+    load_tables_smem(Ts, S.tabs + b);
     TBits t;
     t.wp = reinterpret_cast<const uint32_t *>(p0 - lead);
     t.nwords = (S.in_len[m] + lead + 3) >> 2;

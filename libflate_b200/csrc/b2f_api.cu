@@ -473,6 +473,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
 
     ctx->tm.mark(ctx->stream, "clear");
     CK(cudaMemsetAsync(E.hist, 0, hist_bytes, ctx->stream));
+    CK(cudaMemsetAsync(E.hdr_bits, 0xFF, (size_t)n_blocks * 4, ctx->stream));       // "codes not built yet" (k_huff_build)
     CK(cudaMemsetAsync(ctx->buf[NB_OUT].p, 0, out_total, ctx->stream));
     struct FeedCtx { b2f_ctx *ctx; const EncPlan *P; const EncodeJob *job; uint8_t *d_in; } fc = { ctx, &P, &job, const_cast<uint8_t *>(job.d_in) };
     SliceFeed feed = { &fc, [](void *self, uint32_t c0, uint32_t c1, cudaStream_t st) -> cudaError_t {
@@ -484,9 +485,10 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
             if (a < b) { cudaError_t e = cudaMemcpyAsync(f->d_in + a, f->job->h_in[s] + (a - f->job->in_off[s]), b - a, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e; }
         }
         return cudaSuccess; } };
+    bool sliced = false;
     CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u,
-                     job.h_in ? &feed : nullptr));
-    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz() * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
+                     job.h_in ? &feed : nullptr, P.chunks.data(), &sliced));
+    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz(sliced) * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
     // checksums over the inputs (C1/C2) -> trailers
     const bool ck_async = ctx->overlap && ctx->aux[0] != nullptr;
     const uint32_t *d_crc = nullptr, *d_adler = nullptr;
@@ -521,8 +523,8 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         ctx->stats.kernel_launches += (C.n_pieces ? 1 : 0) + 1;
         d_crc = C.out_crc; d_adler = C.out_adler;
     }
-    CK(enc_launch_entropy(E, ctx->stream, &ctx->tm));
-    ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0);
+    CK(enc_launch_entropy(E, ctx->stream, &ctx->tm, sliced));
+    ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0, sliced);
     if (ck_async && (fmt == B2F_FMT_GZIP || fmt == B2F_FMT_ZLIB)) CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
     ctx->tm.mark(ctx->stream, "framing");
     k_write_framing<<<(unsigned)((n_streams + 63) / 64), 64, 0, ctx->stream>>>(ctx->buf[NB_OUT].as<uint8_t>(), E.out_base, E.stream_end_bits, d_hdr,
@@ -705,10 +707,10 @@ extern "C" int b2f_lz77_default(b2f_ctx *ctx, const uint8_t *buf, size_t len, ui
     uint64_t *d_total = reinterpret_cast<uint64_t *>(tp);
     E.hist = ctx->buf[NB_BLK].as<uint32_t>();
     CK(cudaMemsetAsync(E.hist, 0, kHistStride * 4, ctx->stream));
-    CK(enc_launch_lz(E, pref, pref + 2, pref + 4, pref + 6, ctx->stream, &ctx->tm, nullptr, nullptr, 0, nullptr));
+    CK(enc_launch_lz(E, pref, pref + 2, pref + 4, pref + 6, ctx->stream, &ctx->tm, nullptr, nullptr, 0, nullptr, nullptr, nullptr));
     uint32_t *d_codes = ctx->buf[NB_OUT].as<uint32_t>();
     CK(enc_launch_compact(E, tile_symoff, d_total, d_codes, ctx->stream));
-    ctx->stats.kernel_launches += enc_launch_count_lz() + 2;
+    ctx->stats.kernel_launches += enc_launch_count_lz(false) + 2;
     ctx->tm.finish(ctx->stream);
     CK(ctx->pin_res.ensure(64));
     uint64_t *h_total = ctx->pin_res.as<uint64_t>();

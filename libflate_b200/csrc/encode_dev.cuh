@@ -77,10 +77,12 @@ struct SliceFeed { void *self; cudaError_t (*copy)(void *self, uint32_t c0, uint
 
 cudaError_t enc_init_attributes();
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
-                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed);
-cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm);
+                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed,
+                          const ChunkDesc *h_chunks, bool *sliced);   // h_chunks (host copy of E.chunks) lets slices end on DEFLATE block boundaries and
+                                                                      // run k_huff_build / k_tile_bits for their own blocks; *sliced tells the entropy stage
+cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm, bool sliced);
 cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t *total, uint32_t *dst, cudaStream_t st);
-uint32_t enc_launch_count_lz();
-uint32_t enc_launch_count_entropy(bool has_tiles);
+uint32_t enc_launch_count_lz(bool sliced);
+uint32_t enc_launch_count_entropy(bool has_tiles, bool sliced);
 
 }  // namespace b2f

@@ -741,10 +741,12 @@ __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
 }
 
 // =============================================================================== K6 huff_build
-__global__ void __launch_bounds__(32) k_huff_build(EncDev E) {
+// skip_built: leave out the blocks whose codes a slice already built (hdr_bits is preset to 0xFFFFFFFF by the host)
+__global__ void __launch_bounds__(32) k_huff_build(EncDev E, uint32_t b_off, uint32_t skip_built) {
     __shared__ HuffWork W;
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.x + b_off;
     if (threadIdx.x != 0) return;
+    if (skip_built && E.hdr_bits[b] != 0xFFFFFFFFu) return;
     uint32_t *lit = E.litcode + (uint64_t)b * kLitStride;
     uint32_t *dist = E.distcode + (uint64_t)b * kDistStride;
     if (E.blocks[b].fixed) {
@@ -772,10 +774,10 @@ __device__ __forceinline__ void sym_bits(uint32_t s, const uint32_t *__restrict_
 }
 
 // =============================================================================== K7 tile_bits
-__global__ void __launch_bounds__(256) k_tile_bits(EncDev E) {
-    const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256) k_tile_bits(EncDev E, uint32_t t_off, uint32_t t_lim) {
+    const uint32_t tile = t_off + blockIdx.x * 8 + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
-    if (tile >= E.n_tiles) return;
+    if (tile >= t_lim) return;
     const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
     const ChunkDesc cd = E.chunks[c];
     const uint32_t ts = (tile - E.tile0[c]) * kTile;
@@ -1002,7 +1004,9 @@ static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, 
 // LZ77 stage.  With aux streams the chunks are split into slices that run concurrently: the chain / exits kernels are
 // latency bound (one warp per segment / thread per tile) and leave most issue slots free for the match kernel of another slice.
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
-                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed) {
+                          cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed,
+                          const ChunkDesc *h_chunks, bool *sliced) {
+    if (sliced) *sliced = false;
     if (E.n_chunks == 0) return cudaSuccess;
     if (n_aux < 2 || E.n_chunks < 2 * n_aux) {
         if (feed) { if (tm) tm->mark(st, "h2d"); cudaError_t fe = feed->copy(feed->self, 0, E.n_chunks, st); if (fe != cudaSuccess) return fe; }
@@ -1017,21 +1021,31 @@ cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_
         uint32_t c1 = c0;
         const uint32_t want = (uint32_t)((uint64_t)total * (g + 1) / n_aux);
         while (c1 < E.n_chunks && (h_pt0[c1] < want || g + 1 == n_aux)) c1++;
+        if (h_chunks) while (c1 > c0 && c1 < E.n_chunks && h_chunks[c1].block == h_chunks[c1 - 1].block) c1++;   // whole DEFLATE blocks per slice
         e = cudaStreamWaitEvent(aux[g], ev[0], 0); if (e != cudaSuccess) return e;
         if (feed) { e = feed->copy(feed->self, c0, c1, aux[g]); if (e != cudaSuccess) return e; }   // this slice's H2D overlaps the previous slices' kernels
         e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g], nullptr, g); if (e != cudaSuccess) return e;
+        if (h_chunks && c1 > c0) {
+            // the histograms of this slice's blocks are complete: their code construction (one thread per block, pure latency) runs
+            // here, under the other slices' LZ77 kernels, instead of on the critical path after the join
+            const uint32_t b0 = h_chunks[c0].block, b1 = c1 < E.n_chunks ? h_chunks[c1].block : h_chunks[c1 - 1].block + 1;
+            if (b1 > b0) { k_huff_build<<<b1 - b0, 32, 0, aux[g]>>>(E, b0, 0u); B2F_LAUNCH_CHECK(); }
+            const uint32_t t0 = h_tile0[c0], t1 = h_tile0[c1];
+            if (t1 > t0) { k_tile_bits<<<(t1 - t0 + 7) / 8, 256, 0, aux[g]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
+            if (sliced) *sliced = true;
+        }
         e = cudaEventRecord(ev[1 + g], aux[g]); if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st, ev[1 + g], 0); if (e != cudaSuccess) return e;
         c0 = c1;
     }
     return cudaSuccess;
 }
-cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm) {
+cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm, bool sliced) {
     if (tm) tm->mark(st, "huff_build");
-    k_huff_build<<<E.n_blocks, 32, 0, st>>>(E); B2F_LAUNCH_CHECK();
-    if (E.n_tiles) {
+    k_huff_build<<<E.n_blocks, 32, 0, st>>>(E, 0u, 1u); B2F_LAUNCH_CHECK();          // whatever the slices did not build (all blocks when not sliced)
+    if (E.n_tiles && !sliced) {
         if (tm) tm->mark(st, "tile_bits");
-        k_tile_bits<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E); B2F_LAUNCH_CHECK();
+        k_tile_bits<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E, 0u, E.n_tiles); B2F_LAUNCH_CHECK();
     }
     if (tm) tm->mark(st, "scan");
     k_scan_tiles<<<E.n_blocks, 256, 0, st>>>(E); B2F_LAUNCH_CHECK();
@@ -1049,7 +1063,7 @@ cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t 
     k_compact_syms<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E, tile_symoff, dst); B2F_LAUNCH_CHECK();
     return cudaSuccess;
 }
-uint32_t enc_launch_count_lz() { return g_lz_fused ? 6 : 5; }
-uint32_t enc_launch_count_entropy(bool has_tiles) { return has_tiles ? 6 : 4; }
+uint32_t enc_launch_count_lz(bool sliced) { return (g_lz_fused ? 6u : 5u) + (sliced ? 2u : 0u); }
+uint32_t enc_launch_count_entropy(bool has_tiles, bool sliced) { return has_tiles ? (sliced ? 5u : 6u) : 4u; }
 
 }  // namespace b2f

@@ -1,8 +1,9 @@
 // encode_kernels.cu -- the DEFLATE encode hot path as hand-written sm_100a kernels.
 //
 // Pipeline (one launch each, all on the ctx stream; see DESIGN.md for bytes/unit and rooflines):
-//   K1 lz_chain      one warp per <=256 KiB segment: ordered hash chains out of shared memory   (E2/A2)
-//   K2 lz_match      CTA per 16 KiB tile, 48 KiB window staged in shared memory: prev + LCP     (E2/L1)
+//   K1 lz_find       CTA per 256 KiB segment: ordered hash-table update handed from warp to warp, chain walks + LCP out of
+//                    shared-memory rings; lz_fixup / lz_fixup2 finish the few positions with very long chains    (E2/A2/L1)
+//      (lz_chain + lz_match: the earlier two-kernel form of the same step, B2F_LZ_FUSED=0)
 //   K3 parse_exits   thread per 2 KiB tile: right-to-left exit DP of the greedy walk            (E2)
 //   K4 parse_stitch  thread per chunk: chain the tile entry points
 //   K5 parse_emit    thread per tile: walk, emit symbols, per-block histograms                  (S1/S2)

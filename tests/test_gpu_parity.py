@@ -92,6 +92,30 @@ def test_lz77_multi_segment_chunk(ctx):                        # one chunk > 256
     assert np.array_equal(ctx.lz77_default(d), orc.lz77_default(d))
 
 
+def test_lz77_long_chains_and_long_runs(ctx):
+    """k_lz_find's bounded walks: runs of identical lines fill a few hash buckets with thousands of entries, so text that follows
+    (and collides with those buckets) needs k_lz_fixup (HBM walk) and k_lz_fixup2 (window scan); the runs themselves are
+    period-p matches of length 258 at every position (cooperative extension, max_len cap, chunk end inside a run)."""
+    rng = random.Random(11)
+    words = [bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyzABCDEFG_()0123456789") for _ in range(rng.randint(2, 9))) for _ in range(6000)]
+    def text(n):
+        b = bytearray()
+        while len(b) < n:
+            b += rng.choice(words) + b"\n"
+        return bytes(b[:n])
+    d = (b"Abc\n" * 9000 + text(50000) + b"The_quick\n" * 4000 + text(70000) + bytes(rng.getrandbits(8) for _ in range(20000)) +
+         b"x" * 40000 + text(30000) + b"Zed_(film)\n" * 3000)
+    for data in (d, d[:262144 + 5000], d[3:140001]):
+        got, want = ctx.lz77_default(data), orc.lz77_default(data)
+        assert len(got) == len(want)
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (int(bad[0]), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
+    for window, max_len in ((32768, 258), (5000, 258), (32768, 40)):
+        assert np.array_equal(ctx.lz77_default(d[:200000], window, max_len), orc.lz77_default(d[:200000], window, max_len)), (window, max_len)
+    sched = [8192] * (len(d) // 8192 + 1)
+    assert ctx.encode(1, d, sched) == orc.encode(1, d, sched)                   # zlib, 256 KiB chunks: runs cut by chunk ends
+
+
 # ------------------------------------------------------------------------------------------ encode goldens
 def test_encode_goldens(ctx):
     from libflate_b200 import native as nv

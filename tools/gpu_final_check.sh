@@ -1,3 +1,4 @@
+# Quick GPU check (gpurun): pytest -m gpu, smoke(), bench.py.
 set -x
 mkdir -p gpurun_out
 ( time timeout -s KILL 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/S_pytest.log 2>&1

@@ -1,3 +1,5 @@
+# Full GPU validation of a build (run through gpurun): pytest -m gpu, stage times, bench.py, ncu launch list, ncu --set full of the top kernels.
+# Everything lands in gpurun_out/P_*; copy what is to be kept into profiles/.
 set -x
 mkdir -p gpurun_out
 ( time timeout -s KILL 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/P_pytest.log 2>&1

@@ -379,6 +379,9 @@ __device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volati
 
 // The ring keeps the most recent kResRing bytes; every step is written through to HBM, so sources older than the ring are
 // read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
+#ifndef B2F_RESOLVE_FREE_FIRST
+#define B2F_RESOLVE_FREE_FIRST 0        // 1: copy the matches whose source ends before the step without ordering (modelled on the CPU against
+#endif                                  // sequential LZ77; not yet measured on a GPU -- round-2 candidate)
 constexpr uint32_t kResRing = 24576;
 // ceil(65536 / p): k mod p == k - p * ((k * inv) >> 16) for p < 32, k < 400 (run-length matches; avoids a division per match)
 __constant__ uint32_t kInvPeriod[32] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
@@ -454,10 +457,31 @@ __global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
         const uint32_t p2 = (inorder ? RBACK(d0, dist) : 0u) | (dist << 16);            // ring index of the first source byte | distance
         const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, inorder);
         const uint32_t nm = __popc(mmask);
+#if B2F_RESOLVE_FREE_FIRST
+        // Three of four matches of titles-shaped text (tools/analysis_resolve_steps.py: 12.2 of 16.3 per step) read only bytes
+        // from before the step (dist >= off + len): their sources are final, so they need no ordering among themselves and no
+        // barrier between them -- the copies of successive matches overlap.  Only the others (4.2 per step) run in token order.
+        const bool isfree = inorder && dist >= off + len;
+        const uint32_t fmask = __ballot_sync(0xFFFFFFFFu, isfree), dmask = mmask & ~fmask;
+        const uint32_t nf = __popc(fmask);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (inorder) r_sts64(qb + 8u * (isfree ? (uint32_t)__popc(fmask & lt) : nf + (uint32_t)__popc(dmask & lt)), p1, p2);
+        __syncwarp();
+        for (uint32_t i = 0; i < nf; i++) {
+            const uint2 c = r_lds64(qb + 8u * i);
+            const uint32_t mlen = c.x >> 16;
+            const uint32_t md = (c.x & 0xFFFFu) + lane, ms = (c.y & 0xFFFFu) + lane;
+            for (uint32_t k0 = 0; k0 < mlen; k0 += 32) r_copy8_if(k0 + lane < mlen, rb + RWRAP(ms + k0), rb + RWRAP(md + k0));
+        }
+        __syncwarp();
+        const uint32_t i_first = nf;
+#else
         if (inorder) r_sts64(qb + 8u * __popc(mmask & ((1u << lane) - 1u)), p1, p2);   // compacted, in token order
         __syncwarp();
-        uint2 nx = r_lds64(qb), nx2 = r_lds64(qb + 8u);
-        for (uint32_t i = 0; i < nm; i++) {
+        const uint32_t i_first = 0;
+#endif
+        uint2 nx = r_lds64(qb + 8u * i_first), nx2 = r_lds64(qb + 8u * (i_first + 1u));
+        for (uint32_t i = i_first; i < nm; i++) {
             const uint2 c = nx;
             nx = nx2;
             nx2 = r_lds64(qb + 8u * (i + 2));                       // parameters two matches ahead (slots >= nm are read but never used)

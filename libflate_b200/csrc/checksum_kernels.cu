@@ -47,6 +47,9 @@ __device__ __forceinline__ uint32_t find_owner64(const uint64_t *__restrict__ pr
 }
 
 constexpr uint32_t kPiece = 512;         // bytes per thread
+#ifndef B2F_CHECKSUM_VEC16
+#define B2F_CHECKSUM_VEC16 0             // 1: 16-byte loads in the piece loop (not yet measured on a GPU -- round-2 candidate)
+#endif
 
 // acc_crc[s] ^= crc(piece) * x^(8 * bytes after the piece);  acc_a/acc_b: Adler partial sums (already mod 65521)
 template <bool DO_CRC, bool DO_ADLER>
@@ -86,6 +89,37 @@ __global__ void __launch_bounds__(256) k_checksum(ChecksumDev C) {
             if (DO_ADLER) { s1 += d; s2 += (L - (uint32_t)(i - p0)) * d; }
             i++;
         }
+#if B2F_CHECKSUM_VEC16
+        // Every lane walks its own 512-byte piece, so a warp-wide load touches 32 different lines whatever its width: with 16-byte
+        // loads the L1 handles a quarter of the requests (the kernel is bound by them: 1.0 B of DRAM traffic per byte at 390 GB/s).
+        while (i + 4 <= p1 && ((reinterpret_cast<uintptr_t>(p + i)) & 15)) {       // words up to 16-byte alignment
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(p + i);
+            if (DO_CRC) { const uint32_t a = crc ^ w; crc = T[3][a & 0xFF] ^ T[2][(a >> 8) & 0xFF] ^ T[1][(a >> 16) & 0xFF] ^ T[0][a >> 24]; }
+            if (DO_ADLER) {
+                const uint32_t r = L - (uint32_t)(i - p0);
+                const uint32_t d0 = w & 0xFF, d1 = (w >> 8) & 0xFF, d2 = (w >> 16) & 0xFF, d3 = w >> 24;
+                s1 += d0 + d1 + d2 + d3;
+                s2 += r * d0 + (r - 1) * d1 + (r - 2) * d2 + (r - 3) * d3;
+            }
+            i += 4;
+        }
+        while (i + 16 <= p1) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + i);
+            const uint32_t ww[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                const uint32_t w = ww[q];
+                if (DO_CRC) { const uint32_t a = crc ^ w; crc = T[3][a & 0xFF] ^ T[2][(a >> 8) & 0xFF] ^ T[1][(a >> 16) & 0xFF] ^ T[0][a >> 24]; }
+                if (DO_ADLER) {
+                    const uint32_t r = L - (uint32_t)(i - p0) - 4u * q;
+                    const uint32_t d0 = w & 0xFF, d1 = (w >> 8) & 0xFF, d2 = (w >> 16) & 0xFF, d3 = w >> 24;
+                    s1 += d0 + d1 + d2 + d3;
+                    s2 += r * d0 + (r - 1) * d1 + (r - 2) * d2 + (r - 3) * d3;
+                }
+            }
+            i += 16;
+        }
+#endif
         while (i + 4 <= p1) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(p + i);
             if (DO_CRC) { const uint32_t a = crc ^ w; crc = T[3][a & 0xFF] ^ T[2][(a >> 8) & 0xFF] ^ T[1][(a >> 16) & 0xFF] ^ T[0][a >> 24]; }

@@ -53,7 +53,7 @@ struct PinBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_DEC_CAND, NB_DEC_BLK, NB_DEC_SER, NB_SPEC_TAB, NB_SPEC_SEG, NB_SPEC_TOK, NB_SPEC_SEL, NB_COUNT };
+enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_DEC_CAND, NB_DEC_BLK, NB_DEC_SER, NB_SPEC_TAB, NB_SPEC_SEG, NB_SPEC_TOK, NB_SPEC_SEL, NB_SPEC_SYM, NB_COUNT };
 
 struct b2f_ctx {
     int device = 0;
@@ -253,9 +253,9 @@ int run_checksums(b2f_ctx *ctx, const uint8_t *d_base, const std::vector<uint64_
     const size_t n = off.size();
     crc.assign(n, 0); adler.assign(n, 1);
     if (!n) return B2F_OK;
-    std::vector<uint64_t> piece0(n + 1, 0);
-    for (size_t s = 0; s < n; s++) piece0[s + 1] = piece0[s] + (len[s] + kChecksumPiece - 1) / kChecksumPiece;
-    // layout in NB_CK: off | len | piece0 | acc_a | acc_b | acc_crc | init | out_crc | out_adler
+    std::vector<uint64_t> piece0(n + 1, 0); uint32_t span_rows = 0;
+    checksum_plan(d_base, off.data(), len.data(), n, piece0.data(), &span_rows);
+    // layout in NB_CK: off | len | span0 | acc_a | acc_b | acc_crc | init | out_crc | out_adler
     size_t o_off = 0, o_len = o_off + n * 8, o_p0 = o_len + n * 8, o_a = o_p0 + (n + 1) * 8, o_b = o_a + n * 8, o_c = o_b + n * 8,
            o_init = o_c + n * 4, o_oc = o_init + n * 4, o_oa = o_oc + n * 4, total = align_up(o_oa + n * 4, 16);
     CK(ctx->buf[NB_CK].ensure(total));
@@ -267,15 +267,15 @@ int run_checksums(b2f_ctx *ctx, const uint8_t *d_base, const std::vector<uint64_
     uint8_t *dm = ctx->buf[NB_CK].as<uint8_t>();
     CK(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, ctx->stream));
     ChecksumDev C;
-    C.in = d_base; C.off = (const uint64_t *)(dm + o_off); C.len = (const uint64_t *)(dm + o_len); C.piece0 = (const uint64_t *)(dm + o_p0);
-    C.n_pieces = piece0[n]; C.n_streams = (uint32_t)n;
+    C.in = d_base; C.off = (const uint64_t *)(dm + o_off); C.len = (const uint64_t *)(dm + o_len); C.span0 = (const uint64_t *)(dm + o_p0);
+    C.n_spans = piece0[n]; C.span_rows = span_rows; C.n_streams = (uint32_t)n;
     C.acc_a = (uint64_t *)(dm + o_a); C.acc_b = (uint64_t *)(dm + o_b); C.acc_crc = (uint32_t *)(dm + o_c);
     C.init_crc = (init && do_crc) ? (const uint32_t *)(dm + o_init) : nullptr;
     C.init_adler = (init && do_adler) ? (const uint32_t *)(dm + o_init) : nullptr;
     C.out_crc = (uint32_t *)(dm + o_oc); C.out_adler = (uint32_t *)(dm + o_oa);
     ctx->tm.mark(ctx->stream, "checksum");
     CK(checksum_launch(C, do_crc, do_adler, ctx->stream));
-    ctx->stats.kernel_launches += (C.n_pieces ? 1 : 0) + 1;
+    ctx->stats.kernel_launches += (C.n_spans ? 1 : 0) + 1;
     CK(ctx->pin_res.ensure(n * 8));
     uint32_t *hr = ctx->pin_res.as<uint32_t>();
     CK(cudaMemcpyAsync(hr, dm + o_oc, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -493,8 +493,8 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     const bool ck_async = ctx->overlap && ctx->aux[0] != nullptr;
     const uint32_t *d_crc = nullptr, *d_adler = nullptr;
     if (fmt == B2F_FMT_GZIP || fmt == B2F_FMT_ZLIB) {
-        std::vector<uint64_t> piece0(n_streams + 1, 0);
-        for (size_t s = 0; s < n_streams; s++) piece0[s + 1] = piece0[s] + (job.in_len[s] + kChecksumPiece - 1) / kChecksumPiece;
+        std::vector<uint64_t> piece0(n_streams + 1, 0); uint32_t span_rows = 0;
+        checksum_plan(job.d_in, job.in_off.data(), job.in_len.data(), n_streams, piece0.data(), &span_rows);
         size_t n = n_streams;
         size_t o_off = 0, o_len = o_off + n * 8, o_p0 = o_len + n * 8, o_a = o_p0 + (n + 1) * 8, o_b = o_a + n * 8, o_c = o_b + n * 8,
                o_oc = o_c + n * 4, o_oa = o_oc + n * 4, total = align_up(o_oa + n * 4, 16);
@@ -505,8 +505,8 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         uint8_t *dm = ctx->buf[NB_CK].as<uint8_t>();
         CK(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, ctx->stream));
         ChecksumDev C; memset(&C, 0, sizeof C);
-        C.in = job.d_in; C.off = (const uint64_t *)(dm + o_off); C.len = (const uint64_t *)(dm + o_len); C.piece0 = (const uint64_t *)(dm + o_p0);
-        C.n_pieces = piece0[n]; C.n_streams = (uint32_t)n;
+        C.in = job.d_in; C.off = (const uint64_t *)(dm + o_off); C.len = (const uint64_t *)(dm + o_len); C.span0 = (const uint64_t *)(dm + o_p0);
+        C.n_spans = piece0[n]; C.span_rows = span_rows; C.n_streams = (uint32_t)n;
         C.acc_a = (uint64_t *)(dm + o_a); C.acc_b = (uint64_t *)(dm + o_b); C.acc_crc = (uint32_t *)(dm + o_c);
         C.out_crc = (uint32_t *)(dm + o_oc); C.out_adler = (uint32_t *)(dm + o_oa);
         // The checksum only needs the input: with overlap on it runs on an aux stream next to the entropy stage (huff_build, the scans
@@ -520,7 +520,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
             ctx->tm.mark(ctx->stream, "checksum");
             CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->stream));
         }
-        ctx->stats.kernel_launches += (C.n_pieces ? 1 : 0) + 1;
+        ctx->stats.kernel_launches += (C.n_spans ? 1 : 0) + 1;
         d_crc = C.out_crc; d_adler = C.out_adler;
     }
     CK(enc_launch_entropy(E, ctx->stream, &ctx->tm, sliced));
@@ -927,6 +927,9 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     if (it == cands.end() || it->first != m || it->second != pos) { ok = false; break; }
                     const size_t ci = (size_t)(it - cands.begin());
                     if (h_st[ci] != 0) { ok = false; break; }
+                    // The sub-block decoder fetches whole words, so a symbol can be "completed" by bytes beyond the member (stale or zero
+                    // fill): a block whose EndOfBlock lies past the member's last bit is a truncated stream -> in-order kernel (UnexpectedEof)
+                    if (pos + h_ee[ci] > in_len[m] * 8) { ok = false; break; }
                     sel_blocks.push_back((uint32_t)ci); k_out.push_back(out_off[m] + out); k_len.push_back(h_no[ci]);
                     blk_out0[ci] = out_off[m] + out; blk_tok0[ci] = tok_total;
                     tok_total += h_nt[ci]; out += h_no[ci]; pos += h_ee[ci]; fin = (h_fl[ci] & 1u) != 0;
@@ -998,41 +1001,53 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 Packer PS(ctx->pin_sel, ctx->buf[NB_SPEC_SEL]);
                 const size_t s_sel = PS.add(blk_sel.data(), ncand * 4), s_o0 = PS.add(blk_out0.data(), ncand * 8), s_t0 = PS.add(blk_tok0.data(), ncand * 8),
                              s_lst = PS.add(sel_blocks.data(), nsel * 4);
-                // unit slots: a block of n output bytes can be cut into at most n / kUnitMinBytes + 1 independent LZ77 units
-                std::vector<uint32_t> unit0(nsel + 1, 0);
-                for (size_t k = 0; k < nsel; k++) unit0[k + 1] = unit0[k] + (uint32_t)(k_len[k] / kUnitMinBytes + 1);
-                const uint32_t nunits = unit0.back();
-                const size_t s_u0 = PS.add(unit0.data(), (nsel + 1) * 4);
-                const size_t s_uo = PS.reserve((size_t)nunits * 8), s_ut = PS.reserve((size_t)nunits * 8), s_un = PS.reserve((size_t)nunits * 8),
-                             s_ub = PS.reserve((size_t)nunits * 8), s_uk = PS.reserve((size_t)nunits * 4);
-                const size_t s_err = PS.reserve((size_t)nunits * 4), s_len = PS.reserve((size_t)nunits * 8), s_end = PS.reserve(16);
+                // segment slots: a block of n output bytes is resolved as ceil(n / kSegBytes) segments (spec_kernels.cu)
+                std::vector<uint32_t> slot0(nsel + 1, 0);
+                uint64_t out_hi = 0;
+                for (size_t k = 0; k < nsel; k++) {
+                    slot0[k + 1] = slot0[k] + (uint32_t)std::max<uint64_t>(1, (k_len[k] + kSegBytes - 1) / kSegBytes);
+                    out_hi = std::max<uint64_t>(out_hi, k_out[k] + k_len[k]);
+                }
+                const uint32_t nslots = slot0.back();
+                const size_t s_u0 = PS.add(slot0.data(), (nsel + 1) * 4);
+                const size_t s_st = PS.reserve((size_t)nslots * 8), s_so = PS.reserve((size_t)nslots * 8), s_sn = PS.reserve((size_t)nslots * 4),
+                             s_sb = PS.reserve((size_t)nslots * 4), s_sm = PS.reserve((size_t)nslots * 4), s_sr = PS.reserve((size_t)nslots * 4),
+                             s_sc = PS.reserve((size_t)nslots);
+                const size_t s_err = PS.reserve(n * 4);
                 CK(PS.commit(ctx->stream));
+                CK(ctx->buf[NB_SPEC_SYM].ensure(out_hi * 2 + 256));
                 S.blk_sel = PS.ptr<uint32_t>(s_sel); S.blk_out0 = PS.ptr<uint64_t>(s_o0); S.blk_tok0 = PS.ptr<uint64_t>(s_t0); S.sel_blocks = PS.ptr<uint32_t>(s_lst);
                 S.mem_out_off = PA.ptr<uint64_t>(a_oo);
                 S.tokens = ctx->buf[NB_SPEC_TOK].as<uint32_t>(); S.out = d_out;
-                S.sel_unit0 = PS.ptr<uint32_t>(s_u0); S.unit_out = PS.ptr<uint64_t>(s_uo); S.unit_tok = PS.ptr<uint64_t>(s_ut); S.unit_ntok = PS.ptr<uint64_t>(s_un);
-                S.unit_nout = PS.ptr<uint64_t>(s_ub); S.unit_blk = PS.ptr<uint32_t>(s_uk);
-                S.res_err = PS.ptr<uint32_t>(s_err); S.res_len = PS.ptr<uint64_t>(s_len);
+                S.n_sel = (uint32_t)nsel; S.n_slots = nslots; S.sel_slot0 = PS.ptr<uint32_t>(s_u0);
+                S.seg_tok = PS.ptr<uint64_t>(s_st); S.seg_out = PS.ptr<uint64_t>(s_so); S.seg_ntok = PS.ptr<uint32_t>(s_sn); S.seg_nout = PS.ptr<uint32_t>(s_sb);
+                S.seg_member = PS.ptr<uint32_t>(s_sm); S.seg_reach = PS.ptr<uint32_t>(s_sr); S.seg_cut = PS.ptr<uint8_t>(s_sc);
+                S.sym16 = ctx->buf[NB_SPEC_SYM].as<uint16_t>(); S.mem_err = PS.ptr<uint32_t>(s_err);
+                CK(cudaMemsetAsync(S.mem_err, 0, n * 4, ctx->stream));
                 ctx->tm.mark(ctx->stream, "spec_tokens");
                 CK(spec_launch_tokens(S, (uint32_t)nsel, ctx->stream));
                 ctx->tm.mark(ctx->stream, "lz_resolve");
-                CK(spec_launch_units(S, (uint32_t)nsel, ctx->stream));
-                // The output is copied to pinned host memory on a side stream as soon as the resolve has finished.
+                CK(spec_launch_segments(S, ctx->stream));
+                ctx->tm.mark(ctx->stream, "lz_subst");
+                // The substitution runs in parts over the slots; each part's output is copied to pinned host memory on a side stream
+                // while the next part runs.
                 {
                     uint64_t total_len = 0; for (size_t k = 0; k < nsel; k++) total_len += k_len[k];
-                    // (splitting the resolve itself does not pay: every unit is one latency-bound warp, so each part would take as long
-                    // as the whole; the copy of the output still overlaps the checksum kernel and the host-side trailer checks)
-                    const uint32_t nparts = 1;
+                    bool any_host = false;
+                    for (size_t k = 0; k < nsel; k++) if (mem[cands[sel_blocks[k]].first].h_out) { any_host = true; break; }
+                    const uint32_t nparts = (any_host && total_len >= (64u << 20)) ? 4u : 1u;
                     size_t b0 = 0; uint64_t acc = 0;
                     for (uint32_t part = 0; part < nparts; part++) {
                         size_t b1 = b0;
                         const uint64_t want = total_len * (part + 1) / nparts;
                         while (b1 < nsel && (acc < want || part + 1 == nparts)) { acc += k_len[b1]; b1++; }
-                        CK(spec_launch_resolve(S, unit0[b0], unit0[b1], ctx->stream));
+                        CK(spec_launch_subst(S, slot0[b0], slot0[b1], ctx->stream));
                         ctx->stats.kernel_launches += 1;
-                        bool any_host = false;
-                        for (size_t k = b0; k < b1; k++) if (mem[cands[sel_blocks[k]].first].h_out) { any_host = true; break; }
                         if (any_host) {
+                            // A chain that starts in this part may run on into the next one (foreign streams); the blocks of a part are
+                            // final only when every earlier part is: parts run in order on one stream, so the event covers them.  Blocks whose
+                            // chain started in an EARLIER part are complete too (that launch is before this event).  What may still be
+                            // open is the tail of a chain running into later blocks -- those belong to later parts and are copied there.
                             CK(cudaEventRecord(ctx->aux_ev[part], ctx->stream));
                             CK(cudaStreamWaitEvent(ctx->aux[0], ctx->aux_ev[part], 0));
                             for (size_t k = b0; k < b1; k++) {
@@ -1045,23 +1060,16 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     }
                     for (uint32_t m : big) if (is_par[m] && mem[m].h_out) copied[m] = 1;
                 }
-                ctx->stats.kernel_launches += 2;
+                ctx->stats.kernel_launches += 4;
                 ctx->tm.mark(ctx->stream, "sync");
-                const size_t rb = s_end - s_ub;                      // unit_nout | unit_blk | res_err | res_len
-                CK(ctx->pin_res.ensure(rb + 64));
-                uint8_t *hr2 = ctx->pin_res.as<uint8_t>();
-                CK(cudaMemcpyAsync(hr2, PS.ptr<uint8_t>(s_ub), rb, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(ctx->pin_res.ensure(n * 4 + 64));
+                uint32_t *h_err = ctx->pin_res.as<uint32_t>();
+                CK(cudaMemcpyAsync(h_err, S.mem_err, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
-                const uint64_t *h_un = (const uint64_t *)hr2; const uint32_t *h_ub = (const uint32_t *)(hr2 + (s_uk - s_ub));
-                const uint32_t *h_err = (const uint32_t *)(hr2 + (s_err - s_ub)); const uint64_t *h_len = (const uint64_t *)(hr2 + (s_len - s_ub));
-                // a unit whose matches reach before its own start (foreign stream with cross-block references) or an inconsistent
-                // size: redo the member with the in-order kernel
+                // a member with a match that reaches before its first byte (libflate: "Too long backword reference") or an inconsistent
+                // size: redo it with the in-order kernel, which reproduces the reference's error and partial output
                 std::vector<char> redo(n, 0);
-                for (size_t k = 0; k < nsel; k++) {
-                    uint64_t sum = 0; bool bad = false;
-                    for (uint32_t u = unit0[k]; u < unit0[k + 1]; u++) if (h_ub[u] != 0xFFFFFFFFu) { sum += h_len[u]; if (h_err[u] || h_len[u] != h_un[u]) bad = true; }
-                    if (bad || sum != k_len[k]) redo[cands[sel_blocks[k]].first] = 1;
-                }
+                for (uint32_t m : big) if (is_par[m] && h_err[m]) redo[m] = 1;
                 bool any_redo = false;
                 for (uint32_t m : big) if (is_par[m] && redo[m]) { is_par[m] = 0; copied[m] = 0; serial_spec.push_back(m); any_redo = true; }
                 if (any_redo) CK(cudaStreamSynchronize(ctx->aux[0]));     // early copies of a redone member must not land after its final copy

@@ -1,24 +1,46 @@
-// checksum_kernels.cu -- CRC-32 (ISO-HDLC, reflected 0xEDB88320) and Adler-32 as coalesced reductions.
+// checksum_kernels.cu -- CRC-32 (ISO-HDLC, reflected 0xEDB88320) and Adler-32 as coalesced streaming reductions.
 // Replaces checksum::Crc32 / checksum::Adler32 (src/checksum.rs:4-33 -> crates crc32fast / adler32).
 //
-// Both checksums are linear in the message, so every thread hashes one small piece and the pieces are
-// folded with the algebraic combine:
-//   CRC  : crc(A||B) = crc(A) * x^(8|B|) mod P  xor crc(B)   (GF(2) polynomial product, reflected bit order)
-//   Adler: A = 1 + sum d_i,  B = n + sum (n - i) d_i  (mod 65521)
+// Both checksums are linear in the message (CRC over GF(2), Adler over Z/65521), so the message is cut into pieces that are
+// hashed independently and folded with the algebraic combine.  What makes this version HBM bound is HOW it is cut:
+//   * a warp reads 512-byte rows with one 16-byte load per lane (fully coalesced, eight rows in flight per warp);
+//   * each lane therefore owns four words of every row, i.e. 128 interleaved sub-streams per warp.  For a sub-stream whose words
+//     are 512 bytes apart the CRC recurrence is  R <- Z512(R xor w)  (Z_m = "advance the register over m zero bytes", a linear map),
+//     which costs exactly the four table lookups of slice-by-4 -- with tables for Z512 instead of Z4;
+//   * the four Z512 tables are replicated per lane ("bank private": entry i of lane l at word 32 i + l, 128 KiB of shared memory),
+//     so the data dependent lookups never conflict;
+//   * at the end of a span the 128 sub-streams are folded by a 7-level tree (Z4, Z8 inside a lane, Z16 .. Z256 across lanes by
+//     shuffles; small ordinary tables), and the span's value is moved to its place in the stream with x^(8 k) mod P.
+// Bytes before the stream (alignment lead-in) and after it (row padding) are read as zero: leading zeros do not change a CRC
+// register that starts at 0, trailing zeros are undone by the constant x^(-8*512) in k_checksum_final (x is invertible mod P).
+// Adler-32: per lane S1 = sum of chunk sums, S2 = sum of row index * chunk sum, S3 = sum of in-chunk weighted sums (dp4a);
+// B follows from (bytes after the chunk) * S1 algebra, all reduced mod 65521 at the end of a span.
+// The algebra was checked against zlib on the CPU first (tools/crc_interleave_model.py).
 #include "common.cuh"
 #include "checksum_dev.cuh"
 
 namespace b2f {
 
+constexpr uint32_t kPoly = 0xEDB88320u;
+// tables (per device): Z512 slices | Z4..Z256 slices | x^(8 v 256^w) for w < 5 | x^(2^k)
+__device__ uint32_t g_tabU[4 * 256];
+__device__ uint32_t g_tabZ[7 * 4 * 256];
+__device__ uint32_t g_tabXP[5 * 256];
 __constant__ uint32_t c_x2n[32];        // x^(2^k) mod P, reflected
+__constant__ uint32_t c_xinv512;        // x^(-8*512) mod P
 
 static uint32_t h_multmodp(uint32_t a, uint32_t b) {
     uint32_t m = 1u << 31, p = 0;
     for (;;) {
         if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
         m >>= 1;
-        b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+        b = (b & 1) ? (b >> 1) ^ kPoly : b >> 1;
     }
+    return p;
+}
+static uint32_t h_xpow(uint64_t bits, const uint32_t *x2n) {      // x^bits mod P
+    uint32_t p = 1u << 31; uint32_t k = 0;
+    while (bits) { if (bits & 1) p = h_multmodp(x2n[k & 31], p); bits >>= 1; k++; }
     return p;
 }
 __device__ __forceinline__ uint32_t d_multmodp(uint32_t a, uint32_t b) {
@@ -26,11 +48,11 @@ __device__ __forceinline__ uint32_t d_multmodp(uint32_t a, uint32_t b) {
 #pragma unroll 4
     for (int i = 31; i >= 0; i--) {           // bit 31 of `a` is x^0
         if ((a >> i) & 1u) p ^= b;
-        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+        b = (b & 1u) ? (b >> 1) ^ kPoly : b >> 1;
     }
     return p;
 }
-// x^(8*len) mod P
+// x^(8*len) mod P, generic exponent (k_checksum_final: once per stream)
 __device__ __forceinline__ uint32_t d_xpow8(uint64_t len) {
     uint32_t p = 1u << 31; uint32_t k = 3;
     while (len) {
@@ -39,6 +61,15 @@ __device__ __forceinline__ uint32_t d_xpow8(uint64_t len) {
     }
     return p;
 }
+// v * x^(8*e) mod P with the byte-window table (e < 2^40): at most five products
+__device__ __forceinline__ uint32_t d_shift8(uint32_t v, uint64_t e) {
+#pragma unroll 1
+    for (uint32_t w = 0; w < 5 && e; w++, e >>= 8) {
+        const uint32_t b = (uint32_t)e & 255u;
+        if (b) v = d_multmodp(__ldg(&g_tabXP[w * 256 + b]), v);
+    }
+    return v;
+}
 
 __device__ __forceinline__ uint32_t find_owner64(const uint64_t *__restrict__ prefix, uint32_t n, uint64_t idx) {
     uint32_t lo = 0, hi = n;
@@ -46,110 +77,132 @@ __device__ __forceinline__ uint32_t find_owner64(const uint64_t *__restrict__ pr
     return lo;
 }
 
-constexpr uint32_t kPiece = 512;         // bytes per thread
-#ifndef B2F_CHECKSUM_VEC16
-#define B2F_CHECKSUM_VEC16 0             // 1: 16-byte loads in the piece loop (not yet measured on a GPU -- round-2 candidate)
-#endif
+constexpr uint32_t kCkThreads = 1024;
+constexpr uint32_t kCkUBytes = 4 * 256 * 32 * 4;                  // bank-private Z512 tables
+constexpr uint32_t kCkZBytes = 7 * 4 * 256 * 4;
+constexpr uint32_t kCkSmemCrc = kCkUBytes + kCkZBytes;
 
-// acc_crc[s] ^= crc(piece) * x^(8 * bytes after the piece);  acc_a/acc_b: Adler partial sums (already mod 65521)
+__device__ __forceinline__ uint32_t ck_lds(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// Z512(x): four conflict-free lookups; ul = shared address of the lane's column of table 0
+__device__ __forceinline__ uint32_t ck_adv512(uint32_t x, uint32_t ul) {
+    const uint32_t a = ck_lds(ul + ((x << 7) & 0x7F80u));
+    const uint32_t b = ck_lds(ul + 32768u + ((x >> 1) & 0x7F80u));
+    const uint32_t c = ck_lds(ul + 65536u + ((x >> 9) & 0x7F80u));
+    const uint32_t d = ck_lds(ul + 98304u + ((x >> 17) & 0x7F80u));
+    return a ^ b ^ c ^ d;
+}
+// Z_(4 << level)(x) from the ordinary tables (zt = shared address of g_tabZ's copy)
+__device__ __forceinline__ uint32_t ck_advz(uint32_t x, uint32_t zt, uint32_t level) {
+    const uint32_t t = zt + level * 4096u;
+    return ck_lds(t + ((x & 0xFFu) << 2)) ^ ck_lds(t + 1024u + (((x >> 8) & 0xFFu) << 2)) ^ ck_lds(t + 2048u + (((x >> 16) & 0xFFu) << 2)) ^
+           ck_lds(t + 3072u + ((x >> 24) << 2));
+}
+
+// the lane's 16-byte chunk at virtual position pv of the stream (virtual = counted from the stream start rounded down to 16);
+// bytes outside [mis, nv) read as zero and nothing outside the stream's own 16-byte chunks is touched
+__device__ __forceinline__ uint4 ck_load_edge(const uint8_t *__restrict__ base, uint64_t pv, uint64_t mis, uint64_t nv) {
+    uint32_t w[4] = { 0, 0, 0, 0 };
+    for (uint32_t k = 0; k < 16; k++) {
+        const uint64_t q = pv + k;
+        if (q >= mis && q < nv) w[k >> 2] |= (uint32_t)base[q] << (8u * (k & 3u));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// acc_crc[s] ^= raw(span) * x^(8 * (bytes of the stream after the span's rows + 512));  acc_a / acc_b: Adler partial sums mod 65521
 template <bool DO_CRC, bool DO_ADLER>
-__global__ void __launch_bounds__(256) k_checksum(ChecksumDev C) {
-    __shared__ uint32_t T[4][256];
+__global__ void __launch_bounds__(kCkThreads, 1) k_checksum(ChecksumDev C) {
+    extern __shared__ __align__(16) uint8_t csm[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t ul = 0, zt = 0;
     if (DO_CRC) {
-        for (uint32_t i = threadIdx.x; i < 256; i += 256) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            T[0][i] = c;
+        uint32_t *su = reinterpret_cast<uint32_t *>(csm);
+        // replicate: the warp takes 32 entries at a time, entry e goes to words 32 e + lane (conflict free)
+        for (uint32_t e0 = warp * 32; e0 < 1024; e0 += 32 * (kCkThreads / 32)) {
+            const uint32_t mine = g_tabU[e0 + lane];
+#pragma unroll 8
+            for (uint32_t e = 0; e < 32; e++) su[(e0 + e) * 32 + lane] = __shfl_sync(0xFFFFFFFFu, mine, e);
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < 256; i += 256) {
-            uint32_t c = T[0][i];
-            for (int t = 1; t < 4; t++) { c = (c >> 8) ^ T[0][c & 0xFF]; T[t][i] = c; }
-        }
+        uint32_t *sz = reinterpret_cast<uint32_t *>(csm + kCkUBytes);
+        for (uint32_t i = threadIdx.x; i < 7 * 4 * 256; i += kCkThreads) sz[i] = g_tabZ[i];
+        ul = (uint32_t)__cvta_generic_to_shared(su) + 4u * lane;
+        zt = (uint32_t)__cvta_generic_to_shared(sz);
         __syncthreads();
     }
-    const uint64_t piece = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    const bool active = piece < C.n_pieces;
-    uint32_t s = 0; uint64_t p0 = 0, p1 = 0, n = 0;
-    if (active) {
-        s = find_owner64(C.piece0, C.n_streams, piece);
-        n = C.len[s];
-        p0 = (piece - C.piece0[s]) * kPiece;
-        p1 = p0 + kPiece < n ? p0 + kPiece : n;
-    }
-    const uint8_t *__restrict__ p = C.in + (active ? C.off[s] : 0);
-    uint32_t crc = 0xFFFFFFFFu, s1 = 0, s2 = 0;
-    if (active && p1 > p0) {
-        uint64_t i = p0;
-        const uint32_t L = (uint32_t)(p1 - p0);
-        // head bytes up to 4-byte alignment of the global address
-        while (i < p1 && ((reinterpret_cast<uintptr_t>(p + i)) & 3)) {
-            const uint32_t d = p[i];
-            if (DO_CRC) crc = T[0][(crc ^ d) & 0xFF] ^ (crc >> 8);
-            if (DO_ADLER) { s1 += d; s2 += (L - (uint32_t)(i - p0)) * d; }
-            i++;
-        }
-#if B2F_CHECKSUM_VEC16
-        // Every lane walks its own 512-byte piece, so a warp-wide load touches 32 different lines whatever its width: with 16-byte
-        // loads the L1 handles a quarter of the requests (the kernel is bound by them: 1.0 B of DRAM traffic per byte at 390 GB/s).
-        while (i + 4 <= p1 && ((reinterpret_cast<uintptr_t>(p + i)) & 15)) {       // words up to 16-byte alignment
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(p + i);
-            if (DO_CRC) { const uint32_t a = crc ^ w; crc = T[3][a & 0xFF] ^ T[2][(a >> 8) & 0xFF] ^ T[1][(a >> 16) & 0xFF] ^ T[0][a >> 24]; }
+    for (uint64_t item = (uint64_t)blockIdx.x * (kCkThreads / 32) + warp; item < C.n_spans; item += (uint64_t)gridDim.x * (kCkThreads / 32)) {
+        const uint32_t s = find_owner64(C.span0, C.n_streams, item);
+        const uint8_t *p0 = C.in + C.off[s];
+        const uint64_t mis = reinterpret_cast<uintptr_t>(p0) & 15u;
+        const uint8_t *__restrict__ base = p0 - mis;                          // 16-byte aligned; virtual position 0
+        const uint64_t n = C.len[s], nv = n + mis;
+        const uint64_t rows_total = (nv + kChecksumRow - 1) / kChecksumRow;
+        const uint64_t r0 = (item - C.span0[s]) * C.span_rows;
+        const uint64_t r1 = min(rows_total, r0 + C.span_rows);
+        const uint32_t K = (uint32_t)(r1 - r0);
+        uint32_t R0 = 0, R1 = 0, R2 = 0, R3 = 0;                              // CRC registers of the lane's four sub-streams
+        uint32_t S1 = 0, S2 = 0, S3 = 0;
+        auto row = [&](const uint4 v, uint32_t k, bool last) {
             if (DO_ADLER) {
-                const uint32_t r = L - (uint32_t)(i - p0);
-                const uint32_t d0 = w & 0xFF, d1 = (w >> 8) & 0xFF, d2 = (w >> 16) & 0xFF, d3 = w >> 24;
-                s1 += d0 + d1 + d2 + d3;
-                s2 += r * d0 + (r - 1) * d1 + (r - 2) * d2 + (r - 3) * d3;
+                const uint32_t c0 = __dp4a(v.x, 0x01010101u, 0u), c1 = __dp4a(v.y, 0x01010101u, 0u), c2 = __dp4a(v.z, 0x01010101u, 0u), c3 = __dp4a(v.w, 0x01010101u, 0u);
+                const uint32_t c = c0 + c1 + c2 + c3;
+                S1 += c; S2 += k * c;
+                S3 += __dp4a(v.x, 0x03020100u, 0u) + __dp4a(v.y, 0x03020100u, 0u) + __dp4a(v.z, 0x03020100u, 0u) + __dp4a(v.w, 0x03020100u, 0u) + 4u * c1 + 8u * c2 + 12u * c3;
             }
-            i += 4;
-        }
-        while (i + 16 <= p1) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p + i);
-            const uint32_t ww[4] = { v.x, v.y, v.z, v.w };
+            if (DO_CRC) {
+                R0 ^= v.x; R1 ^= v.y; R2 ^= v.z; R3 ^= v.w;
+                if (!last) { R0 = ck_adv512(R0, ul); R1 = ck_adv512(R1, ul); R2 = ck_adv512(R2, ul); R3 = ck_adv512(R3, ul); }
+            }
+        };
+        // rows that lie wholly inside the stream are loaded unconditionally, four at a time with the next four already in flight
+        const uint64_t ri0 = mis ? 1 : 0, ri1 = nv / kChecksumRow;            // interior rows: [ri0, ri1)
+        uint64_t r = r0;
+        if (r < r1 && r < ri0) { row(ck_load_edge(base, r * kChecksumRow + 16u * lane, mis, nv), (uint32_t)(r - r0), r + 1 == r1); r++; }
+        const uint64_t re = min(r1, ri1);                                     // interior rows of this span: [r, re)
+        if (r < re) {
+            const uint4 *__restrict__ gp = reinterpret_cast<const uint4 *>(base + r * kChecksumRow) + lane;   // row stride = 32 uint4
+            uint32_t k = (uint32_t)(r - r0);
+            const uint32_t cnt = (uint32_t)(re - r);
+            uint4 cur[4], nxt[4];
 #pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                const uint32_t w = ww[q];
-                if (DO_CRC) { const uint32_t a = crc ^ w; crc = T[3][a & 0xFF] ^ T[2][(a >> 8) & 0xFF] ^ T[1][(a >> 16) & 0xFF] ^ T[0][a >> 24]; }
-                if (DO_ADLER) {
-                    const uint32_t r = L - (uint32_t)(i - p0) - 4u * q;
-                    const uint32_t d0 = w & 0xFF, d1 = (w >> 8) & 0xFF, d2 = (w >> 16) & 0xFF, d3 = w >> 24;
-                    s1 += d0 + d1 + d2 + d3;
-                    s2 += r * d0 + (r - 1) * d1 + (r - 2) * d2 + (r - 3) * d3;
-                }
+            for (uint32_t u = 0; u < 4; u++) cur[u] = u < cnt ? __ldg(gp + 32u * u) : make_uint4(0, 0, 0, 0);
+            uint32_t done = 0;
+            while (done < cnt) {
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++) nxt[u] = done + 4 + u < cnt ? __ldg(gp + 32u * (done + 4 + u)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++)
+                    if (done + u < cnt) row(cur[u], k + done + u, r + done + u + 1 == r1);
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++) cur[u] = nxt[u];
+                done += 4;
             }
-            i += 16;
+            r = re;
         }
-#endif
-        while (i + 4 <= p1) {
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(p + i);
-            if (DO_CRC) { const uint32_t a = crc ^ w; crc = T[3][a & 0xFF] ^ T[2][(a >> 8) & 0xFF] ^ T[1][(a >> 16) & 0xFF] ^ T[0][a >> 24]; }
-            if (DO_ADLER) {
-                const uint32_t r = L - (uint32_t)(i - p0);
-                const uint32_t d0 = w & 0xFF, d1 = (w >> 8) & 0xFF, d2 = (w >> 16) & 0xFF, d3 = w >> 24;
-                s1 += d0 + d1 + d2 + d3;
-                s2 += r * d0 + (r - 1) * d1 + (r - 2) * d2 + (r - 3) * d3;
-            }
-            i += 4;
-        }
-        while (i < p1) {
-            const uint32_t d = p[i];
-            if (DO_CRC) crc = T[0][(crc ^ d) & 0xFF] ^ (crc >> 8);
-            if (DO_ADLER) { s1 += d; s2 += (L - (uint32_t)(i - p0)) * d; }
-            i++;
-        }
-    }
-    if (active && p1 > p0) {
-        const uint64_t after = n - p1;
+        for (; r < r1; r++) row(ck_load_edge(base, r * kChecksumRow + 16u * lane, mis, nv), (uint32_t)(r - r0), r + 1 == r1);
+        const uint64_t vend = r1 * kChecksumRow;                              // virtual end of the span's rows (may lie beyond nv in the last row)
         if (DO_CRC) {
-            crc = ~crc;
-            const uint32_t contrib = after ? d_multmodp(d_xpow8(after), crc) : crc;
-            atomicXor(C.acc_crc + s, contrib);
+            // fold the 128 sub-streams: slot q of lane l sits 4 (4 l + q) bytes into the row
+            uint32_t y = ck_advz(ck_advz(R0, zt, 0) ^ R1, zt, 1) ^ (ck_advz(R2, zt, 0) ^ R3);
+#pragma unroll
+            for (uint32_t lv = 0; lv < 5; lv++) {
+                const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, y, 1u << lv);
+                if ((lane & ((2u << lv) - 1u)) == 0) y = ck_advz(y, zt, 2 + lv) ^ other;
+            }
+            // lane 0: raw(rows) = Z4(y); place it: x^(8 (nv - vend + 4 + 512)); the + 512 keeps the exponent positive (undone in the final kernel)
+            if (lane == 0) atomicXor(C.acc_crc + s, d_shift8(y, nv + 4u + kChecksumRow - vend));
         }
         if (DO_ADLER) {
-            const uint64_t a = s1 % 65521u;
-            const uint64_t b = ((uint64_t)s2 + (after % 65521u) * (uint64_t)(s1 % 65521u)) % 65521u;
-            atomicAdd(reinterpret_cast<unsigned long long *>(C.acc_a + s), (unsigned long long)a);
-            atomicAdd(reinterpret_cast<unsigned long long *>(C.acc_b + s), (unsigned long long)b);
+            // weight of the byte j of the chunk of row k: nv - (r0 512 + 512 k + 16 lane + j)
+            const uint64_t w0 = nv - r0 * kChecksumRow - 16u * lane;          // (wraps for lanes beyond the end: their S1 is 0)
+            const uint64_t t1 = (w0 % 65521u) * (uint64_t)(S1 % 65521u) % 65521u;
+            const uint64_t t2 = ((uint64_t)kChecksumRow * S2 + S3) % 65521u;
+            uint32_t a = S1 % 65521u, b = (uint32_t)((t1 + 65521u - t2) % 65521u);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, d); b += __shfl_xor_sync(0xFFFFFFFFu, b, d); }
+            if (lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(C.acc_a + s), (unsigned long long)(a % 65521u));
+                atomicAdd(reinterpret_cast<unsigned long long *>(C.acc_b + s), (unsigned long long)(b % 65521u));
+            }
         }
     }
 }
@@ -160,10 +213,10 @@ __global__ void __launch_bounds__(64) k_checksum_final(ChecksumDev C, int do_crc
     if (s >= C.n_streams) return;
     const uint64_t n = C.len[s];
     if (do_crc) {
+        // crc(M, init) = Z_n(init ^ ~0) ^ raw(M) ^ ~0 ; raw(M) = acc * x^(-8*512)
         const uint32_t init = C.init_crc ? C.init_crc[s] : 0u;
-        uint32_t v = C.acc_crc[s];
-        if (init) v ^= n ? d_multmodp(d_xpow8(n), init) : init;
-        C.out_crc[s] = v;
+        const uint32_t raw = d_multmodp(c_xinv512, C.acc_crc[s]);
+        C.out_crc[s] = n ? (d_multmodp(d_xpow8(n), ~init) ^ raw ^ 0xFFFFFFFFu) : init;
     }
     if (do_adler) {
         const uint32_t init = C.init_adler ? C.init_adler[s] : 1u;
@@ -175,20 +228,39 @@ __global__ void __launch_bounds__(64) k_checksum_final(ChecksumDev C, int do_crc
 }
 
 cudaError_t checksum_init_tables() {
-    uint32_t t[32];
-    uint32_t p = 1u << 30;
-    t[0] = p;
-    for (int n = 1; n < 32; n++) t[n] = p = h_multmodp(p, p);
-    return cudaMemcpyToSymbol(c_x2n, t, sizeof t);
+    static uint32_t hU[4 * 256], hZ[7 * 4 * 256], hXP[5 * 256], x2n[32], t0[256];
+    static bool built = false;
+    static uint32_t xinv = 0;
+    if (!built) {
+        uint32_t p = 1u << 30;
+        x2n[0] = p;
+        for (int n = 1; n < 32; n++) x2n[n] = p = h_multmodp(p, p);
+        for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? kPoly ^ (c >> 1) : c >> 1; t0[i] = c; }
+        auto zadv = [&](uint32_t c, uint32_t m) { for (uint32_t k = 0; k < m; k++) c = t0[c & 0xFF] ^ (c >> 8); return c; };
+        for (uint32_t j = 0; j < 4; j++) for (uint32_t b = 0; b < 256; b++) hU[j * 256 + b] = zadv(b << (8 * j), 512);
+        for (uint32_t lv = 0; lv < 7; lv++) for (uint32_t j = 0; j < 4; j++) for (uint32_t b = 0; b < 256; b++) hZ[(lv * 4 + j) * 256 + b] = zadv(b << (8 * j), 4u << lv);
+        for (uint32_t w = 0; w < 5; w++) for (uint32_t v = 0; v < 256; v++) hXP[w * 256 + v] = h_xpow(8ull * v << (8 * w), x2n);
+        xinv = h_xpow(0xFFFFFFFFull - 8ull * kChecksumRow, x2n);              // x has order 2^32 - 1 modulo the (primitive) CRC-32 polynomial
+        built = true;
+    }
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(g_tabU, hU, sizeof hU)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(g_tabZ, hZ, sizeof hZ)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(g_tabXP, hXP, sizeof hXP)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_x2n, x2n, sizeof x2n)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_xinv512, &xinv, sizeof xinv)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_checksum<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCkSmemCrc)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_checksum<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCkSmemCrc);
 }
 
 cudaError_t checksum_launch(const ChecksumDev &C, bool do_crc, bool do_adler, cudaStream_t st) {
     if (C.n_streams == 0) return cudaSuccess;
-    if (C.n_pieces) {
-        const uint32_t grid = (uint32_t)((C.n_pieces + 255) / 256);
-        if (do_crc && do_adler) k_checksum<true, true><<<grid, 256, 0, st>>>(C);
-        else if (do_crc) k_checksum<true, false><<<grid, 256, 0, st>>>(C);
-        else if (do_adler) k_checksum<false, true><<<grid, 256, 0, st>>>(C);
+    if (C.n_spans) {
+        const uint32_t per = kCkThreads / 32;
+        const uint32_t grid = (uint32_t)((C.n_spans + per - 1) / per < 148 ? (C.n_spans + per - 1) / per : 148);
+        if (do_crc && do_adler) k_checksum<true, true><<<grid, kCkThreads, kCkSmemCrc, st>>>(C);
+        else if (do_crc) k_checksum<true, false><<<grid, kCkThreads, kCkSmemCrc, st>>>(C);
+        else if (do_adler) k_checksum<false, true><<<grid, kCkThreads, 0, st>>>(C);
         cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
     }
     k_checksum_final<<<(C.n_streams + 63) / 64, 64, 0, st>>>(C, do_crc ? 1 : 0, do_adler ? 1 : 0);

@@ -5,7 +5,16 @@
 namespace b2f {
 constexpr uint32_t kSpecBits = 4096;      // bits per speculative subsegment (one thread each)
 constexpr uint32_t kSpecCta = 128;        // subsegments per CTA (all of one block)
-constexpr uint64_t kUnitMinBytes = 65536; // smallest independent LZ77 unit worth its own warp
+// LZ77 resolution works on SEGMENTS: runs of subsegments of one block whose output starts inside the same kSegBytes-aligned
+// window of the block's output.  One warp resolves a segment on its own; bytes copied from before the segment's first byte
+// become 16-bit MARKERS (0x8000 | distance before the segment start - 1) that a second pass substitutes in stream order.
+#ifndef B2F_SEG_BYTES
+#define B2F_SEG_BYTES 6144
+#endif
+constexpr uint32_t kSegBytes = B2F_SEG_BYTES;   // output bytes per segment slot (a segment can be longer: its last subsegment is never split)
+constexpr uint32_t kSegRing = 8192;       // symbols of a segment kept in shared memory by k_seg_resolve
+constexpr uint32_t kSegStepMax = 4096;    // output symbols of one 32-token step (a step with more output is cut short)
+constexpr uint32_t kMarker = 0x8000u;
 struct SpecDev {
     const uint8_t *in; const uint64_t *in_off, *in_len;             // members
     uint32_t n_blocks;                                              // candidate blocks, sorted by (member, bit)
@@ -23,13 +32,18 @@ struct SpecDev {
     const uint32_t *blk_sel; const uint64_t *blk_out0, *blk_tok0; const uint32_t *sel_blocks;
     const uint64_t *mem_out_off;
     uint32_t *tokens; uint8_t *out;
-    const uint32_t *sel_unit0;                                      // [n_sel + 1] prefix of unit slots per selected block
-    uint64_t *unit_out, *unit_tok, *unit_ntok, *unit_nout; uint32_t *unit_blk;   // per unit slot
-    uint32_t *res_err; uint64_t *res_len;                           // per unit slot
+    uint32_t n_sel, n_slots;
+    const uint32_t *sel_slot0;                                      // [n_sel + 1] prefix of segment slots per selected block (stream order)
+    uint64_t *seg_tok, *seg_out;                                    // per slot: first token (absolute index into tokens), first output byte (offset in out)
+    uint32_t *seg_ntok, *seg_nout;                                  // per slot: tokens / output bytes (0 = empty slot)
+    uint32_t *seg_member, *seg_reach;                               // per slot: member; how far before its first byte its matches reach (0 = self-contained)
+    uint8_t *seg_cut;                                               // per slot: 1 = no segment from here on reads anything before this one (chain start)
+    uint16_t *sym16;                                                // [out span] resolved symbol or marker of every output byte (indexed like out)
+    uint32_t *mem_err;                                              // per member: 1 inconsistent size, 2 match reaches before the member's first byte
 };
 cudaError_t spec_init_attributes();
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st);
 cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
-cudaError_t spec_launch_units(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
-cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t u0, uint32_t u1, cudaStream_t st);
+cudaError_t spec_launch_segments(const SpecDev &S, cudaStream_t st);              // k_seg_plan + k_seg_resolve + k_seg_cuts
+cudaError_t spec_launch_subst(const SpecDev &S, uint32_t s0, uint32_t s1, cudaStream_t st);   // k_seg_subst over the chains that start in slots [s0, s1)
 }

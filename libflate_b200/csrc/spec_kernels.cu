@@ -10,9 +10,8 @@
 //   k_spec_verify    CTA per block  : checks that every start equals its left neighbour's exit (=> by induction the true
 //                    parse), finds EndOfBlock, exclusive scans of symbol/byte counts
 //   k_spec_tokens    thread per subsegment: final decode from the true start, writes one token per symbol
-//   k_spec_resolve   warp per block : LZ77 resolution of the token stream, 32 tokens per step, 64 KiB output ring in
-//                    shared memory (history window), multi-round resolution of matches that depend on each other,
-//                    coalesced 32 KiB flushes to HBM
+//   k_seg_plan/resolve/cuts/subst : LZ77 resolution of the token stream by ~6 KiB segments, one warp each, with 16-bit
+//                    markers for bytes copied from before the segment; one substitution pass per chain of dependent segments
 // Nothing here is trusted blindly: the host accepts a block only if its verified EndOfBlock lands exactly on the next
 // block of the chain; otherwise the stream goes to the exact in-order kernel (decode_kernels.cu).
 // Reference behaviour being reproduced: src/deflate/decode.rs:112-130, symbol.rs:193-243, libflate_lz77/src/lib.rs:164-194.
@@ -318,226 +317,271 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
     }
 }
 
-// ---------------------------------------------------------------------------------- independent LZ77 units inside a block
-// A subsegment boundary is a cut point when no later match of the block reaches back across it (libflate's 256 KiB LZ77
-// chunks never reference each other: libflate_lz77/src/default.rs:73,108).  Units between cut points resolve in parallel.
-__global__ void __launch_bounds__(32) k_spec_units(SpecDev S) {
-    const uint32_t b = S.sel_blocks[blockIdx.x];
-    if (threadIdx.x != 0) return;
-    const uint32_t s0 = S.blk_seg0[b];
-    const uint32_t k0 = S.blk_data_rel[b] / kSpecBits, e = S.blk_eob_seg[b];
-    const uint32_t u0 = S.sel_unit0[blockIdx.x], umax = S.sel_unit0[blockIdx.x + 1] - u0;
+// ---------------------------------------------------------------------------------- LZ77 resolution by segments + markers
+// The reference resolves a stream's back-references strictly in order into one growing buffer (libflate_lz77/src/lib.rs:164-194).
+// Here the token stream of the verified chain is cut into SEGMENTS of about kSegBytes output bytes and every segment is resolved
+// by its own warp AS IF nothing were known about the bytes before it: a byte copied from before the segment's first byte becomes
+// a 16-bit marker (kMarker | distance before the segment start - 1); copies of markers stay markers.  Then
+//   k_seg_cuts   finds the segments no later segment reaches across (libflate's 256 KiB LZ77 chunks never reference each other,
+//                libflate_lz77/src/default.rs:73,108; foreign streams have few or no such cuts), and
+//   k_seg_subst  runs one CTA per chain of segments between two cuts: segment after segment, every marker is replaced by the final
+//                byte it points at (all targets lie before the segment, i.e. are final) out of a shared-memory window.
+// The serial dependency of the reference is thereby reduced to one barrier per segment inside a chain; everything else -- the
+// whole token walk -- runs on thousands of independent warps.  Cross-block references (zlib / gzip output) are ordinary markers.
+__global__ void __launch_bounds__(128) k_seg_plan(SpecDev S) {
+    const uint32_t slot = blockIdx.x * 128 + threadIdx.x;
+    if (slot >= S.n_slots) return;
+    const uint32_t k = owner_u32(S.sel_slot0, S.n_sel, slot);
+    const uint32_t b = S.sel_blocks[k], j = slot - S.sel_slot0[k];
+    const uint32_t s0 = S.blk_seg0[b], k0 = S.blk_data_rel[b] / kSpecBits, e = S.blk_eob_seg[b];
     const uint64_t nout = S.blk_nout[b], ntok = S.blk_ntok[b];
-    const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b];
-    // Right to left over the subsegments with `after` = lowest position read by any token of LATER subsegments.  A cut can
-    // only lie inside subsegment k when after >= start(k); the exact token is found by walking k's tokens backwards.
-    uint32_t nu = 0;
-    int64_t after = INT64_MAX;
-    uint64_t unit_end_out = nout, unit_end_tok = ntok;
-    auto emit = [&](uint64_t o, uint64_t tkn) {
-        const uint32_t slot = u0 + umax - 1 - nu;
-        S.unit_out[slot] = o; S.unit_tok[slot] = tkn; S.unit_ntok[slot] = unit_end_tok - tkn; S.unit_nout[slot] = unit_end_out - o; S.unit_blk[slot] = b;
-        unit_end_out = o; unit_end_tok = tkn; nu++;
+    // the block's subsegments k0..e have non-decreasing output offsets: segment j = those that start in [j, j+1) * kSegBytes
+    auto first = [&](uint64_t target) {
+        uint32_t lo = k0, hi = e + 1;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.s_out_rel[s0 + mid] >= target) hi = mid; else lo = mid + 1; }
+        return lo;
     };
-    for (uint32_t k = e + 1; k-- > k0;) {
-        const uint64_t o = S.s_out_rel[s0 + k], t0 = S.s_tok_rel[s0 + k];
-        const uint64_t o_next = k == e ? nout : S.s_out_rel[s0 + k + 1], t_next = k == e ? ntok : S.s_tok_rel[s0 + k + 1];
-        if (k > k0 && after >= (int64_t)o && unit_end_out - o >= kUnitMinBytes && nu + 1 < umax && t_next > t0) {
-            // walk the tokens of subsegment k backwards: cut before token t iff every token >= t reads at or after dst(t)
-            int64_t run = after; uint64_t dst_end = o_next;
-            for (uint64_t t = t_next; t-- > t0;) {
-                const uint32_t tk = tok[t];
-                const uint32_t len = (tk & kSymPtr) ? (tk >> 16) & 0x1FFu : (tk == kTokSkip ? 0u : 1u);
-                const uint64_t dst = dst_end - len;
-                if (tk & kSymPtr) { const int64_t src = (int64_t)dst - (int64_t)(tk & 0xFFFFu); if (src < run) run = src; }
-                if (len && run >= (int64_t)dst && unit_end_out - dst >= kUnitMinBytes && (t > t0 || k > k0)) { emit(dst, t); break; }
-                dst_end = dst;
-            }
-        }
-        const int64_t ms = S.s_min_src[s0 + k];
-        if (ms < after) after = ms;
+    const uint32_t f0 = j == 0 ? k0 : first((uint64_t)j * kSegBytes), f1 = first((uint64_t)(j + 1) * kSegBytes);
+    uint64_t t0 = 0, t1 = 0, o0 = 0, o1 = 0;
+    if (f0 < f1) {
+        t0 = S.s_tok_rel[s0 + f0]; o0 = S.s_out_rel[s0 + f0];
+        t1 = f1 <= e ? S.s_tok_rel[s0 + f1] : ntok; o1 = f1 <= e ? S.s_out_rel[s0 + f1] : nout;
     }
-    emit(S.s_out_rel[s0 + k0], S.s_tok_rel[s0 + k0]);             // the block's first unit
-    // compact to the front of the block's slot range (order does not matter); mark the rest empty
-    for (uint32_t i = 0; i < nu; i++) {
-        const uint32_t from = u0 + umax - nu + i, to = u0 + i;
-        if (from != to) { S.unit_out[to] = S.unit_out[from]; S.unit_tok[to] = S.unit_tok[from]; S.unit_ntok[to] = S.unit_ntok[from]; S.unit_nout[to] = S.unit_nout[from]; S.unit_blk[to] = S.unit_blk[from]; }
-    }
-    for (uint32_t i = nu; i < umax; i++) S.unit_blk[u0 + i] = 0xFFFFFFFFu;
+    S.seg_tok[slot] = S.blk_tok0[b] + t0; S.seg_ntok[slot] = (uint32_t)(t1 - t0);
+    S.seg_out[slot] = S.blk_out0[b] + o0; S.seg_nout[slot] = (uint32_t)(o1 - o0);
+    S.seg_member[slot] = S.blk_member[b]; S.seg_reach[slot] = 0; S.seg_cut[slot] = 0;
 }
 
-// ---------------------------------------------------------------------------------- LZ77 resolution (warp per block)
-__device__ __forceinline__ uint32_t r_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void r_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint2 r_lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void r_sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
-// ring[dst] = ring[src] for the lanes with on != 0, as predicated instructions (no divergent branch)
-__device__ __forceinline__ void r_copy8_if(uint32_t on, uint32_t src, uint32_t dst) {
-    asm volatile("{ .reg .pred p; .reg .u32 v; setp.ne.u32 p, %0, 0; @p ld.shared.u8 v, [%1]; @p st.shared.u8 [%2], v; }" :: "r"(on), "r"(src), "r"(dst) : "memory");
-}
-__device__ __forceinline__ uint32_t r_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+constexpr uint32_t kSegMask = kSegRing - 1;
+constexpr uint32_t kSegFreeQ = 2 * kSegRing;                     // byte offset of the queue of order-free copies (<= 64 entries + 4 read-ahead)
+constexpr uint32_t kSegOrdQ = kSegFreeQ + 68 * 8;                // byte offset of the queue of in-order copies (<= 32 entries + 2 read-ahead)
+constexpr uint32_t kSegSmem = kSegOrdQ + 34 * 8;
+static_assert((kSegRing & kSegMask) == 0 && kSegStepMax + 258 + 8 < kSegRing, "segment ring geometry");
 
-// The ring keeps the most recent kResRing bytes; every step is written through to HBM, so sources older than the ring are
-// read back from HBM/L2 (ld.global.cg).  24 KiB per warp => 9 resident warps per SM instead of 3 with a full 64 KiB window.
-#ifndef B2F_RESOLVE_FREE_FIRST
-#define B2F_RESOLVE_FREE_FIRST 0        // 1: copy the matches whose source ends before the step without ordering (modelled on the CPU against
-#endif                                  // sequential LZ77; not yet measured on a GPU -- round-2 candidate)
-constexpr uint32_t kResRing = 24576;
-// ceil(65536 / p): k mod p == k - p * ((k * inv) >> 16) for p < 32, k < 400 (run-length matches; avoids a division per match)
-__constant__ uint32_t kInvPeriod[32] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
-constexpr uint32_t kResSmem = kResRing + 34 * 8 + 32;            // + the per-step queue of match parameters + 32 write-only dummy bytes
-
-__global__ void __launch_bounds__(32) k_spec_resolve(SpecDev S, uint32_t uoff) {
-    extern __shared__ __align__(16) uint8_t ring[];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t u = blockIdx.x + uoff;
-    const uint32_t b = S.unit_blk[u];
-    if (b == 0xFFFFFFFFu) return;                                // unused slot
-    const uint32_t *__restrict__ tok = S.tokens + S.blk_tok0[b] + S.unit_tok[u];
-    const uint64_t ntok = S.unit_ntok[u];
-    const uint64_t out0 = S.blk_out0[b] + S.unit_out[u];        // absolute offset in S.out of the unit's first byte
-    const uint64_t mem0 = S.mem_out_off[S.blk_member[b]];       // start of the member's output (history before it does not exist)
-    uint8_t *__restrict__ g = S.out;
-    const uint32_t galign = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
-    uint32_t rb;                                                 // 32-bit shared address of the ring, pinned in a register (the
-    {                                                            // compiler would otherwise rebuild it from %cluster_ctaid per access)
-        const uint64_t ga = reinterpret_cast<uint64_t>(ring);
-        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(rb) : "l"(ga));
-    }
-    const uint32_t qb = rb + kResRing;                           // queue of (p1, p2) pairs of the step's in-order matches
-    const uint32_t dummy = qb + 34 * 8 + lane;
-    uint64_t pos = out0;
-    // ring index of `pos`, kept incrementally (no modulo in the loop) and congruent to the global ADDRESS mod 4, so that aligned
-    // words of the ring are aligned words of the output
-    uint32_t rpos = (uint32_t)((out0 + galign) % kResRing);
-    uint64_t flushed = out0;                                     // bytes before this offset are in HBM
-    bool words = false;                                          // write-through by aligned words once `flushed` is word aligned
-    uint32_t err = 0;
-    uint32_t tnext = lane < ntok ? __ldg(tok + lane) : 0u;
-    // ring index of the byte `off` bytes after the step start (off < kResRing) / `back` bytes before index i (back <= kResRing)
-    #define RFWD(off) ((rpos + (off)) >= kResRing ? (rpos + (off)) - kResRing : (rpos + (off)))
-    #define RBACK(i, back) ((i) >= (back) ? (i) - (back) : (i) + kResRing - (back))
-    #define RWRAP(i) ((i) >= kResRing ? (i) - kResRing : (i))
-    for (uint64_t i0 = 0; i0 < ntok; i0 += 32) {
-        const uint32_t tk = tnext;
-        const uint64_t in = i0 + 32 + lane;
-        tnext = in < ntok ? __ldg(tok + in) : 0u;                // prefetch the next step's tokens
-        const bool live = i0 + lane < ntok && tk != kTokSkip;
-        const bool is_m = live && (tk & kSymPtr);
-        const uint32_t len = !live ? 0u : is_m ? (tk >> 16) & 0x1FFu : 1u;
+__global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
+    extern __shared__ __align__(16) uint8_t seg_smem[];
+    uint16_t *ring = reinterpret_cast<uint16_t *>(seg_smem);          // symbol of segment position p at (a0 + p) & kSegMask
+    uint2 *fq = reinterpret_cast<uint2 *>(seg_smem + kSegFreeQ), *oq = reinterpret_cast<uint2 *>(seg_smem + kSegOrdQ);
+    const uint32_t lane = threadIdx.x, slot = blockIdx.x;
+    const uint32_t nout = S.seg_nout[slot];
+    if (!nout) return;
+    const uint32_t ntok = S.seg_ntok[slot];
+    const uint32_t *__restrict__ tok = S.tokens + S.seg_tok[slot];
+    const uint64_t A = S.seg_out[slot];                               // offset in out / sym16 of the segment's first byte
+    const uint32_t mem = S.seg_member[slot];
+    const uint64_t avail = A - S.mem_out_off[mem];                    // bytes of the member that precede the segment
+    uint16_t *__restrict__ gsym = S.sym16 + A;
+    const uint32_t a0 = (uint32_t)A & kSegMask;                       // ring index == absolute offset mod kSegRing: 8-symbol groups of
+                                                                      // the ring are 16-byte aligned groups of sym16
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t lead = (8u - ((uint32_t)A & 7u)) & 7u;             // symbols before the first 16-byte aligned group of sym16
+    uint32_t pos = 0, flushed = 0, err = 0, reach = 0;                // segment-relative
+    for (uint32_t i0 = 0; i0 < ntok;) {
+        const uint32_t tk = i0 + lane < ntok ? __ldg(tok + i0 + lane) : kTokSkip;
+        bool live = tk != kTokSkip;
+        bool is_m = live && (tk & kSymPtr);
+        uint32_t len = !live ? 0u : is_m ? (tk >> 16) & 0x1FFu : 1u;
         uint32_t incl = len;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const uint32_t off = incl - len;                          // offset of this token's output inside the step
-        const uint32_t d0 = RFWD(off);                            // ring index of this token's first output byte
-        if (live && !is_m) ring[d0] = (uint8_t)tk;
+        uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), take = 32;
+        if (total > kSegStepMax) {                                    // (long runs only) keep the step's output well inside the ring
+            take = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, incl <= kSegStepMax));
+            if (lane >= take) { live = false; is_m = false; len = 0; }
+            total = __shfl_sync(0xFFFFFFFFu, incl, take - 1);
+        }
+        const uint32_t off = incl - len;                              // (garbage for dropped lanes, which do nothing)
+        const uint32_t dst = pos + off;
+        const uint32_t d0 = (a0 + dst) & kSegMask;
+        if (live && !is_m) ring[d0] = (uint16_t)(tk & 0xFFu);
         const uint32_t dist = tk & 0xFFFFu;
-        const uint64_t dst = pos + off;
-        const bool ok = is_m && (uint64_t)dist <= dst - out0;     // source inside the unit; anything else is flagged and never dereferenced
-        if (is_m && !ok) err |= (uint64_t)dist > dst - mem0 ? 2u : 1u;   // reaches before the unit (1) / before the stream (2)
-        // Matches whose source is older than the ring read final data from HBM and never depend on this step's output: every
-        // lane resolves its own one now, all in parallel (their loads overlap instead of queueing up one per match).
-        const bool is_far = ok && dist + (total - off) > kResRing;
+        if (is_m && (uint64_t)dist > (uint64_t)dst + avail) err |= 2u;             // "Too long backword reference": the in-order kernel reports it
+        const int32_t srel = (int32_t)dst - (int32_t)dist;            // segment-relative position of the first source byte
+        const uint32_t before = (is_m && srel < 0) ? (uint32_t)(-srel) : 0u;
+        reach = max(reach, before);
+        const uint32_t nmark = min(len, before);                      // leading bytes that come from before the segment
+        const uint32_t len2 = len - nmark, off2 = off + nmark;        // the rest copies segment bytes
+        const bool rest = is_m && len2 != 0;
+        const bool is_far = rest && dist + (total - off2) > kSegRing; // source older than what the ring still holds at the end of the step
+        const bool isfree = rest && !is_far && dist >= off + len;     // source ends before the step: needs no ordering
+        const bool inord = rest && !is_far && !isfree;
+        const uint32_t fm = __ballot_sync(0xFFFFFFFFu, nmark != 0), fc = __ballot_sync(0xFFFFFFFFu, isfree), om = __ballot_sync(0xFFFFFFFFu, inord);
+        const uint32_t nfm = (uint32_t)__popc(fm), nfree = nfm + (uint32_t)__popc(fc), nord = (uint32_t)__popc(om);
+        const uint32_t d2 = (a0 + pos + off2) & kSegMask;
+        if (nmark) fq[__popc(fm & lt)] = make_uint2(d0 | (nmark << 16), kMarker | (before - 1u));                // value of byte k: second word - k
+        if (isfree) fq[nfm + __popc(fc & lt)] = make_uint2(d2 | (len2 << 16), ((d2 - dist) & kSegMask) | (dist << 16));
+        if (inord) oq[__popc(om & lt)] = make_uint2(d2 | (len2 << 16), ((d2 - dist) & kSegMask) | (dist << 16));
         if (is_far) {
-            const uint8_t *gs = g + dst - dist;
-            for (uint32_t k0 = 0; k0 < len; k0 += 16) {           // 16 loads in flight, then the stores (a byte-by-byte loop would
-                uint32_t v[16];                                   // serialise on load latency: ring[] and g[] may alias for the compiler)
+            // (segments much longer than the ring only) the source left the ring: it was written through to sym16 in an earlier step
+            const uint16_t *gs = gsym + (pos + off2 - dist);
+            for (uint32_t k = 0; k < len2; k++) ring[(d2 + k) & kSegMask] = __ldcg(gs + k);
+        }
+        __syncwarp();
+        // ---- order-free work, four entries in flight: markers (no reads at all) and copies whose source is older than the step
+        for (uint32_t i = 0; i < nfree; i += 4) {
+            uint2 c[4]; uint32_t v[4];
 #pragma unroll
-                for (uint32_t t = 0; t < 16; t++) v[t] = k0 + t < len ? (uint32_t)__ldcg(gs + k0 + t) : 0u;
+            for (uint32_t u = 0; u < 4; u++) c[u] = fq[i + u];
 #pragma unroll
-                for (uint32_t t = 0; t < 16; t++)
-                    if (k0 + t < len) { const uint32_t di = RWRAP(d0 + k0 + t); ring[di] = (uint8_t)v[t]; }
+            for (uint32_t u = 0; u < 4; u++) {
+                const uint32_t mdist = c[u].y >> 16;
+                v[u] = mdist ? ring[((c[u].y & 0xFFFFu) + lane) & kSegMask] : (c[u].y & 0xFFFFu) - lane;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+                const uint32_t mlen = c[u].x >> 16;
+                if (i + u < nfree && lane < mlen) ring[((c[u].x & 0xFFFFu) + lane) & kSegMask] = (uint16_t)v[u];
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+                const uint32_t mlen = c[u].x >> 16;
+                if (i + u < nfree && mlen > 32) {                     // (uniform) the rest of a long one
+                    const uint32_t mdist = c[u].y >> 16, md = c[u].x & 0xFFFFu, ms = c[u].y & 0xFFFFu;
+                    for (uint32_t k = 32 + lane; k < mlen; k += 32) ring[(md + k) & kSegMask] = mdist ? ring[(ms + k) & kSegMask] : (uint16_t)(ms - k);
+                }
             }
         }
-        // remaining matches in token order; every copy is spread over the 32 lanes (sorted text makes most matches depend on
-        // the bytes written just before them, so resolving them independently buys nothing).  Each lane packs the parameters of
-        // its own match once; the loop only shuffles them (the next match's while the current one is being copied).
-        const uint32_t p1 = d0 | (len << 16);                                           // ring index of the first output byte | length
-        const bool inorder = ok && !is_far;
-        const uint32_t p2 = (inorder ? RBACK(d0, dist) : 0u) | (dist << 16);            // ring index of the first source byte | distance
-        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, inorder);
-        const uint32_t nm = __popc(mmask);
-#if B2F_RESOLVE_FREE_FIRST
-        // Three of four matches of titles-shaped text (tools/analysis_resolve_steps.py: 12.2 of 16.3 per step) read only bytes
-        // from before the step (dist >= off + len): their sources are final, so they need no ordering among themselves and no
-        // barrier between them -- the copies of successive matches overlap.  Only the others (4.2 per step) run in token order.
-        const bool isfree = inorder && dist >= off + len;
-        const uint32_t fmask = __ballot_sync(0xFFFFFFFFu, isfree), dmask = mmask & ~fmask;
-        const uint32_t nf = __popc(fmask);
-        const uint32_t lt = (1u << lane) - 1u;
-        if (inorder) r_sts64(qb + 8u * (isfree ? (uint32_t)__popc(fmask & lt) : nf + (uint32_t)__popc(dmask & lt)), p1, p2);
         __syncwarp();
-        for (uint32_t i = 0; i < nf; i++) {
-            const uint2 c = r_lds64(qb + 8u * i);
-            const uint32_t mlen = c.x >> 16;
-            const uint32_t md = (c.x & 0xFFFFu) + lane, ms = (c.y & 0xFFFFu) + lane;
-            for (uint32_t k0 = 0; k0 < mlen; k0 += 32) r_copy8_if(k0 + lane < mlen, rb + RWRAP(ms + k0), rb + RWRAP(md + k0));
-        }
-        __syncwarp();
-        const uint32_t i_first = nf;
-#else
-        if (inorder) r_sts64(qb + 8u * __popc(mmask & ((1u << lane) - 1u)), p1, p2);   // compacted, in token order
-        __syncwarp();
-        const uint32_t i_first = 0;
-#endif
-        uint2 nx = r_lds64(qb + 8u * i_first), nx2 = r_lds64(qb + 8u * (i_first + 1u));
-        for (uint32_t i = i_first; i < nm; i++) {
+        // ---- copies that read bytes produced in this step, in token order, each spread over the lanes
+        uint2 nx = oq[0];
+        for (uint32_t i = 0; i < nord; i++) {
             const uint2 c = nx;
-            nx = nx2;
-            nx2 = r_lds64(qb + 8u * (i + 2));                       // parameters two matches ahead (slots >= nm are read but never used)
-            const uint32_t mlen = c.x >> 16, mdist = c.y >> 16;
-            const uint32_t md = (c.x & 0xFFFFu) + lane, ms = (c.y & 0xFFFFu) + lane;    // this lane's byte of the first 32-byte slice
-            if (mdist >= mlen && mlen <= 32) {                      // the common case: one slice, source entirely older than the output
-                r_sts8(lane < mlen ? rb + RWRAP(md) : dummy, r_lds8(rb + RWRAP(ms)));   // idle lanes store into their dummy byte: no branch
-            } else if (mdist >= 32) {                               // each 32-byte slice only reads bytes of earlier slices
+            nx = oq[i + 1];
+            const uint32_t mlen = c.x >> 16, mdist = c.y >> 16, md = c.x & 0xFFFFu, ms = c.y & 0xFFFFu;
+            if (mdist >= mlen && mlen <= 32) {
+                const uint16_t v = ring[(ms + lane) & kSegMask];
+                if (lane < mlen) ring[(md + lane) & kSegMask] = v;
+            } else if (mdist >= 32) {                                 // every 32-symbol slice reads only earlier slices
                 for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
-                    r_copy8_if(k0 + lane < mlen, rb + RWRAP(ms + k0), rb + RWRAP(md + k0));
+                    const uint16_t v = ring[(ms + k0 + lane) & kSegMask];
+                    if (k0 + lane < mlen) ring[(md + k0 + lane) & kSegMask] = v;
                     __syncwarp();
                 }
-            } else {                                                // short period: byte k repeats byte k mod dist of the source
-                const uint32_t inv = kInvPeriod[mdist];
-                for (uint32_t k = lane; k < mlen; k += 32) {
-                    const uint32_t r = k - mdist * ((k * inv) >> 16);
-                    r_sts8(rb + RWRAP(md - lane + k), r_lds8(rb + RWRAP(ms - lane + r)));
-                }
+            } else {                                                  // short period: symbol k repeats symbol k mod dist of the source
+                for (uint32_t k = lane; k < mlen; k += 32) ring[(md + k) & kSegMask] = ring[(ms + k % mdist) & kSegMask];
             }
             __syncwarp();
         }
-        // write the step through to HBM
-        const uint64_t new_end = pos + total;
-        if (words) {
-            const uint64_t fe = new_end - ((new_end + galign) & 3u);        // last word boundary at or below new_end
-            if (fe > flushed) {
-                const uint32_t nw = (uint32_t)(fe - flushed) >> 2;
-                const uint32_t r0 = RBACK(rpos, (uint32_t)(pos - flushed));  // pos - flushed <= 3
-                uint32_t *gw = reinterpret_cast<uint32_t *>(g + flushed);
-                for (uint32_t k = lane; k < nw; k += 32) gw[k] = *reinterpret_cast<const uint32_t *>(ring + RWRAP(r0 + 4 * k));
-                flushed = fe;
+        // ---- write the finished 8-symbol groups through to sym16 (16-byte stores)
+        pos += total;
+        if (pos >= lead) {
+            if (flushed < lead) {                                     // the unaligned head, once
+                if (lane < lead) gsym[lane] = ring[(a0 + lane) & kSegMask];
+                flushed = lead;
             }
-        } else {
-            for (uint32_t k = lane; k < total; k += 32) g[pos + k] = ring[RFWD(k)];
-            if (new_end - out0 >= 8) { words = true; flushed = new_end - ((new_end + galign) & 3u); }
+            const uint32_t target = pos - ((pos - lead) & 7u);        // last group boundary at or below pos
+            if (target > flushed) {
+                const uint32_t ng = (target - flushed) >> 3;
+                for (uint32_t g = lane; g < ng; g += 32)
+                    *reinterpret_cast<uint4 *>(gsym + flushed + 8u * g) = *reinterpret_cast<const uint4 *>(ring + ((a0 + flushed + 8u * g) & kSegMask));
+                flushed = target;
+            }
         }
-        pos = new_end;
-        rpos = RFWD(total);
+        i0 += take;
         __syncwarp();
     }
-    if (words) {                                                 // the bytes after the last whole word
-        const uint32_t nt = (uint32_t)(pos - flushed), r0 = RBACK(rpos, nt);
-        if (lane < nt) g[flushed + lane] = ring[RWRAP(r0 + lane)];
-    }
-    #undef RFWD
-    #undef RBACK
-    #undef RWRAP
+    for (uint32_t k = flushed + lane; k < pos; k += 32) gsym[k] = ring[(a0 + k) & kSegMask];    // the tail
+    if (pos != nout) err |= 1u;
     err = __reduce_or_sync(0xFFFFFFFFu, err);
-    if (lane == 0) { S.res_err[u] = err; S.res_len[u] = pos - out0; }
+    reach = __reduce_max_sync(0xFFFFFFFFu, reach);
+    if (lane == 0) { S.seg_reach[slot] = reach; if (err) atomicOr(S.mem_err + mem, err); }
+}
+
+// seg_cut[c] = 1 when no segment at or after c reads a byte before c's first one (only segments that start less than 32 KiB
+// after it can).  A member's first segment is a cut by construction (a reach before it is an error, flagged by k_seg_resolve).
+__global__ void __launch_bounds__(128) k_seg_cuts(SpecDev S) {
+    const uint32_t c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= S.n_slots || !S.seg_nout[c]) return;
+    const uint64_t A = S.seg_out[c];
+    const uint32_t m = S.seg_member[c];
+    bool cut = true;
+    for (uint32_t s = c; s < S.n_slots && S.seg_member[s] == m; s++) {
+        if (!S.seg_nout[s]) continue;
+        const uint64_t o = S.seg_out[s];
+        if (o >= A + 32768u) break;
+        if ((uint64_t)S.seg_reach[s] > o - A) { cut = false; break; }
+    }
+    S.seg_cut[c] = cut ? 1 : 0;
+}
+
+// One CTA per chain (the slots from a cut up to the next cut of the same member).  The last kSubRing final bytes of the chain are
+// kept in shared memory at index (offset - base) mod kSubRing, base = chain start rounded down to 16, so that aligned 16-byte
+// groups of out are aligned groups of the window.
+constexpr uint32_t kSubThreads = 256, kSubRing = 49152, kSubBatch = 16384;
+__global__ void __launch_bounds__(kSubThreads) k_seg_subst(SpecDev S, uint32_t slot_off) {
+    extern __shared__ __align__(16) uint8_t win[];
+    const uint32_t c = blockIdx.x + slot_off, tid = threadIdx.x;
+    if (!S.seg_nout[c] || !S.seg_cut[c]) return;
+    const uint32_t m = S.seg_member[c];
+    if (S.mem_err[m]) return;                                         // the member goes to the in-order kernel: markers may point anywhere
+    uint8_t *out = S.out;                                             // read back by later segments of the chain: no __restrict__
+    const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    uint32_t rA = (uint32_t)S.seg_out[c] & 15u;                       // window index of the current segment's first byte
+    for (uint32_t s = c; s < S.n_slots; s++) {
+        const uint32_t n = S.seg_nout[s];
+        if (!n) continue;
+        if (s != c && (S.seg_cut[s] || S.seg_member[s] != m)) break;
+        const uint64_t A = S.seg_out[s];
+        const uint16_t *__restrict__ sym = S.sym16;
+        for (uint32_t b0 = 0; b0 < n; b0 += kSubBatch) {              // (segments longer than a batch: highly compressible data)
+            const uint32_t bl = min(kSubBatch, n - b0);
+            const uint64_t B = A + b0;
+            uint32_t rB = rA + b0; rB -= (rB / kSubRing) * kSubRing;   // window index of the batch's first byte
+            // marker value mm (distance before A, minus 1) is still in the window iff A-1-mm >= B+bl-kSubRing
+            const int32_t thr = (int32_t)kSubRing - 1 - (int32_t)b0 - (int32_t)bl;
+            const uint64_t g0 = B & ~15ull;
+            const uint32_t ng = (uint32_t)((B + bl + 15 - g0) >> 4);
+            for (uint32_t g = tid; g < ng; g += kSubThreads) {
+                const uint64_t p = g0 + 16ull * g;                    // offset in out of this 16-byte group
+                uint32_t rp = rB + (uint32_t)(16u * g) + kSubRing - (uint32_t)(B - g0);   // window index of p (+ kSubRing: p may lie below B)
+                rp -= (rp / kSubRing) * kSubRing;
+                const bool full = vec && p >= B && p + 16 <= B + bl;
+                if (full) {
+                    const uint4 x = *reinterpret_cast<const uint4 *>(sym + p), y = *reinterpret_cast<const uint4 *>(sym + p + 8);
+                    const uint32_t w[8] = { x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w };
+                    uint32_t o[4] = { 0, 0, 0, 0 };
+#pragma unroll
+                    for (uint32_t q = 0; q < 16; q++) {
+                        uint32_t v = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+                        if (v & kMarker) {
+                            const int32_t mm = (int32_t)(v & 0x7FFFu);
+                            if (mm <= thr) { int32_t r = (int32_t)rA - 1 - mm; if (r < 0) r += (int32_t)kSubRing; v = win[r]; }
+                            else v = out[A - 1 - (uint64_t)mm];
+                        }
+                        o[q >> 2] |= v << (8u * (q & 3u));
+                    }
+                    const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4 *>(out + p) = ov;
+                    *reinterpret_cast<uint4 *>(win + rp) = ov;
+                } else {
+                    for (uint32_t q = 0; q < 16; q++) {
+                        const uint64_t pp = p + q;
+                        if (pp < B || pp >= B + bl) continue;
+                        uint32_t v = sym[pp];
+                        if (v & kMarker) {
+                            const int32_t mm = (int32_t)(v & 0x7FFFu);
+                            if (mm <= thr) { int32_t r = (int32_t)rA - 1 - mm; if (r < 0) r += (int32_t)kSubRing; v = win[r]; }
+                            else v = out[A - 1 - (uint64_t)mm];
+                        }
+                        out[pp] = (uint8_t)v;
+                        uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing;
+                        win[r] = (uint8_t)v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        rA += n - (n / kSubRing) * kSubRing; if (rA >= kSubRing) rA -= kSubRing;
+    }
 }
 
 // ---------------------------------------------------------------------------------- launchers
 cudaError_t spec_init_attributes() {
     cudaError_t e = cudaFuncSetAttribute(k_spec_headers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(InflateTables)));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_spec_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmem);
+    e = cudaFuncSetAttribute(k_seg_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_seg_subst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubRing);
 }
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st) {
     if (!S.n_blocks) return cudaSuccess;
@@ -559,15 +603,18 @@ cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st
     k_spec_tokens<<<S.n_ctas, kSpecCta, 0, st>>>(S);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_units(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
-    if (!n_sel) return cudaSuccess;
-    k_spec_units<<<n_sel, 32, 0, st>>>(S);
+cudaError_t spec_launch_segments(const SpecDev &S, cudaStream_t st) {
+    if (!S.n_slots) return cudaSuccess;
+    k_seg_plan<<<(S.n_slots + 127) / 128, 128, 0, st>>>(S);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_seg_resolve<<<S.n_slots, 32, kSegSmem, st>>>(S);
+    e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_seg_cuts<<<(S.n_slots + 127) / 128, 128, 0, st>>>(S);
     return cudaGetLastError();
 }
-// resolves the unit slots [u0, u1)
-cudaError_t spec_launch_resolve(const SpecDev &S, uint32_t u0, uint32_t u1, cudaStream_t st) {
-    if (u1 <= u0) return cudaSuccess;
-    k_spec_resolve<<<u1 - u0, 32, kResSmem, st>>>(S, u0);
+cudaError_t spec_launch_subst(const SpecDev &S, uint32_t s0, uint32_t s1, cudaStream_t st) {
+    if (s1 <= s0) return cudaSuccess;
+    k_seg_subst<<<s1 - s0, kSubThreads, kSubRing, st>>>(S, s0);
     return cudaGetLastError();
 }
 

@@ -277,10 +277,12 @@ def test_decode_large_streams_block_parallel_path(ctx):
     before = ctx.stats()
     res = ctx.decode_batch(0, [cases[k] for k in names], caps=[len(plain[k]) + 64 for k in names])
     after = ctx.stats()
-    # the four compressible libflate-style streams must really take the parallel path; incompressible data (fixed-width
-    # codes never self-synchronise), foreign streams with cross-block references, fixed and stored blocks fall back
-    assert after["decode_parallel_streams"] - before["decode_parallel_streams"] == 4, (before, after)
-    assert after["decode_inorder_streams"] - before["decode_inorder_streams"] == 5
+    # the four compressible libflate-style streams and the zlib-6 stream (dynamic blocks with cross-block references: markers)
+    # must really take the parallel path; incompressible data (fixed-width codes never self-synchronise), fixed and stored
+    # blocks fall back to the in-order kernel
+    npar = after["decode_parallel_streams"] - before["decode_parallel_streams"]
+    assert 5 <= npar <= 6, (before, after)
+    assert after["decode_inorder_streams"] - before["decode_inorder_streams"] == 9 - npar
     for k, (st, out, used, _) in zip(names, res):
         assert st == 0, k
         assert out == plain[k], (k, len(out), len(plain[k]), next((i for i in range(min(len(out), len(plain[k]))) if out[i] != plain[k][i]), -1))
@@ -293,6 +295,61 @@ def test_decode_large_streams_block_parallel_path(ctx):
     # too-small output for a large stream
     st, out, _, need = ctx.decode(0, cases["text_A"], cap=1 << 20)
     assert st == -3 and out == text[: 1 << 20] and need == len(text)
+
+
+def test_decode_foreign_streams_take_the_parallel_path(ctx):
+    """zlib / gzip output has cross-block back-references (the reference's own decode benchmark inflates flate2's output,
+    flate_bench/src/main.rs:49-55): blocks are found and parsed speculatively like libflate's, references that reach before a
+    segment become markers and are substituted in stream order (k_seg_resolve / k_seg_subst)."""
+    from libflate_b200 import titles
+    text = titles.generate(12 << 20, seed=5).tobytes()
+    rng = random.Random(43)
+    blockrep = bytes(rng.getrandbits(8) for _ in range(20000)) * 300             # period 20000: every match is long and far
+    for name, plain, enc, fmt in (
+            ("zlib6", text, pyzlib.compress(text, 6), 1), ("zlib9", text, pyzlib.compress(text, 9), 1),
+            ("zlib1", text, pyzlib.compress(text, 1), 1), ("gzip6", text, pygzip.compress(text, 6, mtime=0), 2),
+            ("raw6_blockrep", blockrep, pyzlib.compress(blockrep, 6)[2:-4], 0),
+            ("raw6_zeros", b"\x00" * (40 << 20), pyzlib.compress(b"\x00" * (40 << 20), 6)[2:-4], 0)):
+        before = ctx.stats()
+        st, out, used, _ = ctx.decode(fmt, enc, cap=len(plain) + 64)
+        after = ctx.stats()
+        assert st == 0 and used == len(enc), (name, st, used, len(enc))
+        assert out == plain, (name, len(out), next((i for i in range(min(len(out), len(plain))) if out[i] != plain[i]), -1))
+        if len(enc) >= 128 * 1024 and name != "raw6_zeros":
+            assert after["decode_parallel_streams"] - before["decode_parallel_streams"] == 1, name
+
+
+def test_decode_truncated_and_corrupt_large_streams(ctx):
+    """truncation / bit flips in streams >= 128 KiB compressed (the speculative path): status, partial output and consumed bytes
+    must equal the oracle's, also right after the intact stream was decoded on the same context (stale device memory)"""
+    rng = random.Random(44)
+    text = _text(rng, 3 << 20, nwords=4000)
+    enc = orc.encode(0, text, [8192] * (len(text) // 8192 + 1))
+    assert len(enc) >= 256 * 1024
+    st, out, used, _ = ctx.decode(0, enc, cap=len(text) + 64)
+    assert st == 0 and out == text and used == len(enc)
+    variants = [enc[:-1], enc[:-2], enc[:-3], enc[:-14], enc[: len(enc) // 2 + 1], enc[: 200 * 1024]]
+    for _ in range(6):
+        b = bytearray(enc); i = rng.randrange(len(b)); b[i] ^= 1 << rng.randrange(8); variants.append(bytes(b))
+    for k, v in enumerate(variants):
+        st, out, used, _ = ctx.decode(0, v, cap=len(text) + 64)
+        rc, want, wused, msg = orc.decode(0, v, cap=len(text) + 64)
+        assert st == rc, (k, st, rc, msg)
+        assert out == want, (k, len(out), len(want), msg)
+        if rc == 0:
+            assert used == wused, k
+
+
+def test_decode_multi_member_gzip_with_large_members(ctx):
+    rng = random.Random(45)
+    parts = [_text(rng, n, nwords=3000) for n in (1 << 20, 700000, 5000, 1500000)]
+    members = [orc.encode(2, parts[0], [8192] * 200, mtime=1), pygzip.compress(parts[1], 6, mtime=2), orc.encode(2, parts[2], mtime=3),
+               pygzip.compress(parts[3], 9, mtime=4)]
+    blob = b"".join(members)
+    st, out, used, _ = ctx.decode(3, blob, cap=sum(map(len, parts)) + 64)
+    assert st == 0 and out == b"".join(parts) and used == len(blob)
+    st, out, used, _ = ctx.decode(2, blob, cap=sum(map(len, parts)) + 64)          # gzip::Decoder: first member only
+    assert st == 0 and out == parts[0] and used == len(members[0])
 
 
 def test_decode_output_too_small(ctx):

@@ -77,6 +77,17 @@ void b2f_ctx_destroy(b2f_ctx *ctx);
 const char *b2f_last_error(const b2f_ctx *ctx);  /* valid until the next call on ctx */
 const char *b2f_version(void);
 
+/* ---- host memory ---------------------------------------------------------------------------
+ * Every batch call accepts ORDINARY (pageable) host memory: the library stages the payload through its own page-locked buffers
+ * (three 8 MiB buffers per direction, a few copy threads -- B2F_COPY_THREADS, default 4), overlapping the staging copies with the
+ * DMA transfers and the kernels.  A caller that can allocate its buffers here (or register existing ones) saves that copy: the DMA
+ * engines then read and write the caller's memory in place.  This is the reference's `Vec<u8>` / `W: Write` boundary
+ * (src/deflate/encode.rs:241-249, src/deflate/decode.rs:136-164) -- no CUDA type crosses it. */
+int b2f_host_alloc(size_t bytes, void **out);          /* page-locked, usable from any context/device */
+void b2f_host_free(void *p);
+int b2f_host_register(void *p, size_t bytes);          /* pin an existing allocation in place (page granular; costly: do it once) */
+int b2f_host_unregister(void *p);
+
 /* ---- E1: segmentation plan (pure host arithmetic) ----------------------------------------
  * Replaces the bookkeeping of Block::write / CompressBuf::append (src/deflate/encode.rs:277-286,
  * 405-425) and DefaultLz77Encoder::encode (libflate_lz77/src/default.rs:60-68): given the
@@ -115,6 +126,9 @@ size_t b2f_encode_bound(size_t in_len, size_t n_sched, const b2f_encode_opts *op
  * out_len[s]   = bytes decoded; on error, the bytes decoded before the error (what read_to_end
  *               returned plus Decoder::unread_decoded_data()).
  * in_consumed[s] = bytes pulled from the underlying reader (the decoder never reads past its stream).
+ * Device-resident inputs (b2f_decode_device): the sub-block decoder fetches aligned 32-bit words, so up to 3 bytes after
+ * in_off[s] + in_len[s] may be READ (never interpreted: a block that would end past the stream is rejected); keep d_in at
+ * least 4 bytes longer than the last stream.
  * status[s]    = B2F_OK / B2F_ERR_INVALID_DATA / B2F_ERR_UNEXPECTED_EOF / B2F_ERR_OUTPUT_TOO_SMALL. */
 int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams,
                      const uint8_t *const *in, const size_t *in_len,
@@ -167,6 +181,8 @@ typedef struct b2f_stats {
     float last_device_ms;         /* whole device section of the last call */
     uint64_t decode_parallel_streams;  /* DEFLATE streams decoded by the block/sub-block parallel path since ctx creation */
     uint64_t decode_inorder_streams;   /* streams decoded by the in-order kernel (small, irregular or erroneous streams)  */
+    uint64_t staged_h2d_bytes;         /* payload bytes that went through the internal pinned staging (pageable caller memory) */
+    uint64_t staged_d2h_bytes;
 } b2f_stats;
 int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out);
 const char *b2f_stage_name(b2f_ctx *ctx, uint32_t stage);   /* name of stage i of the last call */

@@ -28,7 +28,8 @@ class EncodeOpts(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("last_kernel_ms", C.c_float * 16), ("last_n_stages", C.c_uint32),
-                ("last_device_ms", C.c_float), ("decode_parallel_streams", C.c_uint64), ("decode_inorder_streams", C.c_uint64)]
+                ("last_device_ms", C.c_float), ("decode_parallel_streams", C.c_uint64), ("decode_inorder_streams", C.c_uint64),
+                ("staged_h2d_bytes", C.c_uint64), ("staged_d2h_bytes", C.c_uint64)]
 
 
 EXPORTS = [
@@ -38,6 +39,7 @@ EXPORTS = [
     "b2f_encoder_new", "b2f_encoder_write", "b2f_encoder_flush", "b2f_encoder_finish", "b2f_encoder_free",
     "b2f_decoder_new", "b2f_decoder_read", "b2f_decoder_unread", "b2f_decoder_consumed", "b2f_decoder_free",
     "b2f_get_stats", "b2f_stage_name", "b2f_ctx_stream", "b2f_ctx_set_overlap",
+    "b2f_host_alloc", "b2f_host_free", "b2f_host_register", "b2f_host_unregister",
 ]
 
 _lib = None
@@ -89,6 +91,10 @@ def lib():
         L.b2f_ctx_stream.restype = vp
         L.b2f_ctx_stream.argtypes = [vp]
         L.b2f_ctx_set_overlap.argtypes = [vp, C.c_int]
+        L.b2f_host_alloc.argtypes = [sz, C.POINTER(vp)]
+        L.b2f_host_free.argtypes = [vp]
+        L.b2f_host_register.argtypes = [vp, sz]
+        L.b2f_host_unregister.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -298,7 +304,22 @@ class Context:
         lib().b2f_get_stats(self._h, C.byref(s))
         stages = [((lib().b2f_stage_name(self._h, i) or b"").decode(), s.last_kernel_ms[i]) for i in range(s.last_n_stages)]
         return {"kernel_launches": s.kernel_launches, "stages": stages, "device_ms": s.last_device_ms,
-                "decode_parallel_streams": s.decode_parallel_streams, "decode_inorder_streams": s.decode_inorder_streams}
+                "decode_parallel_streams": s.decode_parallel_streams, "decode_inorder_streams": s.decode_inorder_streams,
+                "staged_h2d_bytes": s.staged_h2d_bytes, "staged_d2h_bytes": s.staged_d2h_bytes}
+
+
+def host_alloc(nbytes):
+    """page-locked numpy uint8 buffer from b2f_host_alloc (the DMA engines use it in place); free with host_free(arr)"""
+    p = C.c_void_p()
+    rc = lib().b2f_host_alloc(nbytes, C.byref(p))
+    if rc != OK:
+        raise B2fError(rc, "b2f_host_alloc")
+    arr = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(p.value))[:nbytes]
+    return arr
+
+
+def host_free(arr):
+    lib().b2f_host_free(C.c_void_p(arr.ctypes.data))
 
 
 def plan_from_writes(sched, in_len, block_size=1 << 20, window=32768):

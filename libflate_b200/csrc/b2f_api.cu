@@ -10,6 +10,11 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "../../include/b2f.h"
 #include "common.cuh"
@@ -53,6 +58,63 @@ struct PinBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// ------------------------------------------------------------------------------------------ host staging
+// The ABI takes ordinary (pageable) caller memory ("pinned-memory registration is internal").  A cudaMemcpyAsync from
+// or to pageable memory is staged by the driver through one small buffer at ~11 GB/s and blocks the calling thread, so the library
+// does the staging itself: the payload moves in kStageChunk pieces through three page-locked buffers per direction; a small pool of
+// worker threads copies between caller memory and the staging buffer while the DMA engine moves the previous piece and the kernels
+// of earlier pieces run.  Buffers that are already page-locked (b2f_host_alloc / b2f_host_register / cudaHostAlloc) are used in place.
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex mu; std::condition_variable cv_work, cv_done;
+    uint8_t *dst = nullptr; const uint8_t *src = nullptr; size_t n = 0, piece = 0;
+    std::atomic<size_t> next{0};
+    size_t pending = 0; uint64_t gen = 0; bool stop = false;
+    void start(unsigned nthreads) {
+        for (unsigned i = 0; i + 1 < nthreads; i++) th.emplace_back([this] { run(); });   // the calling thread is the last worker
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> lk(mu); cv_work.wait(lk, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; }
+            work();
+            { std::lock_guard<std::mutex> lk(mu); if (--pending == 0) cv_done.notify_all(); }
+        }
+    }
+    void work() {
+        for (;;) {
+            const size_t o = next.fetch_add(piece);
+            if (o >= n) return;
+            memcpy(dst + o, src + o, std::min(piece, n - o));
+        }
+    }
+    void copy(void *d, const void *s_, size_t bytes) {
+        if (th.empty() || bytes < (1u << 20)) { memcpy(d, s_, bytes); return; }
+        { std::lock_guard<std::mutex> lk(mu); dst = (uint8_t *)d; src = (const uint8_t *)s_; n = bytes; piece = 256u << 10; next = 0; pending = th.size(); gen++; }
+        cv_work.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+};
+constexpr size_t kStageChunk = 8u << 20;
+struct Stager {
+    PinBuf buf[3]; cudaEvent_t ev[3] = { nullptr, nullptr, nullptr }; bool busy[3] = { false, false, false };
+    cudaError_t init() {
+        for (int i = 0; i < 3; i++) {
+            cudaError_t e = buf[i].ensure(kStageChunk); if (e != cudaSuccess) return e;
+            if (!ev[i]) { e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        }
+        return cudaSuccess;
+    }
+    void release() { for (int i = 0; i < 3; i++) { buf[i].release(); if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; busy[i] = false; } }
+};
+
 enum { NB_IN, NB_LINK, NB_MD, NB_SYM, NB_EXIT, NB_TILE, NB_BLK, NB_DESC, NB_OUT, NB_MISC, NB_CK, NB_DEC_META, NB_DEC_OUT, NB_DEC_CAND, NB_DEC_BLK, NB_DEC_SER, NB_SPEC_TAB, NB_SPEC_SEG, NB_SPEC_TOK, NB_SPEC_SEL, NB_SPEC_SYM, NB_COUNT };
 
 struct b2f_ctx {
@@ -69,6 +131,8 @@ struct b2f_ctx {
     cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t aux_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     int overlap = 1;               // run independent chunk slices of the LZ77 stage on separate streams
+    CopyPool pool; Stager st_in, st_out; unsigned copy_threads = 4; size_t stage_rr = 0;
+    uint64_t staged_h2d = 0, staged_d2h = 0;     // bytes that went through the internal staging (pageable caller memory)
 };
 
 static thread_local std::string g_create_err;
@@ -77,7 +141,68 @@ static thread_local std::string g_create_err;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-extern "C" const char *b2f_version(void) { return "libb2f 0.1 (sm_100a)"; }
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes pa;
+    const bool pinned = p && cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+// host -> device, stream ordered.  Pinned source: one DMA.  Pageable source: staged (the calling thread and the pool copy piece k+1
+// into a staging buffer while the DMA of piece k and everything queued before it run).
+static cudaError_t h2d_copy(b2f_ctx *ctx, uint8_t *d_dst, const uint8_t *h_src, size_t n, cudaStream_t st, bool pinned) {
+    if (!n) return cudaSuccess;
+    if (pinned) return cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, st);
+    Stager &S = ctx->st_in;
+    cudaError_t e = S.init(); if (e != cudaSuccess) return e;
+    for (size_t o = 0; o < n; o += kStageChunk) {
+        const size_t len = std::min(kStageChunk, n - o);
+        const size_t k = ctx->stage_rr++ % 3;
+        if (S.busy[k]) { e = cudaEventSynchronize(S.ev[k]); if (e != cudaSuccess) return e; }
+        ctx->pool.copy(S.buf[k].p, h_src + o, len);
+        e = cudaMemcpyAsync(d_dst + o, S.buf[k].p, len, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e;
+        e = cudaEventRecord(S.ev[k], st); if (e != cudaSuccess) return e;
+        S.busy[k] = true;
+    }
+    ctx->staged_h2d += n;
+    return cudaSuccess;
+}
+// device -> host.  The source must be complete in stream order on `st`.  Returns when the bytes are in h_dst (pageable) or queued (pinned).
+static cudaError_t d2h_copy(b2f_ctx *ctx, uint8_t *h_dst, const uint8_t *d_src, size_t n, cudaStream_t st, bool pinned) {
+    if (!n) return cudaSuccess;
+    if (pinned) return cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, st);
+    Stager &S = ctx->st_out;
+    cudaError_t e = S.init(); if (e != cudaSuccess) return e;
+    const size_t nchunks = (n + kStageChunk - 1) / kStageChunk;
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t o = c * kStageChunk, len = std::min(kStageChunk, n - o);
+        cudaError_t e2 = cudaMemcpyAsync(S.buf[c % 3].p, d_src + o, len, cudaMemcpyDeviceToHost, st); if (e2 != cudaSuccess) return e2;
+        return cudaEventRecord(S.ev[c % 3], st);
+    };
+    for (size_t c = 0; c < std::min<size_t>(2, nchunks); c++) { e = issue(c); if (e != cudaSuccess) return e; }
+    for (size_t c = 0; c < nchunks; c++) {
+        if (c + 2 < nchunks) { e = issue(c + 2); if (e != cudaSuccess) return e; }      // slot (c+2)%3 was drained by iteration c-1
+        e = cudaEventSynchronize(S.ev[c % 3]); if (e != cudaSuccess) return e;
+        const size_t o = c * kStageChunk, len = std::min(kStageChunk, n - o);
+        ctx->pool.copy(h_dst + o, S.buf[c % 3].p, len);
+    }
+    ctx->staged_d2h += n;
+    return cudaSuccess;
+}
+
+extern "C" const char *b2f_version(void) { return "libb2f 0.2 (sm_100a)"; }
+
+// ---- page-locked host memory for callers that want the DMA engines to read/write their buffers in place
+extern "C" int b2f_host_alloc(size_t bytes, void **out) {
+    if (!out) return B2F_ERR_INVALID_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) == cudaSuccess ? B2F_OK : B2F_ERR_NOMEM;
+}
+extern "C" void b2f_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int b2f_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return B2F_ERR_INVALID_ARG;
+    return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? B2F_OK : B2F_ERR_CUDA;
+}
+extern "C" int b2f_host_unregister(void *p) { return (p && cudaHostUnregister(p) == cudaSuccess) ? B2F_OK : B2F_ERR_INVALID_ARG; }
 
 extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     if (!out) return B2F_ERR_INVALID_ARG;
@@ -101,6 +226,9 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
     for (auto &ev : ctx->aux_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (const char *o = getenv("B2F_OVERLAP")) ctx->overlap = atoi(o);
+    if (const char *o = getenv("B2F_COPY_THREADS")) ctx->copy_threads = (unsigned)std::max(1, atoi(o));
+    ctx->copy_threads = std::min(ctx->copy_threads, std::max(1u, std::thread::hardware_concurrency()));
+    ctx->pool.start(ctx->copy_threads);
     *out = ctx;
     return B2F_OK;
 }
@@ -108,6 +236,8 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->pool.shutdown();
+    ctx->st_in.release(); ctx->st_out.release();
     for (auto &b : ctx->buf) b.release();
     ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release(); ctx->pin_cand.release(); ctx->pin_blk.release(); ctx->pin_ser.release(); ctx->pin_sel.release();
     ctx->tm.destroy();
@@ -119,7 +249,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
 extern "C" const char *b2f_last_error(const b2f_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 extern "C" int b2f_ctx_set_overlap(b2f_ctx *ctx, int on) { if (!ctx) return B2F_ERR_INVALID_ARG; ctx->overlap = on ? 1 : 0; return B2F_OK; }
 extern "C" void *b2f_ctx_stream(b2f_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-extern "C" int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out) { if (!ctx || !out) return B2F_ERR_INVALID_ARG; ctx->stats.decode_parallel_streams = ctx->n_spec_members; ctx->stats.decode_inorder_streams = ctx->n_inorder_members; *out = ctx->stats; return B2F_OK; }
+extern "C" int b2f_get_stats(b2f_ctx *ctx, b2f_stats *out) { if (!ctx || !out) return B2F_ERR_INVALID_ARG; ctx->stats.decode_parallel_streams = ctx->n_spec_members; ctx->stats.decode_inorder_streams = ctx->n_inorder_members; ctx->stats.staged_h2d_bytes = ctx->staged_h2d; ctx->stats.staged_d2h_bytes = ctx->staged_d2h; *out = ctx->stats; return B2F_OK; }
 extern "C" const char *b2f_stage_name(b2f_ctx *ctx, uint32_t i) { return (ctx && i < 16 && ctx->stage_names[i]) ? ctx->stage_names[i] : ""; }
 
 extern "C" void b2f_encode_opts_default(b2f_encode_opts *o) {
@@ -292,7 +422,7 @@ int checksum_batch_host(b2f_ctx *ctx, size_t n, const uint8_t *const *buf, const
     for (size_t s = 0; s < n; s++) { off[s] = total; ln[s] = len[s]; total += align_up(len[s], 16); }
     CK(ctx->buf[NB_IN].ensure(total + 256));
     uint8_t *d = ctx->buf[NB_IN].as<uint8_t>();
-    for (size_t s = 0; s < n; s++) if (len[s]) CK(cudaMemcpyAsync(d + off[s], buf[s], len[s], cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t s = 0; s < n; s++) if (len[s]) CK(h2d_copy(ctx, d + off[s], buf[s], len[s], ctx->stream, is_pinned_host(buf[s])));
     std::vector<uint32_t> crc, adler;
     int rc = run_checksums(ctx, d, off, ln, is_crc, !is_crc, init, crc, adler);
     if (rc) return rc;
@@ -388,6 +518,7 @@ struct EncodeJob {
     // device-resident inputs
     const uint8_t *d_in; std::vector<uint64_t> in_off; std::vector<uint64_t> in_len;
     const uint8_t *const *h_in = nullptr;     // when set, the inputs still live on the host: encode_on_device copies them slice by slice
+    std::vector<char> h_pinned;               // per stream: the host input is page-locked (DMA in place) or pageable (staged)
     // results
     std::vector<uint64_t> out_base; std::vector<uint64_t> out_len;   // in ctx->buf[NB_OUT]
 };
@@ -482,7 +613,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         const uint64_t lo = f->P->chunks[c0].off, hi = f->P->chunks[c1 - 1].off + f->P->chunks[c1 - 1].len;   // device byte range of the slice
         for (size_t s = 0; s < f->job->in_off.size(); s++) {     // streams are laid out in increasing in_off order
             const uint64_t a = std::max<uint64_t>(lo, f->job->in_off[s]), b = std::min<uint64_t>(hi, f->job->in_off[s] + f->job->in_len[s]);
-            if (a < b) { cudaError_t e = cudaMemcpyAsync(f->d_in + a, f->job->h_in[s] + (a - f->job->in_off[s]), b - a, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e; }
+            if (a < b) { cudaError_t e = h2d_copy(f->ctx, f->d_in + a, f->job->h_in[s] + (a - f->job->in_off[s]), b - a, st, f->job->h_pinned[s] != 0); if (e != cudaSuccess) return e; }
         }
         return cudaSuccess; } };
     bool sliced = false;
@@ -583,6 +714,8 @@ static size_t effective_len(const int64_t *sched, size_t n_sched, size_t in_len)
 static int validate_opts(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o) {
     if (fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP) { ctx->err = "bad format"; return B2F_ERR_INVALID_ARG; }
     if (o.block_size == 0 || o.window_size == 0 || o.max_length < 3 || o.mode < 0 || o.mode > 2) { ctx->err = "bad encode options"; return B2F_ERR_INVALID_ARG; }
+    // gzip::ExtraField::write_to fails with "extra field too long" beyond a 16-bit XLEN (src/gzip.rs:489-500)
+    if (o.gzip_has_extra && (o.gzip_extra_len > 0xFFFFu || (o.gzip_extra_len && !o.gzip_extra))) { ctx->err = "gzip extra field: NULL or longer than 65535 bytes"; return B2F_ERR_INVALID_ARG; }
     return B2F_OK;
 }
 
@@ -591,6 +724,7 @@ extern "C" int b2f_encode_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts *o
                                  const int64_t *const *sched, const size_t *n_sched,
                                  uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, int *status) {
     if (!ctx) return B2F_ERR_INVALID_ARG;
+    if (n_streams && (!d_in || !in_off || !in_len || !d_out || !out_off || !out_cap || !out_len || !status)) { ctx->err = "NULL argument"; return B2F_ERR_INVALID_ARG; }
     b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
     int rc = validate_opts(ctx, fmt, *opts); if (rc) return rc;
     if (opts->mode == B2F_MODE_STORED) { ctx->err = "stored mode has no device-resident variant (framing only)"; return B2F_ERR_INVALID_ARG; }
@@ -617,6 +751,7 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
                                 const int64_t *const *sched, const size_t *n_sched,
                                 uint8_t *const *out, const size_t *out_cap, size_t *out_len, int *status) {
     if (!ctx) return B2F_ERR_INVALID_ARG;
+    if (n_streams && (!in || !in_len || !out || !out_cap || !out_len || !status)) { ctx->err = "NULL argument"; return B2F_ERR_INVALID_ARG; }
     b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
     int rc = validate_opts(ctx, fmt, *opts); if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -634,7 +769,7 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
     job.d_in = d_in;
     if (opts->mode == B2F_MODE_STORED) {
         ctx->tm.mark(ctx->stream, "h2d");
-        for (size_t s = 0; s < n_streams; s++) if (job.in_len[s]) CK(cudaMemcpyAsync(d_in + job.in_off[s], in[s], job.in_len[s], cudaMemcpyHostToDevice, ctx->stream));
+        for (size_t s = 0; s < n_streams; s++) if (job.in_len[s]) CK(h2d_copy(ctx, d_in + job.in_off[s], in[s], job.in_len[s], ctx->stream, is_pinned_host(in[s])));
         std::vector<uint32_t> crc, adler;
         rc = run_checksums(ctx, d_in, job.in_off, job.in_len, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
         if (rc) return rc;
@@ -651,6 +786,8 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         return B2F_OK;
     }
     job.h_in = in;                         // the H2D copies are issued per slice inside the LZ77 stage
+    job.h_pinned.resize(n_streams);
+    for (size_t s = 0; s < n_streams; s++) job.h_pinned[s] = is_pinned_host(in[s]) ? 1 : 0;
     rc = encode_on_device(ctx, fmt, *opts, n_streams, sched, n_sched, job);
     if (rc) return rc;
     collect_stats(ctx, false);
@@ -658,7 +795,7 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         out_len[s] = (size_t)job.out_len[s];
         if (job.out_len[s] > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
         status[s] = B2F_OK;
-        CK(cudaMemcpyAsync(out[s], ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s], job.out_len[s], cudaMemcpyDeviceToHost, ctx->stream));
+        CK(d2h_copy(ctx, out[s], ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s], job.out_len[s], ctx->stream, is_pinned_host(out[s])));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return B2F_OK;
@@ -776,7 +913,8 @@ int parse_zlib_header(HostReader &r) {          // zlib::Header::read_from (zlib
 }
 int map_inf_status(int s) { return s == kInfOk ? B2F_OK : s == kInfInvalid ? B2F_ERR_INVALID_DATA : s == kInfEof ? B2F_ERR_UNEXPECTED_EOF : B2F_ERR_OUTPUT_TOO_SMALL; }
 
-struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_off; uint64_t out_cap; uint8_t *h_out; };   // h_out: pinned host destination of this member's output (or NULL)
+struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_off; uint64_t out_cap; uint8_t *h_out; bool h_pinned;      // h_out: host destination of this member's output (or NULL); h_pinned: page-locked
+                uint64_t scan_len; };   // bytes of def_len the block finder / speculative parse may look at (0: in-order kernel)
 
 // Packs several host arrays into one pinned staging area + one H2D copy; returns device pointers.
 struct Packer {
@@ -807,8 +945,10 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     const size_t n = mem.size();
     st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0); copied.assign(n, 0);
     if (!n) return B2F_OK;
-    std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_cap(n), out_end(n);
-    for (size_t i = 0; i < n; i++) { in_off[i] = mem[i].def_off; in_len[i] = mem[i].def_len; out_off[i] = mem[i].out_off; out_cap[i] = mem[i].out_cap; out_end[i] = mem[i].out_off + mem[i].out_cap; }
+    // in_len: what the speculative path may look at (the whole rest of the container for a first member, a window sized after the
+    // previous member for later members of a multi-member file); full_len: what the in-order kernel may read
+    std::vector<uint64_t> in_off(n), in_len(n), full_len(n), out_off(n), out_cap(n), out_end(n);
+    for (size_t i = 0; i < n; i++) { in_off[i] = mem[i].def_off; in_len[i] = std::min(mem[i].scan_len, mem[i].def_len); full_len[i] = mem[i].def_len; out_off[i] = mem[i].out_off; out_cap[i] = mem[i].out_cap; out_end[i] = mem[i].out_off + mem[i].out_cap; }
     std::vector<uint32_t> big;
     for (size_t i = 0; i < n; i++) if (in_len[i] >= kParallelMinBytes) big.push_back((uint32_t)i);
     std::vector<uint32_t> serial;                          // member indices for the in-order kernel
@@ -821,9 +961,9 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     uint64_t big_bytes = 0;
     for (size_t k = 0; k < big.size(); k++) { seg0[k + 1] = seg0[k] + (uint32_t)((in_len[big[k]] + 1023) / 1024); big_bytes += in_len[big[k]]; }
     const size_t a_sel = PA.add(big.data(), big.size() * 4), a_seg = PA.add(seg0.data(), seg0.size() * 4);
-    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(1u << 22, big_bytes / 512 + 4096);
+    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(1u << 24, big_bytes / 512 + 4096);
     const size_t a_cm = PA.reserve((size_t)cand_cap * 4), a_cb = PA.reserve((size_t)cand_cap * 8), a_cc = PA.reserve(64);
-    const uint32_t q_cap = (uint32_t)std::min<uint64_t>(1u << 24, big_bytes / 32 + 8192);      // ~0.1 % of bit offsets pass the cheap tests
+    const uint32_t q_cap = (uint32_t)std::min<uint64_t>(1u << 27, big_bytes / 32 + 8192);      // ~0.1 % of bit offsets pass the cheap tests
     const size_t a_qm = PA.reserve((size_t)q_cap * 4), a_qb = PA.reserve((size_t)q_cap * 8);
     CK(PA.commit(ctx->stream));
     std::vector<uint32_t> c_member; std::vector<uint64_t> c_bit;
@@ -1029,34 +1169,39 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 ctx->tm.mark(ctx->stream, "lz_resolve");
                 CK(spec_launch_segments(S, ctx->stream));
                 ctx->tm.mark(ctx->stream, "lz_subst");
-                // The substitution runs in parts over the slots; each part's output is copied to pinned host memory on a side stream
-                // while the next part runs.
+                // The substitution runs in parts over the slots.  All parts are launched first; then each part's output is copied to the
+                // caller's memory on a side stream (page-locked destination: one DMA per block; pageable: staged through the pinned
+                // buffers, the calling thread copying piece k out while piece k+1 arrives and the later parts still run).
                 {
                     uint64_t total_len = 0; for (size_t k = 0; k < nsel; k++) total_len += k_len[k];
                     bool any_host = false;
                     for (size_t k = 0; k < nsel; k++) if (mem[cands[sel_blocks[k]].first].h_out) { any_host = true; break; }
                     const uint32_t nparts = (any_host && total_len >= (64u << 20)) ? 4u : 1u;
-                    size_t b0 = 0; uint64_t acc = 0;
+                    size_t part_b[5] = { 0, 0, 0, 0, 0 }; uint64_t acc = 0;
                     for (uint32_t part = 0; part < nparts; part++) {
-                        size_t b1 = b0;
+                        size_t b1 = part_b[part];
                         const uint64_t want = total_len * (part + 1) / nparts;
                         while (b1 < nsel && (acc < want || part + 1 == nparts)) { acc += k_len[b1]; b1++; }
-                        CK(spec_launch_subst(S, slot0[b0], slot0[b1], ctx->stream));
+                        part_b[part + 1] = b1;
+                        // A chain that starts in this part may run on into later slots (foreign streams): the launch of the part where it
+                        // starts handles all of it, so after launch p every slot of parts <= p is final.
+                        CK(spec_launch_subst(S, slot0[part_b[part]], slot0[b1], ctx->stream));
                         ctx->stats.kernel_launches += 1;
-                        if (any_host) {
-                            // A chain that starts in this part may run on into the next one (foreign streams); the blocks of a part are
-                            // final only when every earlier part is: parts run in order on one stream, so the event covers them.  Blocks whose
-                            // chain started in an EARLIER part are complete too (that launch is before this event).  What may still be
-                            // open is the tail of a chain running into later blocks -- those belong to later parts and are copied there.
-                            CK(cudaEventRecord(ctx->aux_ev[part], ctx->stream));
+                        if (any_host) CK(cudaEventRecord(ctx->aux_ev[part], ctx->stream));
+                    }
+                    if (any_host) {
+                        for (uint32_t part = 0; part < nparts; part++) {
                             CK(cudaStreamWaitEvent(ctx->aux[0], ctx->aux_ev[part], 0));
-                            for (size_t k = b0; k < b1; k++) {
+                            for (size_t k = part_b[part]; k < part_b[part + 1];) {
+                                // consecutive blocks of one member are contiguous in out: one copy per run
                                 const uint32_t m = cands[sel_blocks[k]].first;
-                                if (mem[m].h_out && k_len[k])
-                                    CK(cudaMemcpyAsync(mem[m].h_out + (k_out[k] - out_off[m]), d_out + k_out[k], k_len[k], cudaMemcpyDeviceToHost, ctx->aux[0]));
+                                size_t k1 = k; uint64_t run = 0;
+                                while (k1 < part_b[part + 1] && cands[sel_blocks[k1]].first == m) { run += k_len[k1]; k1++; }
+                                if (mem[m].h_out && run)
+                                    CK(d2h_copy(ctx, mem[m].h_out + (k_out[k] - out_off[m]), d_out + k_out[k], run, ctx->aux[0], mem[m].h_pinned));
+                                k = k1;
                             }
                         }
-                        b0 = b1;
                     }
                     for (uint32_t m : big) if (is_par[m] && mem[m].h_out) copied[m] = 1;
                 }
@@ -1086,7 +1231,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     if (nser) {
         Packer PC(ctx->pin_blk, ctx->buf[NB_DEC_BLK]);
         std::vector<uint64_t> s_io(nser), s_il(nser), s_oo(nser), s_oc(nser);
-        for (size_t k = 0; k < nser; k++) { uint32_t m = serial[k]; s_io[k] = in_off[m]; s_il[k] = in_len[m]; s_oo[k] = out_off[m]; s_oc[k] = out_cap[m]; }
+        for (size_t k = 0; k < nser; k++) { uint32_t m = serial[k]; s_io[k] = in_off[m]; s_il[k] = full_len[m]; s_oo[k] = out_off[m]; s_oc[k] = out_cap[m]; }
         const size_t s_a = PC.add(s_io.data(), nser * 8), s_b = PC.add(s_il.data(), nser * 8), s_c = PC.add(s_oo.data(), nser * 8), s_d = PC.add(s_oc.data(), nser * 8);
         const size_t s_st = PC.reserve(nser * 4), s_ol = PC.reserve(nser * 8), s_cs = PC.reserve(nser * 8);
         CK(PC.commit(ctx->stream));
@@ -1154,10 +1299,11 @@ struct InputAccess {
 // Shared decode driver: container framing on the host (a few bytes per stream), DEFLATE + checksums on the device.
 int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const uint8_t *d_in, const uint64_t *in_off, const size_t *in_len,
                 uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status,
-                uint8_t *const *h_out = nullptr, std::vector<uint64_t> *h_copied = nullptr) {
+                uint8_t *const *h_out = nullptr, std::vector<uint64_t> *h_copied = nullptr, const std::vector<char> *h_pinned = nullptr) {
     std::vector<size_t> pos(n_streams, 0);            // reader position per stream
     std::vector<uint64_t> produced(n_streams, 0);
     std::vector<char> done(n_streams, 0);
+    std::vector<uint64_t> prev_comp(n_streams, 0);    // compressed size of the stream's previous member (MultiDecoder rounds)
     for (size_t s = 0; s < n_streams; s++) { status[s] = B2F_OK; out_len[s] = 0; in_consumed[s] = 0; }
     bool first = true;
     for (;;) {
@@ -1194,7 +1340,13 @@ int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const 
         for (size_t s : act) {
             if (done[s]) continue;
             Member m = { s, in_off[s] + pos[s], in_len[s] - pos[s], out_off[s] + produced[s], out_cap[s] > produced[s] ? out_cap[s] - produced[s] : 0,
-                         (h_out && h_out[s]) ? h_out[s] + produced[s] : nullptr };
+                         (h_out && h_out[s]) ? h_out[s] + produced[s] : nullptr, h_pinned && (*h_pinned)[s] != 0, 0 };
+            // A first member may be the whole file: the finder scans all of it.  Later members of a multi-member file (BGZF, pigz -i,
+            // concatenated .gz) are sized like their predecessor: scanning the whole remainder for each would cost
+            // O(members x bytes), so the speculative path gets a window of 4 predecessors + 1 MiB, and small members go straight to
+            // the in-order kernel (which stops at BFINAL by itself).  A wrong guess only costs speed: the chain breaks at the window
+            // end and the in-order kernel decodes the member.
+            m.scan_len = first ? m.def_len : (prev_comp[s] < kParallelMinBytes ? 0 : std::min<uint64_t>(m.def_len, 4 * prev_comp[s] + (1u << 20)));
             mem.push_back(m);
         }
         if (mem.empty()) break;
@@ -1208,7 +1360,7 @@ int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const 
         for (size_t i = 0; i < mem.size(); i++) {
             size_t s = mem[i].stream;
             uint64_t wrote = std::min<uint64_t>(olen[i], mem[i].out_cap);
-            pos[s] += cons[i];
+            pos[s] += cons[i]; prev_comp[s] = cons[i];
             produced[s] += olen[i]; out_len[s] = produced[s]; in_consumed[s] = pos[s];
             if (st[i] != kInfOk) { status[s] = map_inf_status(st[i]); done[s] = 1; continue; }
             if (fmt == B2F_FMT_DEFLATE) { done[s] = 1; continue; }
@@ -1251,6 +1403,7 @@ extern "C" int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams, const u
                                 uint8_t *const *out, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status) {
     if (!ctx || fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP_MULTI) return B2F_ERR_INVALID_ARG;
     if (n_streams == 0) return B2F_OK;
+    if (!in || !in_len || !out || !out_cap || !out_len || !in_consumed || !status) { ctx->err = "NULL argument"; return B2F_ERR_INVALID_ARG; }
     CK(cudaSetDevice(ctx->device));
     ctx->tm.reset();
     std::vector<uint64_t> in_off(n_streams), out_off(n_streams); uint64_t tin = 0, tout = 0;
@@ -1259,24 +1412,20 @@ extern "C" int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams, const u
     CK(ctx->buf[NB_DEC_OUT].ensure(tout + 512));
     uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>(), *d_out = ctx->buf[NB_DEC_OUT].as<uint8_t>();
     ctx->tm.mark(ctx->stream, "h2d");
-    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(cudaMemcpyAsync(d_in + in_off[s], in[s], in_len[s], cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(h2d_copy(ctx, d_in + in_off[s], in[s], in_len[s], ctx->stream, is_pinned_host(in[s])));
     InputAccess IA = { ctx, in, d_in, in_off.data(), in_len };
-    // early (overlapped) copies only into pinned destinations: a pageable cudaMemcpyAsync would block the launching thread
-    std::vector<uint8_t *> h_out(n_streams, nullptr);
-    for (size_t s = 0; s < n_streams; s++) {
-        cudaPointerAttributes pa;
-        if (out[s] && cudaPointerGetAttributes(&pa, out[s]) == cudaSuccess && pa.type == cudaMemoryTypeHost) h_out[s] = out[s];
-    }
-    cudaGetLastError();
+    // finished parts of the output are copied out while the rest is still being resolved (inflate_round)
+    std::vector<uint8_t *> h_out(n_streams, nullptr); std::vector<char> h_pinned(n_streams, 0);
+    for (size_t s = 0; s < n_streams; s++) { h_out[s] = out[s]; h_pinned[s] = is_pinned_host(out[s]) ? 1 : 0; }
     std::vector<uint64_t> h_copied(n_streams, 0);
-    int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status, h_out.data(), &h_copied);
+    int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status, h_out.data(), &h_copied, &h_pinned);
     if (rc) return rc;
     ctx->tm.finish(ctx->stream);
     CK(cudaStreamSynchronize(ctx->stream));
     collect_stats(ctx, true);
     for (size_t s = 0; s < n_streams; s++) {
         const size_t w = std::min(out_len[s], out_cap[s]), have = (size_t)std::min<uint64_t>(h_copied[s], w);
-        if (w > have) CK(cudaMemcpyAsync(out[s] + have, d_out + out_off[s] + have, w - have, cudaMemcpyDeviceToHost, ctx->stream));
+        if (w > have) CK(d2h_copy(ctx, out[s] + have, d_out + out_off[s] + have, w - have, ctx->stream, h_pinned[s] != 0));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->aux[0]));
@@ -1287,6 +1436,7 @@ extern "C" int b2f_decode_device(b2f_ctx *ctx, int fmt, size_t n_streams, const 
                                  uint8_t *d_out, const uint64_t *out_off, const size_t *out_cap, size_t *out_len, size_t *in_consumed, int *status) {
     if (!ctx || fmt < B2F_FMT_DEFLATE || fmt > B2F_FMT_GZIP_MULTI) return B2F_ERR_INVALID_ARG;
     if (n_streams == 0) return B2F_OK;
+    if (!d_in || !in_off || !in_len || !d_out || !out_off || !out_cap || !out_len || !in_consumed || !status) { ctx->err = "NULL argument"; return B2F_ERR_INVALID_ARG; }
     CK(cudaSetDevice(ctx->device));
     ctx->tm.reset();
     InputAccess IA = { ctx, nullptr, d_in, in_off, in_len };

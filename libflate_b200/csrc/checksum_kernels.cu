@@ -80,15 +80,17 @@ __device__ __forceinline__ uint32_t find_owner64(const uint64_t *__restrict__ pr
 constexpr uint32_t kCkThreads = 1024;
 constexpr uint32_t kCkUBytes = 4 * 256 * 32 * 4;                  // bank-private Z512 tables
 constexpr uint32_t kCkZBytes = 7 * 4 * 256 * 4;
-constexpr uint32_t kCkSmemCrc = kCkUBytes + kCkZBytes;
+constexpr uint32_t kCkSmemCrc = kCkUBytes + kCkZBytes + 32768;    // + slack to place the Z512 tables on a 32 KiB boundary
 
 __device__ __forceinline__ uint32_t ck_lds(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-// Z512(x): four conflict-free lookups; ul = shared address of the lane's column of table 0
+// Z512(x): four conflict-free lookups; ul = shared address of the lane's column of table 0.  Table 0 starts on a 32 KiB boundary,
+// so bits 7..14 of ul are zero and (byte << 7) | ul is one LOP3; the table number goes into the load's immediate offset.
+template <uint32_t kOff> __device__ __forceinline__ uint32_t ck_lds_off(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(kOff)); return v; }
 __device__ __forceinline__ uint32_t ck_adv512(uint32_t x, uint32_t ul) {
-    const uint32_t a = ck_lds(ul + ((x << 7) & 0x7F80u));
-    const uint32_t b = ck_lds(ul + 32768u + ((x >> 1) & 0x7F80u));
-    const uint32_t c = ck_lds(ul + 65536u + ((x >> 9) & 0x7F80u));
-    const uint32_t d = ck_lds(ul + 98304u + ((x >> 17) & 0x7F80u));
+    const uint32_t a = ck_lds_off<0>(((x << 7) & 0x7F80u) | ul);
+    const uint32_t b = ck_lds_off<32768>(((x >> 1) & 0x7F80u) | ul);
+    const uint32_t c = ck_lds_off<65536>(((x >> 9) & 0x7F80u) | ul);
+    const uint32_t d = ck_lds_off<98304>(((x >> 17) & 0x7F80u) | ul);
     return a ^ b ^ c ^ d;
 }
 // Z_(4 << level)(x) from the ordinary tables (zt = shared address of g_tabZ's copy)
@@ -116,14 +118,16 @@ __global__ void __launch_bounds__(kCkThreads, 1) k_checksum(ChecksumDev C) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t ul = 0, zt = 0;
     if (DO_CRC) {
-        uint32_t *su = reinterpret_cast<uint32_t *>(csm);
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(csm);
+        const uint32_t pad = (32768u - (sbase & 32767u)) & 32767u;             // Z512 tables on a 32 KiB boundary of the shared window
+        uint32_t *su = reinterpret_cast<uint32_t *>(csm + pad);
         // replicate: the warp takes 32 entries at a time, entry e goes to words 32 e + lane (conflict free)
         for (uint32_t e0 = warp * 32; e0 < 1024; e0 += 32 * (kCkThreads / 32)) {
             const uint32_t mine = g_tabU[e0 + lane];
 #pragma unroll 8
             for (uint32_t e = 0; e < 32; e++) su[(e0 + e) * 32 + lane] = __shfl_sync(0xFFFFFFFFu, mine, e);
         }
-        uint32_t *sz = reinterpret_cast<uint32_t *>(csm + kCkUBytes);
+        uint32_t *sz = reinterpret_cast<uint32_t *>(csm + pad + kCkUBytes);
         for (uint32_t i = threadIdx.x; i < 7 * 4 * 256; i += kCkThreads) sz[i] = g_tabZ[i];
         ul = (uint32_t)__cvta_generic_to_shared(su) + 4u * lane;
         zt = (uint32_t)__cvta_generic_to_shared(sz);
@@ -141,44 +145,56 @@ __global__ void __launch_bounds__(kCkThreads, 1) k_checksum(ChecksumDev C) {
         const uint32_t K = (uint32_t)(r1 - r0);
         uint32_t R0 = 0, R1 = 0, R2 = 0, R3 = 0;                              // CRC registers of the lane's four sub-streams
         uint32_t S1 = 0, S2 = 0, S3 = 0;
-        auto row = [&](const uint4 v, uint32_t k, bool last) {
-            if (DO_ADLER) {
-                const uint32_t c0 = __dp4a(v.x, 0x01010101u, 0u), c1 = __dp4a(v.y, 0x01010101u, 0u), c2 = __dp4a(v.z, 0x01010101u, 0u), c3 = __dp4a(v.w, 0x01010101u, 0u);
-                const uint32_t c = c0 + c1 + c2 + c3;
-                S1 += c; S2 += k * c;
-                S3 += __dp4a(v.x, 0x03020100u, 0u) + __dp4a(v.y, 0x03020100u, 0u) + __dp4a(v.z, 0x03020100u, 0u) + __dp4a(v.w, 0x03020100u, 0u) + 4u * c1 + 8u * c2 + 12u * c3;
-            }
-            if (DO_CRC) {
-                R0 ^= v.x; R1 ^= v.y; R2 ^= v.z; R3 ^= v.w;
-                if (!last) { R0 = ck_adv512(R0, ul); R1 = ck_adv512(R1, ul); R2 = ck_adv512(R2, ul); R3 = ck_adv512(R3, ul); }
-            }
+        // one 512-byte row: k = row index inside the span; the span's LAST row is not followed by the Z512 advance
+        auto adler_row = [&](const uint4 v, uint32_t k) {
+            const uint32_t c0 = __dp4a(v.x, 0x01010101u, 0u), c1 = __dp4a(v.y, 0x01010101u, 0u), c2 = __dp4a(v.z, 0x01010101u, 0u), c3 = __dp4a(v.w, 0x01010101u, 0u);
+            const uint32_t c = c0 + c1 + c2 + c3;
+            S1 += c; S2 += k * c;
+            S3 += __dp4a(v.x, 0x03020100u, 0u) + __dp4a(v.y, 0x03020100u, 0u) + __dp4a(v.z, 0x03020100u, 0u) + __dp4a(v.w, 0x03020100u, 0u) + 4u * c1 + 8u * c2 + 12u * c3;
         };
-        // rows that lie wholly inside the stream are loaded unconditionally, four at a time with the next four already in flight
-        const uint64_t ri0 = mis ? 1 : 0, ri1 = nv / kChecksumRow;            // interior rows: [ri0, ri1)
-        uint64_t r = r0;
-        if (r < r1 && r < ri0) { row(ck_load_edge(base, r * kChecksumRow + 16u * lane, mis, nv), (uint32_t)(r - r0), r + 1 == r1); r++; }
-        const uint64_t re = min(r1, ri1);                                     // interior rows of this span: [r, re)
-        if (r < re) {
-            const uint4 *__restrict__ gp = reinterpret_cast<const uint4 *>(base + r * kChecksumRow) + lane;   // row stride = 32 uint4
-            uint32_t k = (uint32_t)(r - r0);
-            const uint32_t cnt = (uint32_t)(re - r);
+        auto row_mid = [&](const uint4 v, uint32_t k) {
+            if (DO_ADLER) adler_row(v, k);
+            if (DO_CRC) { R0 = ck_adv512(R0 ^ v.x, ul); R1 = ck_adv512(R1 ^ v.y, ul); R2 = ck_adv512(R2 ^ v.z, ul); R3 = ck_adv512(R3 ^ v.w, ul); }
+        };
+        auto row_last = [&](const uint4 v, uint32_t k) {
+            if (DO_ADLER) adler_row(v, k);
+            if (DO_CRC) { R0 ^= v.x; R1 ^= v.y; R2 ^= v.z; R3 ^= v.w; }
+        };
+        // Rows that lie wholly inside the stream are loaded unconditionally, four at a time with the next four already in flight.
+        // The span's last row and the (at most two) rows that contain the stream's ends go through the guarded loader.
+        const uint32_t ri0 = mis ? 1u : 0u;                                   // first interior row of the stream
+        const uint64_t ri1 = nv / kChecksumRow;                               // interior rows: [ri0, ri1)
+        uint32_t k = 0;                                                       // row r0 + k is next
+        const uint32_t kl = K - 1;                                            // the span's last row
+        if (r0 < ri0 && k < kl) { row_mid(ck_load_edge(base, r0 * kChecksumRow + 16u * lane, mis, nv), 0); k = 1; }
+        const uint32_t kmid = ri1 > r0 ? (uint32_t)min((uint64_t)kl, ri1 - r0) : 0u;   // rows [k, kmid) are interior and not last
+        if (k < kmid) {
+            const uint4 *__restrict__ gp = reinterpret_cast<const uint4 *>(base + (r0 + k) * kChecksumRow) + lane;   // row stride = 32 uint4
+            const uint32_t cnt = kmid - k, cnt4 = cnt & ~3u;
             uint4 cur[4], nxt[4];
+            if (cnt4) {
 #pragma unroll
-            for (uint32_t u = 0; u < 4; u++) cur[u] = u < cnt ? __ldg(gp + 32u * u) : make_uint4(0, 0, 0, 0);
-            uint32_t done = 0;
-            while (done < cnt) {
+                for (uint32_t u = 0; u < 4; u++) cur[u] = __ldg(gp + 32u * u);
+                for (uint32_t done = 0; done < cnt4; done += 4) {
+                    if (done + 4 < cnt4) {
 #pragma unroll
-                for (uint32_t u = 0; u < 4; u++) nxt[u] = done + 4 + u < cnt ? __ldg(gp + 32u * (done + 4 + u)) : make_uint4(0, 0, 0, 0);
+                        for (uint32_t u = 0; u < 4; u++) nxt[u] = __ldg(gp + 32u * (done + 4 + u));
+                    }
 #pragma unroll
-                for (uint32_t u = 0; u < 4; u++)
-                    if (done + u < cnt) row(cur[u], k + done + u, r + done + u + 1 == r1);
+                    for (uint32_t u = 0; u < 4; u++) row_mid(cur[u], k + done + u);
 #pragma unroll
-                for (uint32_t u = 0; u < 4; u++) cur[u] = nxt[u];
-                done += 4;
+                    for (uint32_t u = 0; u < 4; u++) cur[u] = nxt[u];
+                }
             }
-            r = re;
+            for (uint32_t d = cnt4; d < cnt; d++) row_mid(__ldg(gp + 32u * d), k + d);
+            k = kmid;
         }
-        for (; r < r1; r++) row(ck_load_edge(base, r * kChecksumRow + 16u * lane, mis, nv), (uint32_t)(r - r0), r + 1 == r1);
+        for (; k < kl; k++) row_mid(ck_load_edge(base, (r0 + k) * kChecksumRow + 16u * lane, mis, nv), k);     // (a padded row before the last: never in practice)
+        {
+            const uint64_t r = r0 + kl;
+            const bool interior = r >= ri0 && r < ri1;
+            row_last(interior ? __ldg(reinterpret_cast<const uint4 *>(base + r * kChecksumRow) + lane) : ck_load_edge(base, r * kChecksumRow + 16u * lane, mis, nv), kl);
+        }
         const uint64_t vend = r1 * kChecksumRow;                              // virtual end of the span's rows (may lie beyond nv in the last row)
         if (DO_CRC) {
             // fold the 128 sub-streams: slot q of lane l sits 4 (4 l + q) bytes into the row

@@ -358,6 +358,9 @@ constexpr uint32_t kSegOrdQ = kSegFreeQ + 68 * 8;                // byte offset 
 constexpr uint32_t kSegSmem = kSegOrdQ + 34 * 8;
 static_assert((kSegRing & kSegMask) == 0 && kSegStepMax + 258 + 8 < kSegRing, "segment ring geometry");
 
+// ceil(65536 / p): k mod p == k - p * ((k * inv) >> 16) for p < 32, k < 400 (run-length matches; avoids a division per symbol)
+__constant__ uint32_t kInvPeriod[32] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
+
 __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
     extern __shared__ __align__(16) uint8_t seg_smem[];
     uint16_t *ring = reinterpret_cast<uint16_t *>(seg_smem);          // symbol of segment position p at (a0 + p) & kSegMask
@@ -374,10 +377,13 @@ __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
     const uint32_t a0 = (uint32_t)A & kSegMask;                       // ring index == absolute offset mod kSegRing: 8-symbol groups of
                                                                       // the ring are 16-byte aligned groups of sym16
     const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t sub = lane >> 3, l8 = lane & 7u;                   // order-free copies: four at a time, eight lanes each
     const uint32_t lead = (8u - ((uint32_t)A & 7u)) & 7u;             // symbols before the first 16-byte aligned group of sym16
     uint32_t pos = 0, flushed = 0, err = 0, reach = 0;                // segment-relative
+    uint32_t tnext = lane < ntok ? __ldg(tok + lane) : kTokSkip;
     for (uint32_t i0 = 0; i0 < ntok;) {
-        const uint32_t tk = i0 + lane < ntok ? __ldg(tok + i0 + lane) : kTokSkip;
+        const uint32_t tk = tnext;
+        tnext = i0 + 32 + lane < ntok ? __ldg(tok + i0 + 32 + lane) : kTokSkip;    // the next step's tokens (a step nearly always takes all 32)
         bool live = tk != kTokSkip;
         bool is_m = live && (tk & kSymPtr);
         uint32_t len = !live ? 0u : is_m ? (tk >> 16) & 0x1FFu : 1u;
@@ -389,6 +395,7 @@ __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
             take = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, incl <= kSegStepMax));
             if (lane >= take) { live = false; is_m = false; len = 0; }
             total = __shfl_sync(0xFFFFFFFFu, incl, take - 1);
+            tnext = i0 + take + lane < ntok ? __ldg(tok + i0 + take + lane) : kTokSkip;
         }
         const uint32_t off = incl - len;                              // (garbage for dropped lanes, which do nothing)
         const uint32_t dst = pos + off;
@@ -417,28 +424,14 @@ __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
             for (uint32_t k = 0; k < len2; k++) ring[(d2 + k) & kSegMask] = __ldcg(gs + k);
         }
         __syncwarp();
-        // ---- order-free work, four entries in flight: markers (no reads at all) and copies whose source is older than the step
+        // ---- order-free work: markers (no reads at all) and copies whose source is older than the step; these never overlap
         for (uint32_t i = 0; i < nfree; i += 4) {
-            uint2 c[4]; uint32_t v[4];
-#pragma unroll
-            for (uint32_t u = 0; u < 4; u++) c[u] = fq[i + u];
-#pragma unroll
-            for (uint32_t u = 0; u < 4; u++) {
-                const uint32_t mdist = c[u].y >> 16;
-                v[u] = mdist ? ring[((c[u].y & 0xFFFFu) + lane) & kSegMask] : (c[u].y & 0xFFFFu) - lane;
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < 4; u++) {
-                const uint32_t mlen = c[u].x >> 16;
-                if (i + u < nfree && lane < mlen) ring[((c[u].x & 0xFFFFu) + lane) & kSegMask] = (uint16_t)v[u];
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < 4; u++) {
-                const uint32_t mlen = c[u].x >> 16;
-                if (i + u < nfree && mlen > 32) {                     // (uniform) the rest of a long one
-                    const uint32_t mdist = c[u].y >> 16, md = c[u].x & 0xFFFFu, ms = c[u].y & 0xFFFFu;
-                    for (uint32_t k = 32 + lane; k < mlen; k += 32) ring[(md + k) & kSegMask] = mdist ? ring[(ms + k) & kSegMask] : (uint16_t)(ms - k);
-                }
+            const uint2 c = fq[min(i + sub, nfree - 1u)];
+            const uint32_t mlen = i + sub < nfree ? c.x >> 16 : 0u, md = c.x & 0xFFFFu, ms = c.y & 0xFFFFu;
+            const bool iscopy = (c.y >> 16) != 0;
+            for (uint32_t k = l8; __any_sync(0xFFFFFFFFu, k < mlen); k += 8) {
+                const uint32_t v = iscopy ? (uint32_t)ring[(ms + k) & kSegMask] : ms - k;
+                if (k < mlen) ring[(md + k) & kSegMask] = (uint16_t)v;
             }
         }
         __syncwarp();
@@ -458,7 +451,8 @@ __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
                     __syncwarp();
                 }
             } else {                                                  // short period: symbol k repeats symbol k mod dist of the source
-                for (uint32_t k = lane; k < mlen; k += 32) ring[(md + k) & kSegMask] = ring[(ms + k % mdist) & kSegMask];
+                const uint32_t inv = kInvPeriod[mdist];
+                for (uint32_t k = lane; k < mlen; k += 32) ring[(md + k) & kSegMask] = ring[(ms + k - mdist * ((k * inv) >> 16)) & kSegMask];
             }
             __syncwarp();
         }
@@ -506,9 +500,14 @@ __global__ void __launch_bounds__(128) k_seg_cuts(SpecDev S) {
 
 // One CTA per chain (the slots from a cut up to the next cut of the same member).  The last kSubRing final bytes of the chain are
 // kept in shared memory at index (offset - base) mod kSubRing, base = chain start rounded down to 16, so that aligned 16-byte
-// groups of out are aligned groups of the window.
-constexpr uint32_t kSubThreads = 256, kSubRing = 49152, kSubBatch = 16384;
-__global__ void __launch_bounds__(kSubThreads) k_seg_subst(SpecDev S, uint32_t slot_off) {
+// groups of out are aligned groups of the window.  The chain is walked in BATCHES of one segment's bytes that span at most
+// kSubBatch / 16 aligned 16-byte groups (two per thread); the symbols of the next batch are loaded before the current one is processed, and the sixteen
+// window reads of a group are issued unconditionally (no divergent branch per symbol), so a batch costs about one barrier.
+constexpr uint32_t kSubThreads = 256, kSubRing = 49152, kSubBatch = 8192;
+static_assert(kSubBatch / 16 == 2 * kSubThreads, "two groups per thread and batch");
+struct SubBatch { uint64_t A, B; uint32_t bl, s, rA, rB; bool valid; };   // segment start, batch start, batch bytes, slot, window indices of A and B
+
+__global__ void __launch_bounds__(kSubThreads, 4) k_seg_subst(SpecDev S, uint32_t slot_off) {
     extern __shared__ __align__(16) uint8_t win[];
     const uint32_t c = blockIdx.x + slot_off, tid = threadIdx.x;
     if (!S.seg_nout[c] || !S.seg_cut[c]) return;
@@ -516,62 +515,99 @@ __global__ void __launch_bounds__(kSubThreads) k_seg_subst(SpecDev S, uint32_t s
     if (S.mem_err[m]) return;                                         // the member goes to the in-order kernel: markers may point anywhere
     uint8_t *out = S.out;                                             // read back by later segments of the chain: no __restrict__
     const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    uint32_t rA = (uint32_t)S.seg_out[c] & 15u;                       // window index of the current segment's first byte
-    for (uint32_t s = c; s < S.n_slots; s++) {
-        const uint32_t n = S.seg_nout[s];
-        if (!n) continue;
-        if (s != c && (S.seg_cut[s] || S.seg_member[s] != m)) break;
-        const uint64_t A = S.seg_out[s];
-        const uint16_t *__restrict__ sym = S.sym16;
-        for (uint32_t b0 = 0; b0 < n; b0 += kSubBatch) {              // (segments longer than a batch: highly compressible data)
-            const uint32_t bl = min(kSubBatch, n - b0);
-            const uint64_t B = A + b0;
-            uint32_t rB = rA + b0; rB -= (rB / kSubRing) * kSubRing;   // window index of the batch's first byte
-            // marker value mm (distance before A, minus 1) is still in the window iff A-1-mm >= B+bl-kSubRing
-            const int32_t thr = (int32_t)kSubRing - 1 - (int32_t)b0 - (int32_t)bl;
-            const uint64_t g0 = B & ~15ull;
-            const uint32_t ng = (uint32_t)((B + bl + 15 - g0) >> 4);
-            for (uint32_t g = tid; g < ng; g += kSubThreads) {
-                const uint64_t p = g0 + 16ull * g;                    // offset in out of this 16-byte group
-                uint32_t rp = rB + (uint32_t)(16u * g) + kSubRing - (uint32_t)(B - g0);   // window index of p (+ kSubRing: p may lie below B)
-                rp -= (rp / kSubRing) * kSubRing;
-                const bool full = vec && p >= B && p + 16 <= B + bl;
-                if (full) {
-                    const uint4 x = *reinterpret_cast<const uint4 *>(sym + p), y = *reinterpret_cast<const uint4 *>(sym + p + 8);
-                    const uint32_t w[8] = { x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w };
-                    uint32_t o[4] = { 0, 0, 0, 0 };
+    const uint16_t *__restrict__ sym = S.sym16;
+    // the batch after `b` (every thread computes the same walk: a few cached loads per segment)
+    auto advance = [&](const SubBatch &b) {
+        SubBatch n = b;
+        const uint32_t segn = S.seg_nout[b.s];
+        const uint64_t done = b.B + b.bl - b.A;
+        if (done < segn) {                                            // next batch of the same (long) segment
+            n.B = b.B + b.bl; n.bl = (uint32_t)min((uint64_t)(kSubBatch - ((uint32_t)n.B & 15u)), segn - done);
+            n.rB = b.rB + b.bl; if (n.rB >= kSubRing) n.rB -= kSubRing;
+            return n;
+        }
+        uint32_t rA = b.rB + b.bl; if (rA >= kSubRing) rA -= kSubRing;
+        for (uint32_t s = b.s + 1; s < S.n_slots; s++) {
+            const uint32_t nn = S.seg_nout[s];
+            if (!nn) continue;
+            if (S.seg_cut[s] || S.seg_member[s] != m) break;
+            n.s = s; n.A = n.B = S.seg_out[s]; n.bl = min(kSubBatch - ((uint32_t)n.B & 15u), nn); n.rA = n.rB = rA;
+            return n;
+        }
+        n.valid = false;
+        return n;
+    };
+    // the 2 x 16 symbols of this thread's groups of batch b (aligned on the offset in out; symbols outside the batch are ignored)
+    auto load = [&](const SubBatch &b, uint4 *x) {
+        const uint64_t g0 = b.B & ~15ull;
+        const uint32_t ng = (uint32_t)((b.B + b.bl + 15 - g0) >> 4);
 #pragma unroll
-                    for (uint32_t q = 0; q < 16; q++) {
-                        uint32_t v = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
-                        if (v & kMarker) {
-                            const int32_t mm = (int32_t)(v & 0x7FFFu);
-                            if (mm <= thr) { int32_t r = (int32_t)rA - 1 - mm; if (r < 0) r += (int32_t)kSubRing; v = win[r]; }
-                            else v = out[A - 1 - (uint64_t)mm];
-                        }
-                        o[q >> 2] |= v << (8u * (q & 3u));
+        for (uint32_t u = 0; u < 2; u++) {
+            const uint32_t g = tid + u * kSubThreads;
+            if (g < ng) { const uint4 *p = reinterpret_cast<const uint4 *>(sym + g0 + 16ull * g); x[2 * u] = __ldg(p); x[2 * u + 1] = __ldg(p + 1); }
+        }
+    };
+    SubBatch cur;
+    cur.s = c; cur.A = cur.B = S.seg_out[c]; cur.bl = min(kSubBatch - ((uint32_t)cur.B & 15u), S.seg_nout[c]); cur.rA = cur.rB = (uint32_t)cur.A & 15u; cur.valid = true;
+    uint4 x[4], y[4];
+    load(cur, x);
+    while (cur.valid) {
+        const SubBatch nxt = advance(cur);
+        if (nxt.valid) load(nxt, y);
+        // marker value mm (distance before A, minus 1) is still in the window iff A-1-mm >= B+bl-kSubRing
+        const int32_t thr = (int32_t)kSubRing - 1 - (int32_t)(cur.B - cur.A) - (int32_t)cur.bl;
+        const uint64_t g0 = cur.B & ~15ull;
+        const uint32_t lead16 = (uint32_t)(cur.B - g0);
+        const uint32_t ng = (uint32_t)((cur.B + cur.bl + 15 - g0) >> 4);
+#pragma unroll 1
+        for (uint32_t u = 0; u < 2; u++) {
+            const uint32_t g = tid + u * kSubThreads;
+            if (g < ng) {
+                const uint64_t p = g0 + 16ull * g;                    // offset in out of this 16-byte group
+                uint32_t rp = cur.rB + 16u * g + kSubRing - lead16;   // window index of p (p may lie below B: + kSubRing first)
+                rp -= (rp / kSubRing) * kSubRing;
+                const uint4 xa = u ? x[2] : x[0], xb = u ? x[3] : x[1];
+                const uint32_t w[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
+                uint32_t v[16], t[16];
+#pragma unroll
+                for (uint32_t q = 0; q < 16; q++) {
+                    v[q] = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+                    int32_t r = (int32_t)cur.rA - 1 - (int32_t)(v[q] & 0x7FFFu);
+                    if (r < 0) r += (int32_t)kSubRing;
+                    t[q] = win[r];                                    // unconditional: the index is always inside the window
+                }
+                const uint32_t lo = p < cur.B ? lead16 : 0u;          // symbols [lo, hi) of the group belong to the batch
+                const uint32_t hi = (uint32_t)min((uint64_t)16, cur.B + cur.bl - p);
+                uint32_t o[4] = { 0, 0, 0, 0 };
+#pragma unroll
+                for (uint32_t q = 0; q < 16; q++) {
+                    uint32_t bv = v[q];
+                    if (bv & kMarker) {
+                        bv = t[q];
+                        if ((int32_t)(v[q] & 0x7FFFu) > thr && q >= lo && q < hi) bv = out[cur.A - 1 - (uint64_t)(v[q] & 0x7FFFu)];   // (long segments only)
                     }
+                    v[q] = bv & 0xFFu;
+                    o[q >> 2] |= v[q] << (8u * (q & 3u));
+                }
+                if (lo == 0 && hi == 16) {
                     const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4 *>(out + p) = ov;
                     *reinterpret_cast<uint4 *>(win + rp) = ov;
-                } else {
-                    for (uint32_t q = 0; q < 16; q++) {
-                        const uint64_t pp = p + q;
-                        if (pp < B || pp >= B + bl) continue;
-                        uint32_t v = sym[pp];
-                        if (v & kMarker) {
-                            const int32_t mm = (int32_t)(v & 0x7FFFu);
-                            if (mm <= thr) { int32_t r = (int32_t)rA - 1 - mm; if (r < 0) r += (int32_t)kSubRing; v = win[r]; }
-                            else v = out[A - 1 - (uint64_t)mm];
-                        }
-                        out[pp] = (uint8_t)v;
-                        uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing;
-                        win[r] = (uint8_t)v;
+                    if (vec) *reinterpret_cast<uint4 *>(out + p) = ov;
+                    else {
+#pragma unroll
+                        for (uint32_t q = 0; q < 16; q++) out[p + q] = (uint8_t)v[q];
                     }
+                } else {
+#pragma unroll
+                    for (uint32_t q = 0; q < 16; q++)
+                        if (q >= lo && q < hi) { out[p + q] = (uint8_t)v[q]; uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing; win[r] = (uint8_t)v[q]; }
                 }
             }
-            __syncthreads();
         }
-        rA += n - (n / kSubRing) * kSubRing; if (rA >= kSubRing) rA -= kSubRing;
+        __syncthreads();
+        cur = nxt;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) x[u] = y[u];
     }
 }
 

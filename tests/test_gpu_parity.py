@@ -352,6 +352,48 @@ def test_decode_multi_member_gzip_with_large_members(ctx):
     assert st == 0 and out == parts[0] and used == len(members[0])
 
 
+def test_decode_many_small_members(ctx):
+    """BGZF / pigz -i shape: hundreds of small gzip members back to back (MultiDecoder, src/gzip.rs:1052-1167); later members are
+    sized after their predecessor, so the rest of the file is not re-scanned for every member"""
+    rng = random.Random(46)
+    parts = [_text(rng, rng.randint(20000, 60000)) for _ in range(120)] + [_text(rng, 1 << 20, nwords=3000)] + [_text(rng, 30000) for _ in range(5)]
+    blob = b"".join(pygzip.compress(p, 6, mtime=0) if i % 2 else orc.encode(2, p, mtime=0) for i, p in enumerate(parts))
+    st, out, used, _ = ctx.decode(3, blob, cap=sum(map(len, parts)) + 64)
+    assert st == 0 and out == b"".join(parts) and used == len(blob)
+
+
+def test_pageable_and_page_locked_callers_get_the_same_bytes(ctx):
+    """pinned-memory registration is internal -- ordinary memory is staged by the library, b2f_host_alloc memory is
+    used in place; both give the oracle's bytes"""
+    from libflate_b200 import native, titles
+    d = titles.generate(24 << 20, seed=11)
+    sched = np.full(d.size // 8192 + 1, 8192, dtype=np.int64)
+    want = orc.encode(orc.FMT_GZIP, d.tobytes(), sched.tolist(), mtime=0)
+    cap = native.lib().b2f_encode_bound(d.size, len(sched), None)
+    s0 = ctx.stats()
+    e_page = np.empty(cap, dtype=np.uint8)
+    m = ctx.encode_into(native.FMT_GZIP, d, e_page, sched, mtime=0)
+    s1 = ctx.stats()
+    assert e_page[:m].tobytes() == want
+    assert s1["staged_h2d_bytes"] - s0["staged_h2d_bytes"] == d.size and s1["staged_d2h_bytes"] - s0["staged_d2h_bytes"] == m
+    h_in, h_enc, h_dec = native.host_alloc(d.size), native.host_alloc(cap), native.host_alloc(d.size + 64)
+    try:
+        h_in[:] = d
+        m2 = ctx.encode_into(native.FMT_GZIP, h_in, h_enc, sched, mtime=0)
+        s2 = ctx.stats()
+        assert m2 == m and h_enc[:m].tobytes() == want
+        assert s2["staged_h2d_bytes"] == s1["staged_h2d_bytes"] and s2["staged_d2h_bytes"] == s1["staged_d2h_bytes"]     # in place
+        dl, used, st = ctx.decode_into(native.FMT_GZIP, h_enc, m, h_dec)
+        assert st == 0 and dl == d.size and used == m and np.array_equal(h_dec[:dl], d)
+        p_dec = np.empty(d.size + 64, dtype=np.uint8)
+        dl, used, st = ctx.decode_into(native.FMT_GZIP, e_page, m, p_dec)
+        assert st == 0 and dl == d.size and used == m and np.array_equal(p_dec[:dl], d)
+        assert ctx.stats()["staged_d2h_bytes"] - s2["staged_d2h_bytes"] == d.size
+    finally:
+        for a in (h_in, h_enc, h_dec):
+            native.host_free(a)
+
+
 def test_decode_output_too_small(ctx):
     d = b"abcabcabc" * 5000
     enc = orc.encode(orc.FMT_ZLIB, d)

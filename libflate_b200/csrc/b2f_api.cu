@@ -130,8 +130,10 @@ struct b2f_ctx {
     uint64_t n_spec_members = 0, n_inorder_members = 0;
     cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t aux_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t part_ev[b2f::kMaxParts] = {};
     int overlap = 1;               // run independent chunk slices of the LZ77 stage on separate streams
     CopyPool pool; Stager st_in, st_out; unsigned copy_threads = 4; size_t stage_rr = 0;
+    uint32_t max_parts = 4;        // pipeline depth of the decode's LZ77 resolution + device->host copies (B2F_DECODE_PARTS, <= kMaxParts)
     uint64_t staged_h2d = 0, staged_d2h = 0;     // bytes that went through the internal staging (pageable caller memory)
 };
 
@@ -225,8 +227,10 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     ctx->tm.create();
     for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
     for (auto &ev : ctx->aux_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : ctx->part_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (const char *o = getenv("B2F_OVERLAP")) ctx->overlap = atoi(o);
     if (const char *o = getenv("B2F_COPY_THREADS")) ctx->copy_threads = (unsigned)std::max(1, atoi(o));
+    if (const char *o = getenv("B2F_DECODE_PARTS")) ctx->max_parts = (uint32_t)std::min<int>(kMaxParts, std::max(1, atoi(o)));
     ctx->copy_threads = std::min(ctx->copy_threads, std::max(1u, std::thread::hardware_concurrency()));
     ctx->pool.start(ctx->copy_threads);
     *out = ctx;
@@ -243,6 +247,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     ctx->tm.destroy();
     for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
     for (auto &ev : ctx->aux_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->part_ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1152,7 +1157,8 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 const size_t s_u0 = PS.add(slot0.data(), (nsel + 1) * 4);
                 const size_t s_st = PS.reserve((size_t)nslots * 8), s_so = PS.reserve((size_t)nslots * 8), s_sn = PS.reserve((size_t)nslots * 4),
                              s_sb = PS.reserve((size_t)nslots * 4), s_sm = PS.reserve((size_t)nslots * 4), s_sr = PS.reserve((size_t)nslots * 4),
-                             s_sc = PS.reserve((size_t)nslots);
+                             s_sc = PS.reserve((size_t)nslots), s_rec = PS.reserve(((size_t)nslots + 2) * 16), s_cl = PS.reserve((size_t)nslots * 4),
+                             s_cc = PS.reserve(2 * kMaxParts * 4);
                 const size_t s_err = PS.reserve(n * 4);
                 CK(PS.commit(ctx->stream));
                 CK(ctx->buf[NB_SPEC_SYM].ensure(out_hi * 2 + 256));
@@ -1162,36 +1168,47 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 S.n_sel = (uint32_t)nsel; S.n_slots = nslots; S.sel_slot0 = PS.ptr<uint32_t>(s_u0);
                 S.seg_tok = PS.ptr<uint64_t>(s_st); S.seg_out = PS.ptr<uint64_t>(s_so); S.seg_ntok = PS.ptr<uint32_t>(s_sn); S.seg_nout = PS.ptr<uint32_t>(s_sb);
                 S.seg_member = PS.ptr<uint32_t>(s_sm); S.seg_reach = PS.ptr<uint32_t>(s_sr); S.seg_cut = PS.ptr<uint8_t>(s_sc);
+                S.seg_rec = PS.ptr<uint4>(s_rec); S.chain_list = PS.ptr<uint32_t>(s_cl); S.chain_count = PS.ptr<uint32_t>(s_cc);
                 S.sym16 = ctx->buf[NB_SPEC_SYM].as<uint16_t>(); S.mem_err = PS.ptr<uint32_t>(s_err);
                 CK(cudaMemsetAsync(S.mem_err, 0, n * 4, ctx->stream));
-                ctx->tm.mark(ctx->stream, "spec_tokens");
-                CK(spec_launch_tokens(S, (uint32_t)nsel, ctx->stream));
-                ctx->tm.mark(ctx->stream, "lz_resolve");
-                CK(spec_launch_segments(S, ctx->stream));
-                ctx->tm.mark(ctx->stream, "lz_subst");
-                // The substitution runs in parts over the slots.  All parts are launched first; then each part's output is copied to the
-                // caller's memory on a side stream (page-locked destination: one DMA per block; pageable: staged through the pinned
-                // buffers, the calling thread copying piece k out while piece k+1 arrives and the later parts still run).
+                CK(cudaMemsetAsync(S.chain_count, 0, 2 * kMaxParts * 4, ctx->stream));
+                CK(cudaMemsetAsync(S.seg_rec + nslots, 0, 32, ctx->stream));       // the two read-ahead records behind the last slot
+                // The LZ77 resolution is a pipeline over PARTS (runs of whole blocks): tokens -> segments (markers) -> substitution for
+                // part p, then part p+1, ...; as soon as a part is final its output is copied to the caller's memory on a side stream
+                // (page-locked destination: one DMA per member run; pageable: staged through the pinned buffers, the calling thread
+                // copying piece k out while piece k+1 arrives) while the following parts are still being resolved.
                 {
                     uint64_t total_len = 0; for (size_t k = 0; k < nsel; k++) total_len += k_len[k];
                     bool any_host = false;
                     for (size_t k = 0; k < nsel; k++) if (mem[cands[sel_blocks[k]].first].h_out) { any_host = true; break; }
-                    const uint32_t nparts = (any_host && total_len >= (64u << 20)) ? 4u : 1u;
-                    size_t part_b[5] = { 0, 0, 0, 0, 0 }; uint64_t acc = 0;
+                    const uint32_t nparts = any_host ? (uint32_t)std::min<uint64_t>(ctx->max_parts, std::max<uint64_t>(1, total_len / (48u << 20))) : 1u;
+                    size_t part_b[kMaxParts + 1] = { 0 }; uint64_t acc = 0;
                     for (uint32_t part = 0; part < nparts; part++) {
                         size_t b1 = part_b[part];
                         const uint64_t want = total_len * (part + 1) / nparts;
                         while (b1 < nsel && (acc < want || part + 1 == nparts)) { acc += k_len[b1]; b1++; }
                         part_b[part + 1] = b1;
-                        // A chain that starts in this part may run on into later slots (foreign streams): the launch of the part where it
-                        // starts handles all of it, so after launch p every slot of parts <= p is final.
-                        CK(spec_launch_subst(S, slot0[part_b[part]], slot0[b1], ctx->stream));
-                        ctx->stats.kernel_launches += 1;
-                        if (any_host) CK(cudaEventRecord(ctx->aux_ev[part], ctx->stream));
                     }
+                    S.n_parts = nparts;
+                    for (uint32_t part = 0; part <= nparts; part++) S.part_slot0[part] = slot0[part_b[part]];
+                    for (uint32_t part = 0; part < nparts; part++) {
+                        if (part_b[part + 1] == part_b[part]) continue;
+                        // the part's blocks are a contiguous run of candidate blocks (plus, possibly, unselected ones in between)
+                        const uint32_t cb0 = sel_blocks[part_b[part]], cb1 = sel_blocks[part_b[part + 1] - 1];
+                        ctx->tm.mark(ctx->stream, "spec_tokens");
+                        CK(spec_launch_tokens(S, cta0[cb0], cta0[cb1 + 1], ctx->stream));
+                        ctx->tm.mark(ctx->stream, "lz_resolve");
+                        CK(spec_launch_segments(S, part, ctx->stream));
+                        ctx->tm.mark(ctx->stream, "lz_subst");
+                        CK(spec_launch_subst(S, part, ctx->stream));
+                        ctx->stats.kernel_launches += 5;
+                        if (any_host) CK(cudaEventRecord(ctx->part_ev[part], ctx->stream));
+                    }
+                    ctx->tm.mark(ctx->stream, "sync");
                     if (any_host) {
                         for (uint32_t part = 0; part < nparts; part++) {
-                            CK(cudaStreamWaitEvent(ctx->aux[0], ctx->aux_ev[part], 0));
+                            if (part_b[part + 1] == part_b[part]) continue;
+                            CK(cudaStreamWaitEvent(ctx->aux[0], ctx->part_ev[part], 0));
                             for (size_t k = part_b[part]; k < part_b[part + 1];) {
                                 // consecutive blocks of one member are contiguous in out: one copy per run
                                 const uint32_t m = cands[sel_blocks[k]].first;
@@ -1205,8 +1222,6 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     }
                     for (uint32_t m : big) if (is_par[m] && mem[m].h_out) copied[m] = 1;
                 }
-                ctx->stats.kernel_launches += 4;
-                ctx->tm.mark(ctx->stream, "sync");
                 CK(ctx->pin_res.ensure(n * 4 + 64));
                 uint32_t *h_err = ctx->pin_res.as<uint32_t>();
                 CK(cudaMemcpyAsync(h_err, S.mem_err, n * 4, cudaMemcpyDeviceToHost, ctx->stream));

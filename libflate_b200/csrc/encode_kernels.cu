@@ -141,7 +141,7 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *s, uint32_t off) {     
 }
 constexpr uint32_t kMatchSmem = kPTile + kLookback + 261 + 16 + 32;
 
-// md[p] = 0 (literal) or length<<16 | distance of the single candidate libflate would take at p:
+// md[p] = the byte itself (literal; length field 0) or length<<16 | distance of the single candidate libflate would take at p:
 // the most recent earlier occurrence of the same 3 bytes, if within `window` (default.rs:79-91, 116-129).
 __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
     extern __shared__ __align__(16) uint8_t sb[];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
         for (uint32_t u = 0; u < 4; u++) {
             const uint32_t pos = pos0 + u * 512;
             if (pos >= te) break;
-            uint32_t out = 0;
+            uint32_t out = sb[pos + sbase];                       // literal: the byte itself (length field 0)
             if (pos < end) {
                 const uint32_t si = pos + sbase;
                 const uint32_t t = (uint32_t)sb[si] | ((uint32_t)sb[si + 1] << 8) | ((uint32_t)sb[si + 2] << 16);
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
                 const uint32_t eh = __shfl_sync(0xFFFFFFFFu, ext, hl);
                 if (open) k = eh - (lane - hl);
             }
-            uint32_t out = 0;
+            uint32_t out = tt & 0xFFu;                                             // literal: the byte itself (length field 0)
             if (found) { if (k > limit) k = limit; out = ((3 + k) << 16) | total; }
             // deferred positions go to the fix-up queue of this slice (or, should it be full, are finished here)
             bool deferred = res == 2;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(256) k_lz_fixup(EncDev E, uint32_t slice) {
         const uint16_t *__restrict__ lk = E.link + cd.off;
         const uint32_t n = cd.len, pos = (uint32_t)(g - cd.off);
         const uint32_t t = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
-        uint32_t d = lk[pos], total = 0, j = pos, out = 0, hops = 0;
+        uint32_t d = lk[pos], total = 0, j = pos, out = t & 0xFFu, hops = 0;     // literal unless a match is found
         bool found = false, pushed = false;
         while (d) {
             total += d;
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(256) k_lz_fixup2(EncDev E, uint32_t slice) {
             best = __reduce_max_sync(0xFFFFFFFFu, mine);
             if (best >= 0) break;
         }
-        uint32_t out = 0;
+        uint32_t out = t & 0xFFu;                                                  // literal unless a match is found
         if (best >= 0) {                                                           // uniform
             const uint32_t q = (uint32_t)best;
             const uint32_t limit = min(E.max_len - 3, n - (pos + 3));
@@ -645,82 +645,158 @@ __global__ void __launch_bounds__(256) k_lz_fixup2(EncDev E, uint32_t slice) {
 // =============================================================================== K3 parse_exits
 // Greedy walk i -> i + step(i), step = match length or 1.  For a tile [ts,te) and each of the <= 258
 // positions a previous tile can jump into, exit = (first position >= te reached) - te  (SURVEY App. C).
+// A warp handles 32 consecutive tiles, lane = tile: the right-to-left DP of a tile is serial, the 32 tiles are the parallelism.
+// md[] is read in chunks of 32 positions x 32 tiles: one fully coalesced 128-byte load per tile row (the next chunk is already in
+// flight while the current one is processed), transposed through shared memory (row stride 33 words: conflict free both ways).
+// The DP's ring of the last 260 exits lives in shared memory as [index][lane]; when the DP is done it holds the exits of positions
+// 0..259, i.e. the tile's exit table, which is written out tile by tile with contiguous stores.
 constexpr uint32_t kRing = 260;
-__global__ void __launch_bounds__(64) k_parse_exits(EncDev E, uint32_t off, uint32_t lim) {
-    __shared__ uint16_t ring[64 * kRing];
-    const uint32_t tile = blockIdx.x * 64 + threadIdx.x + off;
-    if (tile >= lim) return;
-    const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
-    const ChunkDesc cd = E.chunks[c];
-    const uint32_t n = cd.len;
-    const uint32_t ts = (tile - E.tile0[c]) * kTile;
-    const uint32_t te = min(ts + kTile, n);
-    uint16_t *r = ring + threadIdx.x * kRing;
-    const uint32_t *__restrict__ m = E.md + cd.off;
-    uint16_t *__restrict__ xt = E.exit_tab + (uint64_t)tile * kExitW;
-    // right to left in groups of 8 positions (one 32-byte sector of md per thread); the next group is loaded before the
-    // current one is processed, so the DP never waits for HBM (the loads were 67 % of this kernel's stall samples)
-    uint32_t cur[8], nxt[8];
-    uint32_t i = te;
+constexpr uint32_t kPxWarps = 4;
+constexpr uint32_t kPxWarpSmem = 32 * 33 * 4 + kRing * 32 * 2 + 32 * 8 + 32 * 4;      // md chunk | ring | row pointers | row lengths
+constexpr uint32_t kPxSmem = kPxWarps * kPxWarpSmem;
+__global__ void __launch_bounds__(kPxWarps * 32) k_parse_exits(EncDev E, uint32_t off, uint32_t lim) {
+    extern __shared__ __align__(16) uint8_t pxs[];
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t tile_base = off + (blockIdx.x * kPxWarps + w) * 32u;
+    if (tile_base >= lim) return;
+    uint8_t *ws = pxs + w * kPxWarpSmem;
+    uint32_t *mds = reinterpret_cast<uint32_t *>(ws);                                  // [32][33]
+    uint16_t *ring = reinterpret_cast<uint16_t *>(ws + 32 * 33 * 4);                   // [kRing][32]
+    const uint32_t **rowp = reinterpret_cast<const uint32_t **>(ws + 32 * 33 * 4 + kRing * 32 * 2);
+    uint32_t *rowlen = reinterpret_cast<uint32_t *>(ws + 32 * 33 * 4 + kRing * 32 * 2 + 32 * 8);
+    const uint32_t tile = tile_base + lane;
+    uint32_t len = 0;                                                                  // positions of this lane's tile (0: no tile)
+    const uint32_t *mrow = E.md;
+    if (tile < lim) {
+        const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
+        const ChunkDesc cd = E.chunks[c];
+        const uint32_t ts = (tile - E.tile0[c]) * kTile;
+        len = min(kTile, cd.len - ts);
+        mrow = E.md + cd.off + ts;
+    }
+    rowp[lane] = mrow; rowlen[lane] = len;
+    __syncwarp();
+    const uint32_t maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
+    uint32_t ridx = len ? (len - 1) % kRing : 0u;                                      // ring index of the position the DP handles next
+    uint32_t prev_ex = 0;                                                              // exit of position p + 1 (literal steps need no ring read)
+    uint32_t cur[32], nxt[32];
+    int32_t j = (int32_t)((maxlen + 31) / 32) - 1;                                     // chunk = positions [32 j, 32 j + 32) of every tile
 #pragma unroll
-    for (uint32_t k = 0; k < 8; k++) cur[k] = (i >= ts + 1 + k) ? m[i - 1 - k] : 0u;
-    while (i > ts) {
-        const uint32_t g = min(8u, i - ts);
-        const uint32_t i2 = i - g;
+    for (uint32_t r = 0; r < 32; r++) cur[r] = (uint32_t)(32 * j) + lane < rowlen[r] ? __ldg(rowp[r] + 32 * j + lane) : 0u;
+    for (; j >= 0; j--) {
+        if (j > 0) {
 #pragma unroll
-        for (uint32_t k = 0; k < 8; k++) nxt[k] = (i2 >= ts + 1 + k) ? m[i2 - 1 - k] : 0u;
-#pragma unroll
-        for (uint32_t k = 0; k < 8; k++) {
-            if (k < g) {
-                const uint32_t p = i - 1 - k;
-                const uint32_t v = cur[k];
-                const uint32_t nx = p + (v ? (v >> 16) : 1u);
-                uint32_t ex;
-                if (nx >= te) ex = nx - te; else ex = r[(nx - ts) % kRing];
-                r[(p - ts) % kRing] = (uint16_t)ex;
-                if (p - ts < kExitW) xt[p - ts] = (uint16_t)ex;
-            }
+            for (uint32_t r = 0; r < 32; r++) nxt[r] = (uint32_t)(32 * (j - 1)) + lane < rowlen[r] ? __ldg(rowp[r] + 32 * (j - 1) + lane) : 0u;
         }
 #pragma unroll
-        for (uint32_t k = 0; k < 8; k++) cur[k] = nxt[k];
-        i = i2;
+        for (uint32_t r = 0; r < 32; r++) mds[r * 33 + lane] = cur[r];
+        __syncwarp();
+        if ((uint32_t)(32 * j) < len) {
+            const uint32_t kmax = min(32u, len - 32u * (uint32_t)j);
+            for (uint32_t k = kmax; k-- > 0;) {
+                const uint32_t p = 32u * (uint32_t)j + k;
+                const uint32_t v = mds[lane * 33 + k];
+                const uint32_t step = (v >> 16) ? (v >> 16) : 1u;
+                const uint32_t nx = p + step;
+                uint32_t ex;
+                if (nx >= len) ex = nx - len;
+                else if (step == 1) ex = prev_ex;
+                else { uint32_t ix = ridx + step; if (ix >= kRing) ix -= kRing; ex = ring[ix * 32 + lane]; }
+                ring[ridx * 32 + lane] = (uint16_t)ex;
+                prev_ex = ex;
+                ridx = ridx ? ridx - 1 : kRing - 1;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (uint32_t r = 0; r < 32; r++) cur[r] = nxt[r];
+    }
+    // ring[i][lane] = exit of position i for i < min(len, 260): the exit tables, one tile after the other
+    for (uint32_t r = 0; r < 32; r++) {
+        const uint32_t lr = rowlen[r];
+        if (!lr) break;
+        uint16_t *__restrict__ xt = E.exit_tab + (uint64_t)(tile_base + r) * kExitW;
+        for (uint32_t i = lane; i < min(kExitW, lr); i += 32) xt[i] = ring[i * 32 + r];
     }
 }
 
 // =============================================================================== K4 parse_stitch
-__global__ void __launch_bounds__(64) k_parse_stitch(EncDev E, uint32_t off, uint32_t lim) {
-    const uint32_t c = blockIdx.x * 64 + threadIdx.x + off;
+// entry[t + 1] = exit_tab[t][entry[t]]: a serial chain over the tiles of a chunk.  One warp per chunk: the exit tables of 32
+// tiles at a time are fetched with coalesced loads into shared memory, then the 32 chain steps are shared-memory reads
+// (they were dependent L2 loads, ~0.7 us each, 256 per 256 KiB chunk).
+constexpr uint32_t kStWarps = 4;
+constexpr uint32_t kStRowWords = kExitW / 2;                                  // 129 words per exit table
+constexpr uint32_t kStSmem = kStWarps * 32 * kStRowWords * 4;
+static_assert(kExitW % 2 == 0, "exit tables are copied as 32-bit words");
+__global__ void __launch_bounds__(kStWarps * 32) k_parse_stitch(EncDev E, uint32_t off, uint32_t lim) {
+    extern __shared__ __align__(16) uint32_t sts[];
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t c = off + blockIdx.x * kStWarps + w;
     if (c >= lim) return;
+    uint32_t *rows = sts + w * 32 * kStRowWords;
+    const uint16_t *rows16 = reinterpret_cast<const uint16_t *>(rows);
     const uint32_t t0 = E.tile0[c], t1 = E.tile0[c + 1];
     uint32_t p = 0;
-    for (uint32_t t = t0; t < t1; t++) {
-        E.tile_entry[t] = (uint16_t)p;
-        if (t + 1 < t1) p = E.exit_tab[(uint64_t)t * kExitW + p];
+    for (uint32_t tb = t0; tb < t1; tb += 32) {
+        const uint32_t nr = min(32u, t1 - tb);
+        // the tables of tiles [tb, tb + nr) are contiguous: nr * 129 words (516-byte rows keep 4-byte alignment)
+        const uint32_t *__restrict__ src = reinterpret_cast<const uint32_t *>(E.exit_tab + (uint64_t)tb * kExitW);
+        for (uint32_t i = lane; i < nr * kStRowWords; i += 32) rows[i] = __ldg(src + i);
+        __syncwarp();
+        uint32_t mine = 0;
+        for (uint32_t r = 0; r < nr; r++) {                                   // uniform: every lane follows the chain, lane r keeps entry r
+            if (r == lane) mine = p;
+            p = rows16[r * kExitW + p];
+        }
+        if (lane < nr) E.tile_entry[tb + lane] = (uint16_t)mine;
+        __syncwarp();
     }
 }
 
 // =============================================================================== K5 parse_emit
+// CTA = 64 consecutive tiles of one chunk (one DEFLATE block => one histogram), warp = 32 tiles, lane = tile.  md[] is streamed
+// like in k_parse_exits (coalesced 128-byte rows, transposed through shared memory, next chunk in flight); each lane walks its
+// tile from its entry point, emits the symbols and counts them in the CTA's shared-memory histogram.
+constexpr uint32_t kPeWarpSmem = 32 * 33 * 4;
 __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
     __shared__ uint32_t sh[kHistStride];
+    __shared__ __align__(16) uint32_t pes[2 * kPeWarpSmem / 4];
     const uint32_t grp = blockIdx.x + off;
     const uint32_t c = find_owner(E.grp0, E.n_chunks, grp);
     const ChunkDesc cd = E.chunks[c];
     for (uint32_t i = threadIdx.x; i < kHistStride; i += 64) sh[i] = 0;
     __syncthreads();
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t *mds = pes + w * (kPeWarpSmem / 4);                               // [32][33]
     const uint32_t n = cd.len;
-    const uint32_t tk = (grp - E.grp0[c]) * kGrpTiles + threadIdx.x;      // tile index inside the chunk
     const uint32_t ntile_c = E.tile0[c + 1] - E.tile0[c];
-    if (tk < ntile_c) {
-        const uint32_t tile = E.tile0[c] + tk;
-        const uint32_t ts = tk * kTile, te = min(ts + kTile, n);
-        const uint32_t *__restrict__ m = E.md + cd.off;
-        const uint8_t *__restrict__ p = E.in + cd.off;
-        uint32_t *__restrict__ so = E.sym + cd.off + ts;
-        uint32_t i = ts + E.tile_entry[tile], cnt = 0;
-        while (i < te) {
-            const uint32_t v = m[i];
-            const uint32_t b = p[i];
-            if (v) {
+    const uint32_t tkb = (grp - E.grp0[c]) * kGrpTiles + w * 32u;             // first tile (index inside the chunk) of this warp
+    const uint32_t tk = tkb + lane;
+    const bool valid = tk < ntile_c;
+    const uint32_t tile = E.tile0[c] + tk;
+    const uint32_t ts = tk * kTile;
+    const uint32_t len = valid ? min(kTile, n - ts) : 0u;
+    const uint32_t *__restrict__ mbase = E.md + cd.off + (uint64_t)tkb * kTile;          // row r starts at mbase + r * kTile
+    uint32_t *__restrict__ so = E.sym + cd.off + ts;
+    uint32_t i = valid ? E.tile_entry[tile] : 0u, cnt = 0;
+    const uint32_t wlen = tkb < ntile_c ? min(32u * kTile, n - tkb * kTile) : 0u;        // positions of the warp's 32 tiles
+    auto rowlen = [&](uint32_t r) { return wlen > r * kTile ? min(kTile, wlen - r * kTile) : 0u; };
+    const uint32_t nchunk = (min(kTile, wlen) + 31) / 32;
+    uint32_t cur[32], nxt[32];
+#pragma unroll
+    for (uint32_t r = 0; r < 32; r++) cur[r] = lane < rowlen(r) ? __ldg(mbase + r * kTile + lane) : 0u;
+    for (uint32_t j = 0; j < nchunk; j++) {
+        if (j + 1 < nchunk) {
+#pragma unroll
+            for (uint32_t r = 0; r < 32; r++) nxt[r] = 32 * (j + 1) + lane < rowlen(r) ? __ldg(mbase + r * kTile + 32 * (j + 1) + lane) : 0u;
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < 32; r++) mds[r * 33 + lane] = cur[r];
+        __syncwarp();
+        const uint32_t cend = min(len, 32 * (j + 1));
+        while (i < cend) {
+            const uint32_t v = mds[lane * 33 + (i - 32 * j)];
+            if (v >> 16) {
                 uint32_t lc, le, lx, dc, de, dx;
                 length_code(v >> 16, lc, le, lx);
                 dist_code(v & 0xFFFFu, dc, de, dx);
@@ -729,16 +805,19 @@ __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
                 so[cnt++] = kSymPtr | v;
                 i += v >> 16;
             } else {
-                atomicAdd(&sh[b], 1u);
-                so[cnt++] = b;
+                atomicAdd(&sh[v & 0xFFu], 1u);
+                so[cnt++] = v & 0xFFu;
                 i += 1;
             }
         }
-        E.tile_nsym[tile] = cnt;
+        __syncwarp();
+#pragma unroll
+        for (uint32_t r = 0; r < 32; r++) cur[r] = nxt[r];
     }
+    if (valid) E.tile_nsym[tile] = cnt;
     __syncthreads();
     uint32_t *__restrict__ gh = E.hist + (uint64_t)cd.block * kHistStride;
-    for (uint32_t i = threadIdx.x; i < 316; i += 64) if (sh[i]) atomicAdd(&gh[i], sh[i]);
+    for (uint32_t k = threadIdx.x; k < 316; k += 64) if (sh[k]) atomicAdd(&gh[k], sh[k]);
 }
 
 // =============================================================================== K6 huff_build
@@ -969,6 +1048,10 @@ cudaError_t enc_init_attributes() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_lz_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_parse_exits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPxSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_parse_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmem);
+    if (e != cudaSuccess) return e;
     if (const char *v = getenv("B2F_LZ_FUSED")) g_lz_fused = atoi(v) != 0;          // 0 = k_lz_chain + k_lz_match (A/B and fallback)
     e = cudaFuncSetAttribute(k_bitpack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kPackWords * 4));
     return e;
@@ -994,9 +1077,9 @@ static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, 
         k_lz_match<<<npt, 512, kMatchSmem, st>>>(E, h_pt0[c0]); B2F_LAUNCH_CHECK();
     }
     if (tm) tm->mark(st, "parse_exits");
-    k_parse_exits<<<(nt + 63) / 64, 64, 0, st>>>(E, h_tile0[c0], h_tile0[c1]); B2F_LAUNCH_CHECK();
+    k_parse_exits<<<(nt + 32 * kPxWarps - 1) / (32 * kPxWarps), kPxWarps * 32, kPxSmem, st>>>(E, h_tile0[c0], h_tile0[c1]); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_stitch");
-    k_parse_stitch<<<(c1 - c0 + 63) / 64, 64, 0, st>>>(E, c0, c1); B2F_LAUNCH_CHECK();
+    k_parse_stitch<<<(c1 - c0 + kStWarps - 1) / kStWarps, kStWarps * 32, kStSmem, st>>>(E, c0, c1); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "parse_emit");
     k_parse_emit<<<ng, 64, 0, st>>>(E, h_grp0[c0]); B2F_LAUNCH_CHECK();
     return cudaSuccess;

@@ -15,6 +15,7 @@ constexpr uint32_t kSegBytes = B2F_SEG_BYTES;   // output bytes per segment slot
 constexpr uint32_t kSegRing = 8192;       // symbols of a segment kept in shared memory by k_seg_resolve
 constexpr uint32_t kSegStepMax = 4096;    // output symbols of one 32-token step (a step with more output is cut short)
 constexpr uint32_t kMarker = 0x8000u;
+constexpr uint32_t kMaxParts = 8;         // pipeline depth of the LZ77 resolution (part p's output is copied out while part p+1 is resolved)
 struct SpecDev {
     const uint8_t *in; const uint64_t *in_off, *in_len;             // members
     uint32_t n_blocks;                                              // candidate blocks, sorted by (member, bit)
@@ -38,12 +39,16 @@ struct SpecDev {
     uint32_t *seg_ntok, *seg_nout;                                  // per slot: tokens / output bytes (0 = empty slot)
     uint32_t *seg_member, *seg_reach;                               // per slot: member; how far before its first byte its matches reach (0 = self-contained)
     uint8_t *seg_cut;                                               // per slot: 1 = no segment from here on reads anything before this one (chain start)
+    uint4 *seg_rec;                                                 // [n_slots + 2] packed copy for k_seg_subst: out offset lo/hi, bytes, cut | member << 1
+    uint32_t *chain_list;                                           // [n_slots] chain starts, grouped by part (part p from part_slot0[p])
+    uint32_t *chain_count;                                          // [2 * kMaxParts] zeroed: chains per part | next chain to take per part
+    uint32_t n_parts, part_slot0[kMaxParts + 1];                    // parts = slot ranges that are resolved, substituted and copied out one after the other
     uint16_t *sym16;                                                // [out span] resolved symbol or marker of every output byte (indexed like out)
     uint32_t *mem_err;                                              // per member: 1 inconsistent size, 2 match reaches before the member's first byte
 };
 cudaError_t spec_init_attributes();
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st);
-cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st);
-cudaError_t spec_launch_segments(const SpecDev &S, cudaStream_t st);              // k_seg_plan + k_seg_resolve + k_seg_cuts
-cudaError_t spec_launch_subst(const SpecDev &S, uint32_t s0, uint32_t s1, cudaStream_t st);   // k_seg_subst over the chains that start in slots [s0, s1)
+cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t cta_lo, uint32_t cta_hi, cudaStream_t st);   // CTAs (128 subsegments each) [cta_lo, cta_hi)
+cudaError_t spec_launch_segments(const SpecDev &S, uint32_t part, cudaStream_t st);   // k_seg_plan + k_seg_resolve + k_seg_cuts over the part's slots
+cudaError_t spec_launch_subst(const SpecDev &S, uint32_t part, cudaStream_t st);      // k_seg_subst over the chains that start in the part
 }

@@ -282,14 +282,15 @@ __global__ void __launch_bounds__(256) k_spec_verify(SpecDev S) {
 }
 
 // ---------------------------------------------------------------------------------- final decode -> tokens
-__global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
+__global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S, uint32_t cta_off) {
     __shared__ __align__(16) InflateTables Ts;
     __shared__ __align__(16) uint32_t stage[kSpecCta * 8];
-    const uint32_t b = owner_u32(S.blk_cta0, S.n_blocks, blockIdx.x);
+    const uint32_t cta = blockIdx.x + cta_off;
+    const uint32_t b = owner_u32(S.blk_cta0, S.n_blocks, cta);
     if (S.blk_sel[b] == 0) return;                               // not on the verified chain
     load_tables_smem(Ts, S.tabs + b);
     const uint32_t data_rel = S.blk_data_rel[b];
-    const uint32_t k = (blockIdx.x - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
+    const uint32_t k = (cta - S.blk_cta0[b]) * kSpecCta + threadIdx.x;
     const uint32_t k0 = data_rel / kSpecBits, e = S.blk_eob_seg[b];
     const bool mine = k >= k0 && k <= e;
     const uint32_t sg = S.blk_seg0[b] + (mine ? k : k0);
@@ -328,9 +329,9 @@ __global__ void __launch_bounds__(kSpecCta) k_spec_tokens(SpecDev S) {
 //                byte it points at (all targets lie before the segment, i.e. are final) out of a shared-memory window.
 // The serial dependency of the reference is thereby reduced to one barrier per segment inside a chain; everything else -- the
 // whole token walk -- runs on thousands of independent warps.  Cross-block references (zlib / gzip output) are ordinary markers.
-__global__ void __launch_bounds__(128) k_seg_plan(SpecDev S) {
-    const uint32_t slot = blockIdx.x * 128 + threadIdx.x;
-    if (slot >= S.n_slots) return;
+__global__ void __launch_bounds__(128) k_seg_plan(SpecDev S, uint32_t slot_lo, uint32_t slot_hi) {
+    const uint32_t slot = slot_lo + blockIdx.x * 128 + threadIdx.x;
+    if (slot >= slot_hi) return;
     const uint32_t k = owner_u32(S.sel_slot0, S.n_sel, slot);
     const uint32_t b = S.sel_blocks[k], j = slot - S.sel_slot0[k];
     const uint32_t s0 = S.blk_seg0[b], k0 = S.blk_data_rel[b] / kSpecBits, e = S.blk_eob_seg[b];
@@ -353,19 +354,20 @@ __global__ void __launch_bounds__(128) k_seg_plan(SpecDev S) {
 }
 
 constexpr uint32_t kSegMask = kSegRing - 1;
+constexpr uint32_t kSegLazy = 2048;                               // symbols that may wait in the ring before they are written to sym16
 constexpr uint32_t kSegFreeQ = 2 * kSegRing;                     // byte offset of the queue of order-free copies (<= 64 entries + 4 read-ahead)
 constexpr uint32_t kSegOrdQ = kSegFreeQ + 68 * 8;                // byte offset of the queue of in-order copies (<= 32 entries + 2 read-ahead)
 constexpr uint32_t kSegSmem = kSegOrdQ + 34 * 8;
-static_assert((kSegRing & kSegMask) == 0 && kSegStepMax + 258 + 8 < kSegRing, "segment ring geometry");
+static_assert((kSegRing & kSegMask) == 0 && kSegStepMax + kSegLazy + 258 + 8 < kSegRing, "segment ring geometry");
 
 // ceil(65536 / p): k mod p == k - p * ((k * inv) >> 16) for p < 32, k < 400 (run-length matches; avoids a division per symbol)
 __constant__ uint32_t kInvPeriod[32] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
 
-__global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
+__global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S, uint32_t slot_lo) {
     extern __shared__ __align__(16) uint8_t seg_smem[];
     uint16_t *ring = reinterpret_cast<uint16_t *>(seg_smem);          // symbol of segment position p at (a0 + p) & kSegMask
     uint2 *fq = reinterpret_cast<uint2 *>(seg_smem + kSegFreeQ), *oq = reinterpret_cast<uint2 *>(seg_smem + kSegOrdQ);
-    const uint32_t lane = threadIdx.x, slot = blockIdx.x;
+    const uint32_t lane = threadIdx.x, slot = blockIdx.x + slot_lo;
     const uint32_t nout = S.seg_nout[slot];
     if (!nout) return;
     const uint32_t ntok = S.seg_ntok[slot];
@@ -456,9 +458,11 @@ __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
             }
             __syncwarp();
         }
-        // ---- write the finished 8-symbol groups through to sym16 (16-byte stores)
+        // ---- write the finished 8-symbol groups through to sym16 (16-byte stores), once enough of them have piled up: at the
+        // start of a step less than kSegLazy symbols are unwritten, so the ring (step output <= kSegStepMax) never overwrites them
+        // and a far source (older than pos + total - kSegRing) is always in sym16
         pos += total;
-        if (pos >= lead) {
+        if (pos >= lead && pos - flushed >= kSegLazy) {
             if (flushed < lead) {                                     // the unaligned head, once
                 if (lane < lead) gsym[lane] = ring[(a0 + lane) & kSegMask];
                 flushed = lead;
@@ -474,140 +478,223 @@ __global__ void __launch_bounds__(32) k_seg_resolve(SpecDev S) {
         i0 += take;
         __syncwarp();
     }
-    for (uint32_t k = flushed + lane; k < pos; k += 32) gsym[k] = ring[(a0 + k) & kSegMask];    // the tail
+    if (pos >= lead) {                                                // what is left: head, whole groups, then the tail symbol by symbol
+        if (flushed < lead) { if (lane < lead) gsym[lane] = ring[(a0 + lane) & kSegMask]; flushed = lead; }
+        const uint32_t target = pos - ((pos - lead) & 7u);
+        for (uint32_t g = lane; g < ((target - flushed) >> 3); g += 32)
+            *reinterpret_cast<uint4 *>(gsym + flushed + 8u * g) = *reinterpret_cast<const uint4 *>(ring + ((a0 + flushed + 8u * g) & kSegMask));
+        flushed = target;
+    }
+    for (uint32_t k = flushed + lane; k < pos; k += 32) gsym[k] = ring[(a0 + k) & kSegMask];
     if (pos != nout) err |= 1u;
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     reach = __reduce_max_sync(0xFFFFFFFFu, reach);
     if (lane == 0) { S.seg_reach[slot] = reach; if (err) atomicOr(S.mem_err + mem, err); }
 }
 
-// seg_cut[c] = 1 when no segment at or after c reads a byte before c's first one (only segments that start less than 32 KiB
-// after it can).  A member's first segment is a cut by construction (a reach before it is an error, flagged by k_seg_resolve).
-__global__ void __launch_bounds__(128) k_seg_cuts(SpecDev S) {
-    const uint32_t c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= S.n_slots || !S.seg_nout[c]) return;
+// seg_cut[c] = 1 when no segment at or after c (inside c's part) reads a byte before c's first one -- only segments that start
+// less than 32 KiB after it can.  A member's first segment is a cut by construction (a reach before it is an error, flagged by
+// k_seg_resolve).  The first segment of a part starts a chain in any case: the parts are processed one after the other, so
+// everything before it is final and its CTA preloads the window from out ("warm" start).
+// Also packs what k_seg_subst needs of a slot into one 16-byte record (out offset, bytes | warm << 31, start | member << 1) and
+// appends every chain start to the list of its part.
+__global__ void __launch_bounds__(128) k_seg_cuts(SpecDev S, uint32_t part) {
+    const uint32_t lo = S.part_slot0[part], hi = S.part_slot0[part + 1];
+    const uint32_t c = lo + blockIdx.x * 128 + threadIdx.x;
+    if (c >= hi) return;
     const uint64_t A = S.seg_out[c];
-    const uint32_t m = S.seg_member[c];
-    bool cut = true;
-    for (uint32_t s = c; s < S.n_slots && S.seg_member[s] == m; s++) {
-        if (!S.seg_nout[s]) continue;
-        const uint64_t o = S.seg_out[s];
-        if (o >= A + 32768u) break;
-        if ((uint64_t)S.seg_reach[s] > o - A) { cut = false; break; }
+    const uint32_t m = S.seg_member[c], n = S.seg_nout[c];
+    bool cut = n != 0;
+    if (n) {
+        for (uint32_t s = c; s < hi && S.seg_member[s] == m; s++) {
+            if (!S.seg_nout[s]) continue;
+            const uint64_t o = S.seg_out[s];
+            if (o >= A + 32768u) break;
+            if ((uint64_t)S.seg_reach[s] > o - A) { cut = false; break; }
+        }
     }
-    S.seg_cut[c] = cut ? 1 : 0;
+    bool first = n != 0;                                              // first non-empty slot of the part?
+    for (uint32_t s = c; first && s > lo; s--) if (S.seg_nout[s - 1]) first = false;
+    const bool warm = first && !cut;
+    S.seg_cut[c] = (cut || first) ? 1 : 0;
+    S.seg_rec[c] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), n | (warm ? 0x80000000u : 0u), ((cut || first) ? 1u : 0u) | (m << 1));
+    if (cut || first) S.chain_list[lo + atomicAdd(S.chain_count + part, 1u)] = c;
 }
 
-// One CTA per chain (the slots from a cut up to the next cut of the same member).  The last kSubRing final bytes of the chain are
-// kept in shared memory at index (offset - base) mod kSubRing, base = chain start rounded down to 16, so that aligned 16-byte
-// groups of out are aligned groups of the window.  The chain is walked in BATCHES of one segment's bytes that span at most
-// kSubBatch / 16 aligned 16-byte groups (two per thread); the symbols of the next batch are loaded before the current one is processed, and the sixteen
-// window reads of a group are issued unconditionally (no divergent branch per symbol), so a batch costs about one barrier.
-constexpr uint32_t kSubThreads = 256, kSubRing = 49152, kSubBatch = 8192;
-static_assert(kSubBatch / 16 == 2 * kSubThreads, "two groups per thread and batch");
-struct SubBatch { uint64_t A, B; uint32_t bl, s, rA, rB; bool valid; };   // segment start, batch start, batch bytes, slot, window indices of A and B
+// Persistent CTAs take chains (the slots from a cut up to the next cut of the same member) from the part's list.  The last
+// kSubRing final bytes of the chain are kept in shared memory at index (offset - base) mod kSubRing, base = chain start rounded
+// down to 16, so that aligned 16-byte groups of out are aligned groups of the window.  The chain is walked slot by slot, one
+// 16-byte group per thread; everything the next step needs is requested one step ahead (the slot records two steps ahead, the
+// symbols one), and the sixteen window reads of a group are issued unconditionally, so a step costs little more than its barrier.
+constexpr uint32_t kSubThreads = 512, kSubRing = 49152, kSubGroups = kSubThreads;
+__device__ __forceinline__ uint32_t sub_cap(uint64_t B) { return kSubGroups * 16u - ((uint32_t)B & 15u); }   // bytes of one step from offset B
 
-__global__ void __launch_bounds__(kSubThreads, 4) k_seg_subst(SpecDev S, uint32_t slot_off) {
-    extern __shared__ __align__(16) uint8_t win[];
-    const uint32_t c = blockIdx.x + slot_off, tid = threadIdx.x;
-    if (!S.seg_nout[c] || !S.seg_cut[c]) return;
-    const uint32_t m = S.seg_member[c];
-    if (S.mem_err[m]) return;                                         // the member goes to the in-order kernel: markers may point anywhere
+// one step: bytes [B, B + bl) of the segment that starts at A.  kFirst: B == A (every marker target is still in the window).
+template <bool kFirst>
+__device__ __forceinline__ void sub_step(uint8_t *out, uint8_t *win, bool vec, uint64_t A, uint64_t B, uint32_t bl, uint32_t rA, uint32_t rB,
+                                         const uint4 xa, const uint4 xb, uint32_t tid) {
+    const uint32_t lead16 = (uint32_t)B & 15u;
+    const uint32_t ng = (lead16 + bl + 15u) >> 4;
+    if (tid >= ng) return;
+    const uint64_t p = (B - lead16) + 16ull * tid;                    // offset in out of this thread's 16-byte group
+    uint32_t rp = rB + 16u * tid + kSubRing - lead16;                 // window index of p (p may lie below B: + kSubRing first)
+    rp -= rp >= 2 * kSubRing ? 2 * kSubRing : rp >= kSubRing ? kSubRing : 0u;
+    const int32_t thr = kFirst ? 0x7FFF : (int32_t)kSubRing - 1 - (int32_t)(B - A) - (int32_t)bl;   // markers above it have left the window
+    const uint32_t w[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
+    uint32_t v[16], t[16];
+#pragma unroll
+    for (uint32_t q = 0; q < 16; q++) {
+        v[q] = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+        int32_t r = (int32_t)rA - 1 - (int32_t)(v[q] & 0x7FFFu);
+        r += (r >> 31) & (int32_t)kSubRing;
+        t[q] = win[r];                                                // unconditional: the index is always inside the window
+    }
+    const uint32_t lo = tid == 0 ? lead16 : 0u;                       // symbols [lo, hi) of the group belong to the step
+    const uint32_t hi = min(16u, lead16 + bl - 16u * tid);
+    if (!kFirst) {
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++)                             // (steps after the first of a long segment only)
+            if (q >= lo && q < hi && (v[q] & kMarker) && (int32_t)(v[q] & 0x7FFFu) > thr) t[q] = out[A - 1 - (uint64_t)(v[q] & 0x7FFFu)];
+    }
+    uint32_t o[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (uint32_t q = 0; q < 16; q++) {
+        v[q] = ((v[q] & kMarker) ? t[q] : v[q]) & 0xFFu;
+        o[q >> 2] |= v[q] << (8u * (q & 3u));
+    }
+    if (lo == 0 && hi == 16) {
+        const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(win + rp) = ov;
+        if (vec) *reinterpret_cast<uint4 *>(out + p) = ov;
+        else {
+#pragma unroll
+            for (uint32_t q = 0; q < 16; q++) out[p + q] = (uint8_t)v[q];
+        }
+    } else {
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++)
+            if (q >= lo && q < hi) { out[p + q] = (uint8_t)v[q]; uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing; win[r] = (uint8_t)v[q]; }
+    }
+}
+__device__ __forceinline__ void sub_load(const uint16_t *__restrict__ sym, uint64_t B, uint32_t bl, uint32_t tid, uint4 &xa, uint4 &xb) {
+    const uint32_t lead16 = (uint32_t)B & 15u;
+    if (tid < ((lead16 + bl + 15u) >> 4)) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(sym + (B - lead16) + 16ull * tid);
+        xa = __ldg(p); xb = __ldg(p + 1);
+    }
+}
+// mbarrier + bulk-copy (TMA engine, 1-D) helpers: the symbols of the next segments are fetched into shared memory by the copy
+// engine while the CTA works on the current one; no thread waits for HBM on the critical path
+__device__ __forceinline__ void sb_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void sb_expect(uint32_t a, uint32_t bytes) { asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(a), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void sb_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void sb_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+constexpr uint32_t kSubStages = 4;                                    // segments in flight (symbols prefetched by the copy engine)
+constexpr uint32_t kSubStageBytes = kSubGroups * 32;                  // 16 symbols (32 bytes) per thread
+constexpr uint32_t kSubSmem = kSubRing + kSubStages * kSubStageBytes + kSubStages * 16 + kSubStages * 8 + 16;   // window | stages | descriptors | mbarriers | chain
+
+__global__ void __launch_bounds__(kSubThreads, 2) k_seg_subst(SpecDev S, uint32_t part) {
+    extern __shared__ __align__(128) uint8_t ssm[];
+    uint8_t *win = ssm;
+    uint8_t *stage = ssm + kSubRing;
+    uint4 *desc = reinterpret_cast<uint4 *>(ssm + kSubRing + kSubStages * kSubStageBytes);          // record of the slot each stage holds
+    const uint32_t mb_a = (uint32_t)__cvta_generic_to_shared(ssm + kSubRing + kSubStages * kSubStageBytes + kSubStages * 16);
+    uint32_t *chain_s = reinterpret_cast<uint32_t *>(ssm + kSubRing + kSubStages * kSubStageBytes + kSubStages * 16 + kSubStages * 8);
+    const uint32_t stage_a = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t tid = threadIdx.x;
     uint8_t *out = S.out;                                             // read back by later segments of the chain: no __restrict__
     const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     const uint16_t *__restrict__ sym = S.sym16;
-    // the batch after `b` (every thread computes the same walk: a few cached loads per segment)
-    auto advance = [&](const SubBatch &b) {
-        SubBatch n = b;
-        const uint32_t segn = S.seg_nout[b.s];
-        const uint64_t done = b.B + b.bl - b.A;
-        if (done < segn) {                                            // next batch of the same (long) segment
-            n.B = b.B + b.bl; n.bl = (uint32_t)min((uint64_t)(kSubBatch - ((uint32_t)n.B & 15u)), segn - done);
-            n.rB = b.rB + b.bl; if (n.rB >= kSubRing) n.rB -= kSubRing;
-            return n;
-        }
-        uint32_t rA = b.rB + b.bl; if (rA >= kSubRing) rA -= kSubRing;
-        for (uint32_t s = b.s + 1; s < S.n_slots; s++) {
-            const uint32_t nn = S.seg_nout[s];
-            if (!nn) continue;
-            if (S.seg_cut[s] || S.seg_member[s] != m) break;
-            n.s = s; n.A = n.B = S.seg_out[s]; n.bl = min(kSubBatch - ((uint32_t)n.B & 15u), nn); n.rA = n.rB = rA;
-            return n;
-        }
-        n.valid = false;
-        return n;
-    };
-    // the 2 x 16 symbols of this thread's groups of batch b (aligned on the offset in out; symbols outside the batch are ignored)
-    auto load = [&](const SubBatch &b, uint4 *x) {
-        const uint64_t g0 = b.B & ~15ull;
-        const uint32_t ng = (uint32_t)((b.B + b.bl + 15 - g0) >> 4);
-#pragma unroll
-        for (uint32_t u = 0; u < 2; u++) {
-            const uint32_t g = tid + u * kSubThreads;
-            if (g < ng) { const uint4 *p = reinterpret_cast<const uint4 *>(sym + g0 + 16ull * g); x[2 * u] = __ldg(p); x[2 * u + 1] = __ldg(p + 1); }
-        }
-    };
-    SubBatch cur;
-    cur.s = c; cur.A = cur.B = S.seg_out[c]; cur.bl = min(kSubBatch - ((uint32_t)cur.B & 15u), S.seg_nout[c]); cur.rA = cur.rB = (uint32_t)cur.A & 15u; cur.valid = true;
-    uint4 x[4], y[4];
-    load(cur, x);
-    while (cur.valid) {
-        const SubBatch nxt = advance(cur);
-        if (nxt.valid) load(nxt, y);
-        // marker value mm (distance before A, minus 1) is still in the window iff A-1-mm >= B+bl-kSubRing
-        const int32_t thr = (int32_t)kSubRing - 1 - (int32_t)(cur.B - cur.A) - (int32_t)cur.bl;
-        const uint64_t g0 = cur.B & ~15ull;
-        const uint32_t lead16 = (uint32_t)(cur.B - g0);
-        const uint32_t ng = (uint32_t)((cur.B + cur.bl + 15 - g0) >> 4);
-#pragma unroll 1
-        for (uint32_t u = 0; u < 2; u++) {
-            const uint32_t g = tid + u * kSubThreads;
-            if (g < ng) {
-                const uint64_t p = g0 + 16ull * g;                    // offset in out of this 16-byte group
-                uint32_t rp = cur.rB + 16u * g + kSubRing - lead16;   // window index of p (p may lie below B: + kSubRing first)
-                rp -= (rp / kSubRing) * kSubRing;
-                const uint4 xa = u ? x[2] : x[0], xb = u ? x[3] : x[1];
-                const uint32_t w[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
-                uint32_t v[16], t[16];
-#pragma unroll
-                for (uint32_t q = 0; q < 16; q++) {
-                    v[q] = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
-                    int32_t r = (int32_t)cur.rA - 1 - (int32_t)(v[q] & 0x7FFFu);
-                    if (r < 0) r += (int32_t)kSubRing;
-                    t[q] = win[r];                                    // unconditional: the index is always inside the window
-                }
-                const uint32_t lo = p < cur.B ? lead16 : 0u;          // symbols [lo, hi) of the group belong to the batch
-                const uint32_t hi = (uint32_t)min((uint64_t)16, cur.B + cur.bl - p);
-                uint32_t o[4] = { 0, 0, 0, 0 };
-#pragma unroll
-                for (uint32_t q = 0; q < 16; q++) {
-                    uint32_t bv = v[q];
-                    if (bv & kMarker) {
-                        bv = t[q];
-                        if ((int32_t)(v[q] & 0x7FFFu) > thr && q >= lo && q < hi) bv = out[cur.A - 1 - (uint64_t)(v[q] & 0x7FFFu)];   // (long segments only)
-                    }
-                    v[q] = bv & 0xFFu;
-                    o[q >> 2] |= v[q] << (8u * (q & 3u));
-                }
-                if (lo == 0 && hi == 16) {
-                    const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4 *>(win + rp) = ov;
-                    if (vec) *reinterpret_cast<uint4 *>(out + p) = ov;
-                    else {
-#pragma unroll
-                        for (uint32_t q = 0; q < 16; q++) out[p + q] = (uint8_t)v[q];
-                    }
-                } else {
-#pragma unroll
-                    for (uint32_t q = 0; q < 16; q++)
-                        if (q >= lo && q < hi) { out[p + q] = (uint8_t)v[q]; uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing; win[r] = (uint8_t)v[q]; }
-                }
+    const uint4 *__restrict__ rec = S.seg_rec;                       // n_slots + 2 entries
+    const uint32_t *__restrict__ list = S.chain_list + S.part_slot0[part];
+    const uint32_t nchains = S.chain_count[part];
+    const uint32_t part_hi = S.part_slot0[part + 1];
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kSubStages; i++) sb_init(mb_a + 8u * i, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t uses = 0;                                                // completed uses of the stage ring (parity of stage k = (use / kSubStages) & 1)
+    for (;;) {
+        __syncthreads();                                              // the previous chain is done with the window, the stages and chain_s
+        if (tid == 0) *chain_s = atomicAdd(S.chain_count + kMaxParts + part, 1u);
+        __syncthreads();
+        if (*chain_s >= nchains) return;
+        const uint32_t c = list[*chain_s];
+        const uint4 rc = rec[c];
+        const uint32_t mem = rc.w >> 1;
+        if (S.mem_err[mem]) continue;                                 // the member goes to the in-order kernel: markers may point anywhere
+        uint32_t rA = rc.x & 15u;                                     // window index of the current segment's first byte
+        if (rc.z & 0x80000000u) {
+            // warm start (first chain of a later part): the 32 KiB before the segment are final in out -- preload them
+            const uint64_t A = rc.x | ((uint64_t)rc.y << 32), m0 = S.mem_out_off[mem];
+            const uint32_t back = (uint32_t)min((uint64_t)32768u, A - m0);
+            for (uint32_t k = tid; k < back; k += kSubThreads) {      // byte k+1 before A -> window index rA - 1 - k (mod kSubRing)
+                int32_t r = (int32_t)rA - 1 - (int32_t)k; r += (r >> 31) & (int32_t)kSubRing;
+                win[r] = out[A - 1 - k];
             }
         }
-        __syncthreads();
-        cur = nxt;
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) x[u] = y[u];
+        // frontier f: next slot to fetch; slots [s, f) are in flight.  Every thread walks the records identically (two of them are
+        // always on their way), thread 0 alone talks to the copy engine.
+        uint32_t sl = c, f = c;
+        bool open = true;
+        uint4 q0 = rc, q1 = rec[c + 1];                               // rec[f], rec[f + 1]
+        auto consider = [&]() {
+            const uint4 r = q0;
+            if (f != c && (f >= part_hi || (r.w & 1u) || (r.w >> 1) != mem)) { open = false; return; }
+            const uint32_t n = r.z & 0x7FFFFFFFu;
+            const uint32_t k = (f - c + uses) % kSubStages;
+            if (tid == 0) {
+                desc[k] = make_uint4(r.x, r.y, n, 0);
+                if (n) {
+                    const uint64_t A = r.x | ((uint64_t)r.y << 32);
+                    const uint32_t lead16 = (uint32_t)A & 15u;
+                    const uint32_t bytes = ((lead16 + min(n, sub_cap(A)) + 15u) >> 4) * 32u;
+                    sb_expect(mb_a + 8u * k, bytes);
+                    sb_bulk_g2s(stage_a + k * kSubStageBytes, sym + (A - lead16), bytes, mb_a + 8u * k);
+                } else sb_expect(mb_a + 8u * k, 0u);                  // an empty slot still completes its phase of the stage's barrier
+            }
+            q0 = q1; q1 = rec[f + 2]; f++;
+        };
+#pragma unroll 1
+        for (uint32_t i = 0; i < kSubStages && open; i++) consider();
+        __syncthreads();                                              // descriptors + warm window visible
+        while (sl < f) {
+            const uint32_t use = sl - c + uses, k = use % kSubStages;
+            const uint4 r0 = desc[k];
+            const uint32_t n = r0.z;
+            if (n) {
+                const uint64_t A = r0.x | ((uint64_t)r0.y << 32);
+                const uint32_t bl0 = min(n, sub_cap(A));
+                sb_wait(mb_a + 8u * k, (use / kSubStages) & 1u);
+                const uint4 *sp = reinterpret_cast<const uint4 *>(stage + k * kSubStageBytes) + 2 * tid;
+                const bool mine = tid < ((((uint32_t)A & 15u) + bl0 + 15u) >> 4);
+                const uint4 xa = mine ? sp[0] : make_uint4(0, 0, 0, 0), xb = mine ? sp[1] : make_uint4(0, 0, 0, 0);
+                sub_step<true>(out, win, vec, A, A, bl0, rA, rA, xa, xb, tid);
+                __syncthreads();
+                for (uint32_t b0 = bl0; b0 < n;) {                    // (segments longer than one step: highly compressible data)
+                    const uint64_t B = A + b0;
+                    const uint32_t bl = min(n - b0, sub_cap(B));
+                    uint32_t rB = rA + b0; rB -= (rB / kSubRing) * kSubRing;
+                    uint4 za = make_uint4(0, 0, 0, 0), zb = za;
+                    sub_load(sym, B, bl, tid, za, zb);
+                    sub_step<false>(out, win, vec, A, B, bl, rA, rB, za, zb, tid);
+                    __syncthreads();
+                    b0 += bl;
+                }
+                rA += n - (n / kSubRing) * kSubRing; if (rA >= kSubRing) rA -= kSubRing;
+            } else __syncthreads();                                   // (keeps descriptor reuse ordered for empty slots too)
+            sl++;
+            if (open) consider();                                     // refill the stage that was just released
+        }
+        uses += f - c;
     }
 }
 
@@ -617,7 +704,7 @@ cudaError_t spec_init_attributes() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_seg_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_seg_subst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubRing);
+    return cudaFuncSetAttribute(k_seg_subst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubSmem);
 }
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st) {
     if (!S.n_blocks) return cudaSuccess;
@@ -634,23 +721,25 @@ cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st
     k_spec_verify<<<S.n_blocks, 256, 0, st>>>(R);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t n_sel, cudaStream_t st) {
-    if (!n_sel) return cudaSuccess;
-    k_spec_tokens<<<S.n_ctas, kSpecCta, 0, st>>>(S);
+cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t cta_lo, uint32_t cta_hi, cudaStream_t st) {
+    if (cta_hi <= cta_lo) return cudaSuccess;
+    k_spec_tokens<<<cta_hi - cta_lo, kSpecCta, 0, st>>>(S, cta_lo);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_segments(const SpecDev &S, cudaStream_t st) {
-    if (!S.n_slots) return cudaSuccess;
-    k_seg_plan<<<(S.n_slots + 127) / 128, 128, 0, st>>>(S);
+cudaError_t spec_launch_segments(const SpecDev &S, uint32_t part, cudaStream_t st) {
+    const uint32_t lo = S.part_slot0[part], hi = S.part_slot0[part + 1];
+    if (hi <= lo) return cudaSuccess;
+    k_seg_plan<<<(hi - lo + 127) / 128, 128, 0, st>>>(S, lo, hi);
     cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
-    k_seg_resolve<<<S.n_slots, 32, kSegSmem, st>>>(S);
+    k_seg_resolve<<<hi - lo, 32, kSegSmem, st>>>(S, lo);
     e = cudaGetLastError(); if (e != cudaSuccess) return e;
-    k_seg_cuts<<<(S.n_slots + 127) / 128, 128, 0, st>>>(S);
+    k_seg_cuts<<<(hi - lo + 127) / 128, 128, 0, st>>>(S, part);
     return cudaGetLastError();
 }
-cudaError_t spec_launch_subst(const SpecDev &S, uint32_t s0, uint32_t s1, cudaStream_t st) {
-    if (s1 <= s0) return cudaSuccess;
-    k_seg_subst<<<s1 - s0, kSubThreads, kSubRing, st>>>(S, s0);
+cudaError_t spec_launch_subst(const SpecDev &S, uint32_t part, cudaStream_t st) {
+    if (part >= S.n_parts || S.part_slot0[part + 1] <= S.part_slot0[part]) return cudaSuccess;
+    const uint32_t slots = S.part_slot0[part + 1] - S.part_slot0[part];
+    k_seg_subst<<<slots < 148u * 2u ? slots : 148u * 2u, kSubThreads, kSubSmem, st>>>(S, part);      // persistent: one chain at a time per CTA
     return cudaGetLastError();
 }
 

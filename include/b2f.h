@@ -155,6 +155,25 @@ int b2f_decode_device(b2f_ctx *ctx, int fmt, size_t n_streams,
 /* framing helpers for the device path: header/trailer bytes are tiny and are produced on the host */
 size_t b2f_header_len(int fmt, const b2f_encode_opts *opts);
 
+/* ---- ONE stream split into parts (several contexts / GPUs) ---------------------
+ * libflate's blocks are independent (fresh LZ77 table per chunk, libflate_lz77/src/default.rs:73,108; own Huffman codes per block,
+ * src/deflate/symbol.rs:321-342), so contiguous runs of whole blocks can be encoded separately.  b2f_plan_from_writes gives the
+ * block boundaries for a write schedule; a part = the writes of a run of blocks (the schedule entries are the caller's).
+ * b2f_encode_part_device writes the part's raw DEFLATE bits starting at bit 0 of d_out (no container framing; BFINAL + the
+ * finish() block only when is_last) and returns their length in BITS plus the part's own CRC-32 / Adler-32.  The assembler --
+ * any host code -- places part k at bit offset 8 * header + sum of the earlier parts' bits: shift it on its GPU by (offset mod 8)
+ * with b2f_bits_shift_device, copy it out, OR the seam bytes, fold the checksums with the combine functions (Crc32 / Adler32 are
+ * linear: src/checksum.rs:4-33) and append b2f_stream_trailer.  The result is byte-identical to the single-call encode. */
+int b2f_encode_part_device(b2f_ctx *ctx, const b2f_encode_opts *opts, const uint8_t *d_in, size_t in_len,
+                           const int64_t *sched, size_t n_sched, int is_last,
+                           uint8_t *d_out, size_t out_cap, uint64_t *out_bits, uint32_t *crc32, uint32_t *adler32);
+/* d_dst bit (i + shift) = d_src bit i for i < n_bits (LSB first); d_dst needs (n_bits + 7) / 8 + 1 bytes; shift 0..7 */
+int b2f_bits_shift_device(b2f_ctx *ctx, const uint8_t *d_src, uint64_t n_bits, uint32_t shift, uint8_t *d_dst);
+uint32_t b2f_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);       /* value of the concatenation (pure host arithmetic) */
+uint32_t b2f_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
+size_t b2f_stream_header(int fmt, const b2f_encode_opts *opts, uint8_t *out, size_t cap);     /* returns the header length */
+size_t b2f_stream_trailer(int fmt, uint32_t crc32, uint32_t adler32, uint64_t total_len, uint8_t *out /* >= 8 bytes */);
+
 /* ---- streaming handles: the Read/Write-shaped surface -----------------------------------
  * A b2f_encoder mirrors Encoder<W,E>: write()/flush() record the schedule and buffer the input,
  * finish() runs the batch path and returns the complete stream (src/deflate/encode.rs:241-249,

@@ -40,6 +40,7 @@ EXPORTS = [
     "b2f_decoder_new", "b2f_decoder_read", "b2f_decoder_unread", "b2f_decoder_consumed", "b2f_decoder_free",
     "b2f_get_stats", "b2f_stage_name", "b2f_ctx_stream", "b2f_ctx_set_overlap",
     "b2f_host_alloc", "b2f_host_free", "b2f_host_register", "b2f_host_unregister",
+    "b2f_encode_part_device", "b2f_bits_shift_device", "b2f_crc32_combine", "b2f_adler32_combine", "b2f_stream_header", "b2f_stream_trailer",
 ]
 
 _lib = None
@@ -95,6 +96,16 @@ def lib():
         L.b2f_host_free.argtypes = [vp]
         L.b2f_host_register.argtypes = [vp, sz]
         L.b2f_host_unregister.argtypes = [vp]
+        L.b2f_encode_part_device.argtypes = [vp, C.POINTER(EncodeOpts), vp, sz, vp, sz, C.c_int, vp, sz, C.POINTER(u64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.b2f_bits_shift_device.argtypes = [vp, vp, u64, C.c_uint32, vp]
+        L.b2f_crc32_combine.restype = C.c_uint32
+        L.b2f_crc32_combine.argtypes = [C.c_uint32, C.c_uint32, u64]
+        L.b2f_adler32_combine.restype = C.c_uint32
+        L.b2f_adler32_combine.argtypes = [C.c_uint32, C.c_uint32, u64]
+        L.b2f_stream_header.restype = sz
+        L.b2f_stream_header.argtypes = [C.c_int, C.POINTER(EncodeOpts), vp, sz]
+        L.b2f_stream_trailer.restype = sz
+        L.b2f_stream_trailer.argtypes = [C.c_int, C.c_uint32, C.c_uint32, u64, vp]
         _lib = L
     return _lib
 
@@ -253,6 +264,22 @@ class Context:
         out_len, used, status = (C.c_size_t * n)(), (C.c_size_t * n)(), (C.c_int * n)()
         self._check(L.b2f_decode_device(self._h, fmt, n, C.c_void_p(d_in), a_off, a_len, C.c_void_p(d_out), o_off, o_cap, out_len, used, status))
         return list(out_len), list(used), list(status)
+
+    # ---- one part of a stream (whole blocks), device resident: returns (bits, crc32, adler32)
+    def encode_part_device(self, d_in, in_len, d_out, out_cap, schedule=None, is_last=False, **kw):
+        o = make_opts(**kw)
+        bits, crc, adler = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        if schedule is not None:
+            a = schedule if isinstance(schedule, np.ndarray) else np.asarray(list(schedule) + [0], dtype=np.int64)
+            sp, ns = C.c_void_p(a.ctypes.data), len(schedule)
+        else:
+            sp, ns = None, 0
+        self._check(lib().b2f_encode_part_device(self._h, C.byref(o), C.c_void_p(d_in), in_len, sp, ns, 1 if is_last else 0,
+                                                 C.c_void_p(d_out), out_cap, C.byref(bits), C.byref(crc), C.byref(adler)))
+        return bits.value, crc.value, adler.value
+
+    def bits_shift_device(self, d_src, n_bits, shift, d_dst):
+        self._check(lib().b2f_bits_shift_device(self._h, C.c_void_p(d_src), n_bits, shift, C.c_void_p(d_dst)))
 
     # ---- host-buffer calls on caller-owned numpy buffers (no copies in Python; used by bench.py's e2e leg)
     def encode_into(self, fmt, src, dst, schedule=None, **kw):

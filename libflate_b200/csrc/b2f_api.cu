@@ -135,6 +135,7 @@ struct b2f_ctx {
     CopyPool pool; Stager st_in, st_out; unsigned copy_threads = 4; size_t stage_rr = 0;
     uint32_t max_parts = 4;        // pipeline depth of the decode's LZ77 resolution + device->host copies (B2F_DECODE_PARTS, <= kMaxParts)
     uint64_t staged_h2d = 0, staged_d2h = 0;     // bytes that went through the internal staging (pageable caller memory)
+    std::vector<uint64_t> last_good;             // per stream of the last decode call: bytes of the blocks that completed before an error
 };
 
 static thread_local std::string g_create_err;
@@ -286,7 +287,9 @@ struct PlanOut {
     std::vector<uint8_t> block_after_flush;   // block was closed by an explicit flush() (candidate for the zlib sync marker)
 };
 // Block::write / CompressBuf::append / DefaultLz77Encoder::encode bookkeeping (encode.rs:277-286,405-425; default.rs:60-68)
-void plan_stream(const int64_t *sched, size_t n_sched, uint64_t in_len, uint64_t block_size, uint32_t window, PlanOut &P) {
+// emit_final = false: the stream continues in another part (b2f_encode_part_device): no finish() block; returns false when the part
+// does not end exactly on a block boundary.
+bool plan_stream(const int64_t *sched, size_t n_sched, uint64_t in_len, uint64_t block_size, uint32_t window, PlanOut &P, bool emit_final = true) {
     const uint64_t chunk_thresh = (uint64_t)window * 8;
     uint64_t lz = 0, orig = 0, pos = 0; uint32_t chunks_in_block = 0;
     auto end_chunk = [&]() { P.chunk_ends.push_back(pos); chunks_in_block++; lz = 0; };
@@ -304,7 +307,9 @@ void plan_stream(const int64_t *sched, size_t n_sched, uint64_t in_len, uint64_t
         if (lz >= chunk_thresh) end_chunk();
         while (orig >= block_size) flush_block(false);
     }
+    if (!emit_final) return lz == 0 && orig == 0 && !P.block_ends.empty();
     flush_block(false);                    // finish(): always one more block, possibly empty (encode.rs:296-303)
+    return true;
 }
 }  // namespace
 
@@ -458,19 +463,21 @@ struct EncPlan {
 
 // Fills plan for streams laid out at in_off[] in the device input.
 int build_plan(b2f_ctx *ctx, const b2f_encode_opts &o, size_t n_streams, const uint64_t *in_off, const size_t *in_len,
-               const int64_t *const *sched, const size_t *n_sched, int fmt, EncPlan &P) {
+               const int64_t *const *sched, const size_t *n_sched, int fmt, EncPlan &P, bool emit_final = true) {
     const uint32_t window = o.window_size > 32768 ? 32768 : o.window_size;
     P.stream_blk0.assign(1, 0);
     P.seg0.assign(1, 0); P.pt0.assign(1, 0); P.tile0.assign(1, 0); P.grp0.assign(1, 0);
     for (size_t s = 0; s < n_streams; s++) {
         PlanOut po;
-        plan_stream(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s], o.block_size, window, po);
+        if (!plan_stream(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s], o.block_size, window, po, emit_final)) {
+            ctx->err = "a part that is not the last one must end exactly on a DEFLATE block boundary (see b2f_plan_from_writes)"; return B2F_ERR_INVALID_ARG;
+        }
         uint64_t cstart = 0; size_t ci = 0;
         for (size_t b = 0; b < po.block_ends.size(); b++) {
             BlockDesc bd; memset(&bd, 0, sizeof bd);
             bd.stream = (uint32_t)s; bd.chunk0 = (uint32_t)P.chunks.size(); bd.nchunks = po.block_chunks[b];
             bd.tile0 = P.tile0.back();
-            bd.is_final = b + 1 == po.block_ends.size();
+            bd.is_final = emit_final && b + 1 == po.block_ends.size();
             bd.sync_after = (fmt == B2F_FMT_ZLIB && o.zlib_flush_sync && po.block_after_flush[b]) ? 1 : 0;
             bd.fixed = o.mode == B2F_MODE_FIXED;
             for (uint32_t k = 0; k < bd.nchunks; k++, ci++) {
@@ -524,6 +531,8 @@ struct EncodeJob {
     const uint8_t *d_in; std::vector<uint64_t> in_off; std::vector<uint64_t> in_len;
     const uint8_t *const *h_in = nullptr;     // when set, the inputs still live on the host: encode_on_device copies them slice by slice
     std::vector<char> h_pinned;               // per stream: the host input is page-locked (DMA in place) or pageable (staged)
+    bool part = false, part_last = true;      // b2f_encode_part_device: raw blocks of one part of a stream (no container framing)
+    std::vector<uint64_t> out_bits;           // per stream: length of the DEFLATE bits (parts are not byte aligned)
     // results
     std::vector<uint64_t> out_base; std::vector<uint64_t> out_len;   // in ctx->buf[NB_OUT]
 };
@@ -535,7 +544,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     EncPlan P;
     std::vector<size_t> lens(n_streams);
     for (size_t s = 0; s < n_streams; s++) lens[s] = (size_t)job.in_len[s];
-    int rc = build_plan(ctx, o, n_streams, job.in_off.data(), lens.data(), sched, n_sched, fmt, P);
+    int rc = build_plan(ctx, o, n_streams, job.in_off.data(), lens.data(), sched, n_sched, fmt, P, !job.part || job.part_last);
     if (rc) return rc;
     std::vector<uint8_t> hdr; make_header(fmt, o, hdr);
     const size_t tl = trailer_len(fmt);
@@ -668,11 +677,13 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 1;
     ctx->tm.finish(ctx->stream);
-    CK(ctx->pin_res.ensure(n_streams * 8 + 64));
+    CK(ctx->pin_res.ensure(n_streams * 16 + 64));
     uint64_t *h_out_len = ctx->pin_res.as<uint64_t>();
     CK(cudaMemcpyAsync(h_out_len, d_out_len, n_streams * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_out_len + n_streams, E.stream_end_bits, n_streams * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (size_t s = 0; s < n_streams; s++) job.out_len[s] = h_out_len[s];
+    job.out_bits.resize(n_streams);
+    for (size_t s = 0; s < n_streams; s++) { job.out_len[s] = h_out_len[s]; job.out_bits[s] = h_out_len[n_streams + s] - 8ull * hdr.size(); }
     return B2F_OK;
 }
 
@@ -802,6 +813,88 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         status[s] = B2F_OK;
         CK(d2h_copy(ctx, out[s], ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s], job.out_len[s], ctx->stream, is_pinned_host(out[s])));
     }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2F_OK;
+}
+
+// ------------------------------------------------------------------------------------------ one stream split into parts
+// The blocks of a DEFLATE stream are independent in libflate's output (fresh LZ77 table per chunk, own Huffman codes per block),
+// so contiguous runs of blocks can be encoded by different contexts / GPUs.  What has to be exchanged afterwards is 8 bytes per
+// part: its length in BITS (blocks are not byte aligned, src/deflate/encode.rs:291-293) -- an exclusive scan of those gives every
+// part's position -- plus its checksum, folded with the algebraic combine below.  Payload bytes never cross GPUs.
+namespace {
+__global__ void k_shift_copy(uint8_t *dst, const uint8_t *src, uint64_t nbytes_in, uint32_t shift) {
+    // dst bit (i + shift) = src bit i, LSB first; dst has nbytes_in + 1 bytes (bits below `shift` of dst[0] are zero)
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nbytes_in) return;
+    const uint32_t lo = i ? src[i - 1] : 0u, hi = i < nbytes_in ? src[i] : 0u;
+    dst[i] = (uint8_t)(((hi << 8 | lo) << shift) >> 8);
+}
+uint32_t crc_mulmod(uint32_t a, uint32_t b) {                  // product mod the reflected CRC-32 polynomial
+    uint32_t p = 0;
+    for (int i = 31; i >= 0; i--) { if ((a >> i) & 1u) p ^= b; b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1; }
+    return p;
+}
+}  // namespace
+
+extern "C" uint32_t b2f_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+    // crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B)   (what checksum::Crc32 would give after update(A), update(B))
+    uint32_t xp = 1u << 31, sq = 1u << 30;                       // x^0, x^1
+    for (uint64_t e = len2 * 8; e; e >>= 1) { if (e & 1) xp = crc_mulmod(sq, xp); sq = crc_mulmod(sq, sq); }
+    return crc_mulmod(xp, crc1) ^ crc2;
+}
+extern "C" uint32_t b2f_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2) {
+    const uint64_t M = 65521, a1 = adler1 & 0xFFFF, b1 = adler1 >> 16, a2 = adler2 & 0xFFFF, b2 = adler2 >> 16, r = len2 % M;
+    const uint64_t a = (a1 + a2 + M - 1) % M;
+    const uint64_t b = (b1 + b2 + r * ((a1 + M - 1) % M)) % M;
+    return (uint32_t)((b << 16) | a);
+}
+extern "C" size_t b2f_stream_header(int fmt, const b2f_encode_opts *opts, uint8_t *out, size_t cap) {
+    b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
+    std::vector<uint8_t> h; make_header(fmt, *opts, h);
+    if (out && cap >= h.size()) memcpy(out, h.data(), h.size());
+    return h.size();
+}
+extern "C" size_t b2f_stream_trailer(int fmt, uint32_t crc32, uint32_t adler32, uint64_t total_len, uint8_t *out) {
+    if (fmt == B2F_FMT_GZIP) { for (int k = 0; k < 4; k++) { out[k] = (uint8_t)(crc32 >> (8 * k)); out[4 + k] = (uint8_t)((uint32_t)total_len >> (8 * k)); } return 8; }
+    if (fmt == B2F_FMT_ZLIB) { for (int k = 0; k < 4; k++) out[k] = (uint8_t)(adler32 >> (8 * (3 - k))); return 4; }
+    return 0;
+}
+extern "C" int b2f_encode_part_device(b2f_ctx *ctx, const b2f_encode_opts *opts, const uint8_t *d_in, size_t in_len, const int64_t *sched, size_t n_sched,
+                                      int is_last, uint8_t *d_out, size_t out_cap, uint64_t *out_bits, uint32_t *crc32, uint32_t *adler32) {
+    if (!ctx || !d_in || !d_out || !out_bits) return B2F_ERR_INVALID_ARG;
+    b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
+    int rc = validate_opts(ctx, B2F_FMT_DEFLATE, *opts); if (rc) return rc;
+    if (opts->mode == B2F_MODE_STORED) { ctx->err = "stored mode has no part variant"; return B2F_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.reset();
+    EncodeJob job; job.d_in = d_in; job.part = true; job.part_last = is_last != 0;
+    job.in_off.assign(1, 0); job.in_len.assign(1, effective_len(sched, n_sched, in_len));
+    const int64_t *sp = sched; size_t sn = n_sched;
+    rc = encode_on_device(ctx, B2F_FMT_DEFLATE, *opts, 1, sched ? &sp : nullptr, sched ? &sn : nullptr, job);
+    if (rc) return rc;
+    *out_bits = job.out_bits[0];
+    if (job.out_len[0] + 1 > out_cap) return B2F_ERR_OUTPUT_TOO_SMALL;
+    CK(cudaMemcpyAsync(d_out, ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[0], job.out_len[0], cudaMemcpyDeviceToDevice, ctx->stream));
+    if (crc32 || adler32) {
+        std::vector<uint32_t> c, a;
+        rc = run_checksums(ctx, d_in, job.in_off, job.in_len, true, true, nullptr, c, a);
+        if (rc) return rc;
+        if (crc32) *crc32 = c[0];
+        if (adler32) *adler32 = a[0];
+    }
+    ctx->tm.finish(ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_stats(ctx, false);
+    return B2F_OK;
+}
+extern "C" int b2f_bits_shift_device(b2f_ctx *ctx, const uint8_t *d_src, uint64_t n_bits, uint32_t shift, uint8_t *d_dst) {
+    if (!ctx || !d_src || !d_dst || shift > 7) return B2F_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nb = (n_bits + 7) / 8;
+    k_shift_copy<<<(unsigned)((nb + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_dst, d_src, nb, shift);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
     CK(cudaStreamSynchronize(ctx->stream));
     return B2F_OK;
 }
@@ -946,9 +1039,9 @@ constexpr uint64_t kParallelMinBytes = 128 * 1024;    // smaller streams are dec
 //  - small members, and any member whose chain is not clean (non-dynamic blocks, cross-block back-references,
 //    errors, too-small output): in-order kernel, which reproduces libflate's error kinds and partial output.
 int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::vector<Member> &mem,
-                  std::vector<int> &st, std::vector<uint64_t> &olen, std::vector<uint64_t> &cons, std::vector<char> &copied) {
+                  std::vector<int> &st, std::vector<uint64_t> &olen, std::vector<uint64_t> &cons, std::vector<char> &copied, std::vector<uint64_t> &good) {
     const size_t n = mem.size();
-    st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0); copied.assign(n, 0);
+    st.assign(n, 0); olen.assign(n, 0); cons.assign(n, 0); copied.assign(n, 0); good.assign(n, 0);
     if (!n) return B2F_OK;
     // in_len: what the speculative path may look at (the whole rest of the container for a first member, a window sized after the
     // previous member for later members of a multi-member file); full_len: what the in-order kernel may read
@@ -1019,7 +1112,11 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
         bool too_big = false;
         for (size_t i = 0; i < ncand; i++) {
             bm[i] = cands[i].first; bb[i] = cands[i].second;
-            be[i] = (i + 1 < ncand && cands[i + 1].first == bm[i]) ? cands[i + 1].second : in_len[bm[i]] * 8;
+            // A candidate's extent runs to the candidate AFTER the next one: the finder's rare false positives (about one per 300 Mbit)
+            // lie inside a true block, and with the doubled extent that block's parse simply runs across it to its EndOfBlock -- no second
+            // parse of the whole stream.  The parse is latency bound (one thread per 4096-bit subsegment), so the extra threads are nearly
+            // free; two false positives in a row still take the drop-and-retry path below.
+            be[i] = (i + 2 < ncand && cands[i + 2].first == bm[i]) ? cands[i + 2].second : in_len[bm[i]] * 8;
             const uint64_t bits = be[i] - bb[i];
             if (bits >= 0xFFFF0000ull) too_big = true;
             const uint32_t ns = (uint32_t)((bits + kSpecBits - 1) / kSpecBits);
@@ -1191,17 +1288,18 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                     }
                     S.n_parts = nparts;
                     for (uint32_t part = 0; part <= nparts; part++) S.part_slot0[part] = slot0[part_b[part]];
+                    // the token pass is one launch for all parts (a thread per subsegment: its duration is the latency of one thread, so
+                    // per-part launches would pay that latency once per part)
+                    ctx->tm.mark(ctx->stream, "spec_tokens");
+                    CK(spec_launch_tokens(S, cta0[sel_blocks[0]], cta0[sel_blocks[nsel - 1] + 1], ctx->stream));
+                    ctx->stats.kernel_launches += 1;
                     for (uint32_t part = 0; part < nparts; part++) {
                         if (part_b[part + 1] == part_b[part]) continue;
-                        // the part's blocks are a contiguous run of candidate blocks (plus, possibly, unselected ones in between)
-                        const uint32_t cb0 = sel_blocks[part_b[part]], cb1 = sel_blocks[part_b[part + 1] - 1];
-                        ctx->tm.mark(ctx->stream, "spec_tokens");
-                        CK(spec_launch_tokens(S, cta0[cb0], cta0[cb1 + 1], ctx->stream));
                         ctx->tm.mark(ctx->stream, "lz_resolve");
                         CK(spec_launch_segments(S, part, ctx->stream));
                         ctx->tm.mark(ctx->stream, "lz_subst");
                         CK(spec_launch_subst(S, part, ctx->stream));
-                        ctx->stats.kernel_launches += 5;
+                        ctx->stats.kernel_launches += 4;
                         if (any_host) CK(cudaEventRecord(ctx->part_ev[part], ctx->stream));
                     }
                     ctx->tm.mark(ctx->stream, "sync");
@@ -1248,13 +1346,13 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
         std::vector<uint64_t> s_io(nser), s_il(nser), s_oo(nser), s_oc(nser);
         for (size_t k = 0; k < nser; k++) { uint32_t m = serial[k]; s_io[k] = in_off[m]; s_il[k] = full_len[m]; s_oo[k] = out_off[m]; s_oc[k] = out_cap[m]; }
         const size_t s_a = PC.add(s_io.data(), nser * 8), s_b = PC.add(s_il.data(), nser * 8), s_c = PC.add(s_oo.data(), nser * 8), s_d = PC.add(s_oc.data(), nser * 8);
-        const size_t s_st = PC.reserve(nser * 4), s_ol = PC.reserve(nser * 8), s_cs = PC.reserve(nser * 8);
+        const size_t s_st = PC.reserve(nser * 4), s_ol = PC.reserve(nser * 8), s_cs = PC.reserve(nser * 8), s_gl = PC.reserve(nser * 8);
         CK(PC.commit(ctx->stream));
         ctx->tm.mark(ctx->stream, "inflate_inorder");
         DecDev D;
         D.in = d_in; D.in_off = PC.ptr<uint64_t>(s_a); D.in_len = PC.ptr<uint64_t>(s_b);
         D.out = d_out; D.out_off = PC.ptr<uint64_t>(s_c); D.out_cap = PC.ptr<uint64_t>(s_d); D.n = (uint32_t)nser;
-        D.status = PC.ptr<int32_t>(s_st); D.out_len = PC.ptr<uint64_t>(s_ol); D.consumed = PC.ptr<uint64_t>(s_cs);
+        D.status = PC.ptr<int32_t>(s_st); D.out_len = PC.ptr<uint64_t>(s_ol); D.consumed = PC.ptr<uint64_t>(s_cs); D.good_len = PC.ptr<uint64_t>(s_gl);
         CK(dec_launch_serial(D, ctx->stream));
         ctx->stats.kernel_launches += 1;
         ctx->tm.mark(ctx->stream, "results");
@@ -1266,8 +1364,10 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
         for (size_t k = 0; k < nser; k++) {
             uint32_t m = serial[k];
             st[m] = ((int32_t *)hr)[k]; olen[m] = ((uint64_t *)(hr + (s_ol - s_st)))[k]; cons[m] = ((uint64_t *)(hr + (s_cs - s_st)))[k];
+            good[m] = ((uint64_t *)(hr + (s_gl - s_st)))[k];
         }
     }
+    for (size_t i = 0; i < n; i++) if (is_par[i]) good[i] = olen[i];
     return B2F_OK;
 }
 
@@ -1319,6 +1419,7 @@ int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const 
     std::vector<uint64_t> produced(n_streams, 0);
     std::vector<char> done(n_streams, 0);
     std::vector<uint64_t> prev_comp(n_streams, 0);    // compressed size of the stream's previous member (MultiDecoder rounds)
+    ctx->last_good.assign(n_streams, 0);
     for (size_t s = 0; s < n_streams; s++) { status[s] = B2F_OK; out_len[s] = 0; in_consumed[s] = 0; }
     bool first = true;
     for (;;) {
@@ -1365,9 +1466,10 @@ int decode_core(b2f_ctx *ctx, int fmt, size_t n_streams, InputAccess &IA, const 
             mem.push_back(m);
         }
         if (mem.empty()) break;
-        std::vector<int> st; std::vector<uint64_t> olen, cons; std::vector<char> copied;
-        int rc = inflate_round(ctx, d_in, d_out, mem, st, olen, cons, copied);
+        std::vector<int> st; std::vector<uint64_t> olen, cons, good; std::vector<char> copied;
+        int rc = inflate_round(ctx, d_in, d_out, mem, st, olen, cons, copied, good);
         if (rc) return rc;
+        for (size_t i = 0; i < mem.size(); i++) ctx->last_good[mem[i].stream] = produced[mem[i].stream] + std::min<uint64_t>(good[i], mem[i].out_cap);
         // bytes of each stream that are already on the host (a prefix: members are decoded in order)
         if (h_copied) for (size_t i = 0; i < mem.size(); i++) if (copied[i] && (*h_copied)[mem[i].stream] == produced[mem[i].stream]) (*h_copied)[mem[i].stream] += std::min<uint64_t>(olen[i], mem[i].out_cap);
         // ---- trailers + checksums of what was produced in this round
@@ -1465,7 +1567,7 @@ extern "C" int b2f_decode_device(b2f_ctx *ctx, int fmt, size_t n_streams, const 
 
 // ------------------------------------------------------------------------------------------ streaming handles
 struct b2f_encoder { b2f_ctx *ctx; int fmt; b2f_encode_opts opts; std::vector<uint8_t> data; std::vector<int64_t> sched; std::vector<uint8_t> out; bool finished; std::string name, comment; std::vector<uint8_t> extra; };
-struct b2f_decoder { b2f_ctx *ctx; int fmt; std::vector<uint8_t> in; std::vector<uint8_t> out; size_t rd; size_t consumed; int status; bool decoded; };
+struct b2f_decoder { b2f_ctx *ctx; int fmt; std::vector<uint8_t> in; std::vector<uint8_t> out; size_t rd; size_t consumed; int status; bool decoded; size_t good; };
 
 extern "C" int b2f_encoder_new(b2f_ctx *ctx, int fmt, const b2f_encode_opts *opts, b2f_encoder **out) {
     if (!ctx || !out) return B2F_ERR_INVALID_ARG;
@@ -1519,15 +1621,17 @@ static int decoder_run(b2f_decoder *d) {
         if (rc) return rc;
         if (st == B2F_ERR_OUTPUT_TOO_SMALL) { cap = std::max(cap * 2, ol + 64); continue; }
         d->out.resize(std::min(ol, cap)); d->consumed = ic; d->status = st; d->decoded = true;
+        d->good = st == B2F_OK ? d->out.size() : std::min<size_t>(d->out.size(), d->ctx->last_good.empty() ? 0 : (size_t)d->ctx->last_good[0]);
         return B2F_OK;
     }
 }
 extern "C" int64_t b2f_decoder_read(b2f_decoder *d, uint8_t *buf, size_t len) {
     if (!d) return B2F_ERR_INVALID_ARG;
     if (!d->decoded) { int rc = decoder_run(d); if (rc) return rc; }
-    // Decoder::read: data decoded before an error is NOT handed out by read() (it stays in unread_decoded_data()); the error is returned.
-    if (d->status != B2F_OK) return d->status;
-    size_t k = std::min(len, d->out.size() - d->rd);
+    // Decoder::read (decode.rs:136-164) decodes block by block: the bytes of every block that completed are handed out by read();
+    // the error surfaces when the failing block is reached, and that block's partial bytes stay in unread_decoded_data()
+    if (d->status != B2F_OK && d->rd >= d->good) return d->status;
+    size_t k = std::min(len, (d->status != B2F_OK ? d->good : d->out.size()) - d->rd);
     memcpy(buf, d->out.data() + d->rd, k); d->rd += k;
     return (int64_t)k;
 }

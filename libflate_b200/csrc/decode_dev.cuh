@@ -15,6 +15,7 @@ struct DecDev {
     int32_t *status;             // [n] kInf*
     uint64_t *out_len;           // [n]
     uint64_t *consumed;          // [n] bytes pulled from the reader
+    uint64_t *good_len;          // [n] output bytes of the blocks that completed (Decoder::read hands those out before an error surfaces)
 };
 // block-boundary finder over a subset of members
 struct FindDev {

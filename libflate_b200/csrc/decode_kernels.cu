@@ -24,7 +24,7 @@ constexpr uint32_t kRingBytes = 65536, kRingMask = kRingBytes - 1;
 // back-references are served from it; every time the write position crosses a 32 KiB boundary the completed half is
 // flushed to HBM with coalesced 4-byte stores.
 struct WindowOut {
-    uint8_t *ring; uint8_t *g; uint64_t capacity; uint64_t flushed; uint32_t lane;
+    uint8_t *ring; uint8_t *g; uint64_t capacity; uint64_t flushed; uint32_t lane; uint64_t last_block;
     __device__ __forceinline__ uint64_t cap() const { return capacity; }
     __device__ __forceinline__ void flush_to(uint64_t upto) {
         if (upto > capacity) upto = capacity;
@@ -63,7 +63,7 @@ struct WindowOut {
         if (pos + n > flushed) flushed = pos + n;
         __syncwarp();
     }
-    __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t, bool) {}
+    __device__ __forceinline__ void block_end(uint64_t, uint64_t, uint64_t out_pos, bool) { last_block = out_pos; }
     __device__ __forceinline__ int fast(BitIn &b, const InflateTables &T, uint64_t &out_pos, uint64_t hist_base);
 };
 
@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(32) k_inflate_streams(DecDev D) {
     const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3);       // start the reader on an aligned word (the lead bytes are never consumed)
     bi_init(b, p0 - lead, D.in_len[s] + lead, 8ull * lead);
     const uint64_t o0 = D.out_off[s];
-    WindowOut out = { ring, D.out, o0 + D.out_cap[s], o0, lane };
+    WindowOut out = { ring, D.out, o0 + D.out_cap[s], o0, lane, o0 };
     InflateResult R;
     inflate_blocks(b, T, out, o0, 0ull - o0, 0xFFFFFFFFu, (int)lane, 32, WarpSync(), R);
     out.flush_to(R.out_len);
-    if (lane == 0) { D.status[s] = R.status; D.out_len[s] = R.out_len - o0; D.consumed[s] = R.consumed - lead; }
+    if (lane == 0) { D.status[s] = R.status; D.out_len[s] = R.out_len - o0; D.consumed[s] = R.consumed - lead; D.good_len[s] = out.last_block - o0; }
 }
 
 // ---------------------------------------------------------------------------------- block-boundary finder

@@ -7,7 +7,7 @@
 //   K3 parse_exits   thread per 2 KiB tile: right-to-left exit DP of the greedy walk            (E2)
 //   K4 parse_stitch  thread per chunk: chain the tile entry points
 //   K5 parse_emit    thread per tile: walk, emit symbols, per-block histograms                  (S1/S2)
-//   K6 huff_build    one lane per DEFLATE block: code lengths, canonical codes, header bits     (H1-H3/S3/S4)
+//   K6 huff_build    one warp per DEFLATE block: code lengths, canonical codes, header bits     (H1-H3/S3/S4)
 //   K7 tile_bits     warp per tile: coded size of the tile
 //   K8 scan_tiles / scan_blocks: bit offsets of every tile / block / stream                     (B2, E1)
 //   K9 write_headers warp per block: BFINAL/BTYPE, dynamic header, EOB, sync marker             (B2)
@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "huff_build.cuh"
+#include "huff_warp.cuh"
 #include "encode_dev.cuh"
 
 namespace b2f {
@@ -691,20 +692,41 @@ __global__ void __launch_bounds__(kPxWarps * 32) k_parse_exits(EncDev E, uint32_
 #pragma unroll
         for (uint32_t r = 0; r < 32; r++) mds[r * 33 + lane] = cur[r];
         __syncwarp();
-        if ((uint32_t)(32 * j) < len) {
-            const uint32_t kmax = min(32u, len - 32u * (uint32_t)j);
-            for (uint32_t k = kmax; k-- > 0;) {
-                const uint32_t p = 32u * (uint32_t)j + k;
-                const uint32_t v = mds[lane * 33 + k];
-                const uint32_t step = (v >> 16) ? (v >> 16) : 1u;
-                const uint32_t nx = p + step;
-                uint32_t ex;
-                if (nx >= len) ex = nx - len;
-                else if (step == 1) ex = prev_ex;
-                else { uint32_t ix = ridx + step; if (ix >= kRing) ix -= kRing; ex = ring[ix * 32 + lane]; }
-                ring[ridx * 32 + lane] = (uint16_t)ex;
+        // the lane's 32 values of the chunk go to registers first (conflict-free reads), so that the serial chain below is only
+        // ring read -> select -> ring write
+        uint32_t mv[32];
+#pragma unroll
+        for (uint32_t k = 0; k < 32; k++) mv[k] = mds[lane * 33 + k];
+        if (__all_sync(0xFFFFFFFFu, 32u * (uint32_t)(j + 1) <= len)) {
+            // full chunk in every lane (all but the last chunks of a chunk's last tile): no branches, so that everything that does not
+            // depend on the previous position (step, ring indices) is computed ahead and the serial chain is read -> select -> write
+            const uint32_t pbase = 32u * (uint32_t)j;
+#pragma unroll
+            for (int k = 31; k >= 0; k--) {
+                const uint32_t step = max(mv[k] >> 16, 1u);
+                uint32_t rk = ridx + kRing - (31u - (uint32_t)k); rk -= rk >= kRing ? kRing : 0u;      // ring index of position pbase + k
+                uint32_t ix = rk + step; ix -= ix >= kRing ? kRing : 0u;
+                const uint32_t nx = pbase + (uint32_t)k + step;
+                const uint32_t rv = ring[ix * 32 + lane];
+                const uint32_t ex = nx >= len ? nx - len : step == 1 ? prev_ex : rv;
+                ring[rk * 32 + lane] = (uint16_t)ex;
                 prev_ex = ex;
-                ridx = ridx ? ridx - 1 : kRing - 1;
+            }
+            ridx = ridx + kRing - 32u; ridx -= ridx >= kRing ? kRing : 0u;
+        } else if ((uint32_t)(32 * j) < len) {
+            const uint32_t kmax = min(32u, len - 32u * (uint32_t)j);
+#pragma unroll
+            for (int k = 31; k >= 0; k--) {
+                if ((uint32_t)k < kmax) {
+                    const uint32_t step = max(mv[k] >> 16, 1u);
+                    const uint32_t nx = 32u * (uint32_t)j + (uint32_t)k + step;
+                    uint32_t ix = ridx + step; ix -= ix >= kRing ? kRing : 0u;
+                    const uint32_t rv = ring[ix * 32 + lane];                       // (always a valid index; unused when the step leaves the tile)
+                    const uint32_t ex = nx >= len ? nx - len : step == 1 ? prev_ex : rv;
+                    ring[ridx * 32 + lane] = (uint16_t)ex;
+                    prev_ex = ex;
+                    ridx = ridx ? ridx - 1 : kRing - 1;
+                }
             }
         }
         __syncwarp();
@@ -741,6 +763,7 @@ __global__ void __launch_bounds__(kStWarps * 32) k_parse_stitch(EncDev E, uint32
         const uint32_t nr = min(32u, t1 - tb);
         // the tables of tiles [tb, tb + nr) are contiguous: nr * 129 words (516-byte rows keep 4-byte alignment)
         const uint32_t *__restrict__ src = reinterpret_cast<const uint32_t *>(E.exit_tab + (uint64_t)tb * kExitW);
+#pragma unroll 16
         for (uint32_t i = lane; i < nr * kStRowWords; i += 32) rows[i] = __ldg(src + i);
         __syncwarp();
         uint32_t mine = 0;
@@ -759,12 +782,13 @@ __global__ void __launch_bounds__(kStWarps * 32) k_parse_stitch(EncDev E, uint32
 // tile from its entry point, emits the symbols and counts them in the CTA's shared-memory histogram.
 constexpr uint32_t kPeWarpSmem = 32 * 33 * 4;
 __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
-    __shared__ uint32_t sh[kHistStride];
+    __shared__ uint32_t sh[kHistStride], shl[256];                            // lit/len + distance codes | raw match lengths (len - 3)
     __shared__ __align__(16) uint32_t pes[2 * kPeWarpSmem / 4];
     const uint32_t grp = blockIdx.x + off;
     const uint32_t c = find_owner(E.grp0, E.n_chunks, grp);
     const ChunkDesc cd = E.chunks[c];
     for (uint32_t i = threadIdx.x; i < kHistStride; i += 64) sh[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 256; i += 64) shl[i] = 0;
     __syncthreads();
     const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t *mds = pes + w * (kPeWarpSmem / 4);                               // [32][33]
@@ -796,14 +820,14 @@ __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
         const uint32_t cend = min(len, 32 * (j + 1));
         while (i < cend) {
             const uint32_t v = mds[lane * 33 + (i - 32 * j)];
-            if (v >> 16) {
-                uint32_t lc, le, lx, dc, de, dx;
-                length_code(v >> 16, lc, le, lx);
+            const uint32_t L = v >> 16;
+            if (L) {                                                          // lengths are counted raw (folded into codes at the end)
+                uint32_t dc, de, dx;
                 dist_code(v & 0xFFFFu, dc, de, dx);
-                atomicAdd(&sh[lc], 1u);
+                atomicAdd(&shl[L - 3], 1u);
                 atomicAdd(&sh[286 + dc], 1u);
                 so[cnt++] = kSymPtr | v;
-                i += v >> 16;
+                i += L;
             } else {
                 atomicAdd(&sh[v & 0xFFu], 1u);
                 so[cnt++] = v & 0xFFu;
@@ -816,6 +840,11 @@ __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
     }
     if (valid) E.tile_nsym[tile] = cnt;
     __syncthreads();
+    for (uint32_t k = threadIdx.x; k < 256; k += 64) {                        // raw lengths -> length codes 257..285
+        const uint32_t nl = shl[k];
+        if (nl) { uint32_t lc, le, lx; length_code(k + 3, lc, le, lx); atomicAdd(&sh[lc], nl); }
+    }
+    __syncthreads();
     uint32_t *__restrict__ gh = E.hist + (uint64_t)cd.block * kHistStride;
     for (uint32_t k = threadIdx.x; k < 316; k += 64) if (sh[k]) atomicAdd(&gh[k], sh[k]);
 }
@@ -823,17 +852,17 @@ __global__ void __launch_bounds__(64) k_parse_emit(EncDev E, uint32_t off) {
 // =============================================================================== K6 huff_build
 // skip_built: leave out the blocks whose codes a slice already built (hdr_bits is preset to 0xFFFFFFFF by the host)
 __global__ void __launch_bounds__(32) k_huff_build(EncDev E, uint32_t b_off, uint32_t skip_built) {
-    __shared__ HuffWork W;
+    __shared__ HuffWarp W;
     const uint32_t b = blockIdx.x + b_off;
-    if (threadIdx.x != 0) return;
     if (skip_built && E.hdr_bits[b] != 0xFFFFFFFFu) return;
     uint32_t *lit = E.litcode + (uint64_t)b * kLitStride;
     uint32_t *dist = E.distcode + (uint64_t)b * kDistStride;
     if (E.blocks[b].fixed) {
-        build_fixed_codes(lit, dist);
-        E.hdr_bits[b] = 0;
+        if (threadIdx.x == 0) { build_fixed_codes(lit, dist); E.hdr_bits[b] = 0; }
     } else {
-        E.hdr_bits[b] = build_block_codes(E.hist + (uint64_t)b * kHistStride, lit, dist, E.hdr_words + (uint64_t)b * kHdrWords, W);
+        // one warp per block (huff_warp.cuh); huff_build.cuh is the serial statement of the same construction
+        const uint32_t nbits = hw_build_block_codes(E.hist + (uint64_t)b * kHistStride, lit, dist, E.hdr_words + (uint64_t)b * kHdrWords, W);
+        if (threadIdx.x == 0) E.hdr_bits[b] = nbits;
     }
 }
 

@@ -104,25 +104,34 @@ B2F_HD bool validate_dynamic_header(const uint8_t *p, uint64_t nbytes, uint64_t 
     uint8_t pw[19];
     for (int i = 0; i < 19; i++) pw[i] = 0;
     for (uint32_t k = 0; k < hclen; k++) pw[ORDER[k]] = (uint8_t)vb_get(b, 3);
-    uint32_t cnt[8], first[8], off[8]; uint8_t sorted[19];
+    uint32_t cnt[8], first[8];
     for (int i = 0; i < 8; i++) cnt[i] = 0;
     for (int i = 0; i < 19; i++) cnt[pw[i]]++;
     cnt[0] = 0;
-    uint32_t code = 0, o = 0; first[0] = 0; off[0] = 0;
-    for (uint32_t l = 1; l < 8; l++) { code = (code + cnt[l - 1]) << 1; first[l] = code; off[l] = o; o += cnt[l]; if (code + cnt[l] > (1u << l)) return false; }
-    { uint32_t nxt[8]; for (int l = 0; l < 8; l++) nxt[l] = off[l]; for (uint32_t s = 0; s < 19; s++) if (pw[s]) sorted[nxt[pw[s]]++] = (uint8_t)s; }
+    uint32_t code = 0; first[0] = 0;
+    for (uint32_t l = 1; l < 8; l++) { code = (code + cnt[l - 1]) << 1; first[l] = code; if (code + cnt[l] > (1u << l)) return false; }
+    // 7-bit lookup table of the code-length code (symbol | width << 5, 0 = no code): one load per symbol instead of a bit-by-bit
+    // canonical search -- the validation is the larger half of the finder's time and nearly all of it is this loop
+    uint8_t lut[128];
+    for (int i = 0; i < 128; i++) lut[i] = 0;
+    {
+        uint32_t nxt[8];
+        for (int l = 0; l < 8; l++) nxt[l] = first[l];
+        for (uint32_t s = 0; s < 19; s++) {
+            const uint32_t l = pw[s];
+            if (!l) continue;
+            const uint32_t r = bitrev(nxt[l]++, l);
+            for (uint32_t k = r; k < 128; k += (1u << l)) lut[k] = (uint8_t)(s | (l << 5));
+        }
+    }
     uint32_t total = 0, want = hlit + hdist, prev = 0;
     uint32_t lit_kraft = 0, dist_kraft = 0, nlit = 0, ndist = 0, eob_len = 0;
     while (total < want) {
         if (b.pos >= limit) return false;
         if (b.bc < 32) { b.bb |= (uint64_t)vb_load32(b.p, b.next, b.nbytes) << b.bc; b.bc += 32; b.next += 4; }
-        const uint32_t peek = (uint32_t)b.bb & 127u;
-        uint32_t sym = 0xFFu, used = 0, acc = 0;
-        for (uint32_t l = 1; l < 8; l++) {
-            acc = (acc << 1) | ((peek >> (l - 1)) & 1u);            // MSB-first code value of the first l bits
-            if (cnt[l] && acc >= first[l] && acc - first[l] < cnt[l]) { sym = sorted[off[l] + acc - first[l]]; used = l; break; }
-        }
-        if (sym == 0xFFu) return false;
+        const uint32_t e = lut[(uint32_t)b.bb & 127u];
+        if (!e) return false;
+        const uint32_t sym = e & 31u, used = e >> 5;
         b.bb >>= used; b.bc -= used; b.pos += used;
         uint32_t rep = 1, val = sym;
         if (sym == 16) { if (total == 0) return false; rep = vb_get(b, 2) + 3; val = prev; }
@@ -130,11 +139,11 @@ B2F_HD bool validate_dynamic_header(const uint8_t *p, uint64_t nbytes, uint64_t 
         else if (sym == 18) { rep = vb_get(b, 7) + 11; val = 0; }
         if (b.pos > limit || total + rep > want) return false;
         if (val) {
-            for (uint32_t k = 0; k < rep; k++) {
-                const uint32_t idx = total + k;
-                if (idx < hlit) { lit_kraft += 32768u >> val; nlit++; if (idx == 256) eob_len = val; }
-                else { dist_kraft += 32768u >> val; ndist++; }
-            }
+            // rep entries of width val, split at the lit/len | distance boundary
+            const uint32_t nl = total < hlit ? (total + rep <= hlit ? rep : hlit - total) : 0u, nd = rep - nl;
+            lit_kraft += nl * (32768u >> val); nlit += nl;
+            dist_kraft += nd * (32768u >> val); ndist += nd;
+            if (nl && total <= 256 && total + nl > 256) eob_len = val;
             if (lit_kraft > 32768u || dist_kraft > 32768u) return false;      // over-subscribed: give up early
         }
         total += rep; prev = val;

@@ -597,104 +597,120 @@ __device__ __forceinline__ void sb_wait(uint32_t a, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr uint32_t kSubStages = 4;                                    // segments in flight (symbols prefetched by the copy engine)
-constexpr uint32_t kSubStageBytes = kSubGroups * 32;                  // 16 symbols (32 bytes) per thread
-constexpr uint32_t kSubSmem = kSubRing + kSubStages * kSubStageBytes + kSubStages * 16 + kSubStages * 8 + 16;   // window | stages | descriptors | mbarriers | chain
+constexpr uint32_t kSubStages = 3;                                    // segments in flight (symbols prefetched by the copy engine)
+constexpr uint32_t kSubStageBytes = kSubGroups * 32;                  // 16 symbols (32 bytes) per consumer thread
+constexpr uint32_t kSubSmem = kSubRing + kSubStages * kSubStageBytes + kSubStages * 16 + 2 * kSubStages * 8;   // window | stages | descriptors | full + empty barriers
+constexpr uint32_t kSubCtaThreads = kSubThreads + 32;                 // 16 consumer warps + 1 producer warp
+constexpr uint32_t kDescStart = 1u, kDescWarm = 2u, kDescExit = 4u;   // descriptor flags (word w; the member index sits above bit 3)
+__device__ __forceinline__ void sb_arrive(uint32_t a) { asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(a) : "memory"); }
+__device__ __forceinline__ void sub_bar() { asm volatile("bar.sync 1, %0;" :: "n"(kSubThreads) : "memory"); }      // the consumer warps only
 
-__global__ void __launch_bounds__(kSubThreads, 2) k_seg_subst(SpecDev S, uint32_t part) {
+// Persistent CTAs: ONE producer thread walks the chains of the part (taken from the part's list with an atomic counter), and for
+// every segment posts a descriptor and starts a bulk copy (TMA engine) of its symbols into one of kSubStages shared-memory stages;
+// 512 consumer threads wait for the stage (mbarrier, complete_tx), substitute the markers out of the window and hand the stage back
+// (second set of mbarriers).  The producer runs up to four segments ahead -- across chain ends too -- so neither the slot records
+// (dependent L2 reads) nor the symbols (HBM) are ever waited for on the consumers' critical path: a step is ~100 instructions per
+// warp plus one barrier.
+__global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint32_t part) {
     extern __shared__ __align__(128) uint8_t ssm[];
     uint8_t *win = ssm;
     uint8_t *stage = ssm + kSubRing;
-    uint4 *desc = reinterpret_cast<uint4 *>(ssm + kSubRing + kSubStages * kSubStageBytes);          // record of the slot each stage holds
-    const uint32_t mb_a = (uint32_t)__cvta_generic_to_shared(ssm + kSubRing + kSubStages * kSubStageBytes + kSubStages * 16);
-    uint32_t *chain_s = reinterpret_cast<uint32_t *>(ssm + kSubRing + kSubStages * kSubStageBytes + kSubStages * 16 + kSubStages * 8);
+    uint4 *desc = reinterpret_cast<uint4 *>(ssm + kSubRing + kSubStages * kSubStageBytes);          // what each stage holds
+    const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(ssm + kSubRing + kSubStages * kSubStageBytes + kSubStages * 16);
+    const uint32_t empty_a = full_a + kSubStages * 8;
     const uint32_t stage_a = (uint32_t)__cvta_generic_to_shared(stage);
     const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kSubStages; i++) { sb_init(full_a + 8u * i, 1u); sb_init(empty_a + 8u * i, 1u); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= kSubThreads) {
+        // ------------------------------------------------------------------ producer (one thread)
+        if (tid != kSubThreads) return;
+        const uint16_t *__restrict__ sym = S.sym16;
+        const uint4 *__restrict__ rec = S.seg_rec;                   // n_slots + 2 entries
+        const uint32_t *__restrict__ list = S.chain_list + S.part_slot0[part];
+        const uint32_t nchains = S.chain_count[part];
+        const uint32_t part_hi = S.part_slot0[part + 1];
+        uint32_t use = 0;
+        auto post = [&](uint32_t x, uint32_t y, uint32_t n, uint32_t flags) {
+            const uint32_t k = use % kSubStages;
+            if (use >= kSubStages) sb_wait(empty_a + 8u * k, ((use / kSubStages) - 1u) & 1u);      // the consumers are done with this stage's previous use
+            desc[k] = make_uint4(x, y, n, flags);
+            uint32_t bytes = 0;
+            if (n) {
+                const uint64_t A = x | ((uint64_t)y << 32);
+                const uint32_t lead16 = (uint32_t)A & 15u;
+                bytes = ((lead16 + min(n, sub_cap(A)) + 15u) >> 4) * 32u;
+            }
+            sb_expect(full_a + 8u * k, bytes);                        // release: the descriptor is visible to whoever sees the phase complete
+            if (bytes) sb_bulk_g2s(stage_a + k * kSubStageBytes, sym + ((x | ((uint64_t)y << 32)) & ~15ull), bytes, full_a + 8u * k);
+            use++;
+        };
+        for (;;) {
+            const uint32_t ci = atomicAdd(S.chain_count + kMaxParts + part, 1u);
+            if (ci >= nchains) break;
+            uint32_t s = list[ci];
+            uint4 r0 = rec[s], r1 = rec[s + 1], r2 = rec[s + 2];
+            const uint32_t mem = r0.w >> 1;
+            if (S.mem_err[mem]) continue;                             // the member goes to the in-order kernel: markers may point anywhere
+            post(r0.x, r0.y, r0.z & 0x7FFFFFFFu, kDescStart | ((r0.z & 0x80000000u) ? kDescWarm : 0u) | (mem << 3));
+            for (;;) {
+                s++;
+                r0 = r1; r1 = r2; r2 = rec[s + 2];                   // (two records are always on their way)
+                if (s >= part_hi || (r0.w & 1u) || (r0.w >> 1) != mem) break;
+                if (r0.z) post(r0.x, r0.y, r0.z, mem << 3);           // (empty slots carry no start flag: walked through)
+            }
+        }
+        post(0, 0, 0, kDescExit);
+        return;
+    }
+    // ---------------------------------------------------------------------- consumers
     uint8_t *out = S.out;                                             // read back by later segments of the chain: no __restrict__
     const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     const uint16_t *__restrict__ sym = S.sym16;
-    const uint4 *__restrict__ rec = S.seg_rec;                       // n_slots + 2 entries
-    const uint32_t *__restrict__ list = S.chain_list + S.part_slot0[part];
-    const uint32_t nchains = S.chain_count[part];
-    const uint32_t part_hi = S.part_slot0[part + 1];
-    if (tid == 0) {
-        for (uint32_t i = 0; i < kSubStages; i++) sb_init(mb_a + 8u * i, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    uint32_t uses = 0;                                                // completed uses of the stage ring (parity of stage k = (use / kSubStages) & 1)
-    for (;;) {
-        __syncthreads();                                              // the previous chain is done with the window, the stages and chain_s
-        if (tid == 0) *chain_s = atomicAdd(S.chain_count + kMaxParts + part, 1u);
-        __syncthreads();
-        if (*chain_s >= nchains) return;
-        const uint32_t c = list[*chain_s];
-        const uint4 rc = rec[c];
-        const uint32_t mem = rc.w >> 1;
-        if (S.mem_err[mem]) continue;                                 // the member goes to the in-order kernel: markers may point anywhere
-        uint32_t rA = rc.x & 15u;                                     // window index of the current segment's first byte
-        if (rc.z & 0x80000000u) {
-            // warm start (first chain of a later part): the 32 KiB before the segment are final in out -- preload them
-            const uint64_t A = rc.x | ((uint64_t)rc.y << 32), m0 = S.mem_out_off[mem];
-            const uint32_t back = (uint32_t)min((uint64_t)32768u, A - m0);
-            for (uint32_t k = tid; k < back; k += kSubThreads) {      // byte k+1 before A -> window index rA - 1 - k (mod kSubRing)
-                int32_t r = (int32_t)rA - 1 - (int32_t)k; r += (r >> 31) & (int32_t)kSubRing;
-                win[r] = out[A - 1 - k];
-            }
-        }
-        // frontier f: next slot to fetch; slots [s, f) are in flight.  Every thread walks the records identically (two of them are
-        // always on their way), thread 0 alone talks to the copy engine.
-        uint32_t sl = c, f = c;
-        bool open = true;
-        uint4 q0 = rc, q1 = rec[c + 1];                               // rec[f], rec[f + 1]
-        auto consider = [&]() {
-            const uint4 r = q0;
-            if (f != c && (f >= part_hi || (r.w & 1u) || (r.w >> 1) != mem)) { open = false; return; }
-            const uint32_t n = r.z & 0x7FFFFFFFu;
-            const uint32_t k = (f - c + uses) % kSubStages;
-            if (tid == 0) {
-                desc[k] = make_uint4(r.x, r.y, n, 0);
-                if (n) {
-                    const uint64_t A = r.x | ((uint64_t)r.y << 32);
-                    const uint32_t lead16 = (uint32_t)A & 15u;
-                    const uint32_t bytes = ((lead16 + min(n, sub_cap(A)) + 15u) >> 4) * 32u;
-                    sb_expect(mb_a + 8u * k, bytes);
-                    sb_bulk_g2s(stage_a + k * kSubStageBytes, sym + (A - lead16), bytes, mb_a + 8u * k);
-                } else sb_expect(mb_a + 8u * k, 0u);                  // an empty slot still completes its phase of the stage's barrier
-            }
-            q0 = q1; q1 = rec[f + 2]; f++;
-        };
-#pragma unroll 1
-        for (uint32_t i = 0; i < kSubStages && open; i++) consider();
-        __syncthreads();                                              // descriptors + warm window visible
-        while (sl < f) {
-            const uint32_t use = sl - c + uses, k = use % kSubStages;
-            const uint4 r0 = desc[k];
-            const uint32_t n = r0.z;
-            if (n) {
-                const uint64_t A = r0.x | ((uint64_t)r0.y << 32);
-                const uint32_t bl0 = min(n, sub_cap(A));
-                sb_wait(mb_a + 8u * k, (use / kSubStages) & 1u);
-                const uint4 *sp = reinterpret_cast<const uint4 *>(stage + k * kSubStageBytes) + 2 * tid;
-                const bool mine = tid < ((((uint32_t)A & 15u) + bl0 + 15u) >> 4);
-                const uint4 xa = mine ? sp[0] : make_uint4(0, 0, 0, 0), xb = mine ? sp[1] : make_uint4(0, 0, 0, 0);
-                sub_step<true>(out, win, vec, A, A, bl0, rA, rA, xa, xb, tid);
-                __syncthreads();
-                for (uint32_t b0 = bl0; b0 < n;) {                    // (segments longer than one step: highly compressible data)
-                    const uint64_t B = A + b0;
-                    const uint32_t bl = min(n - b0, sub_cap(B));
-                    uint32_t rB = rA + b0; rB -= (rB / kSubRing) * kSubRing;
-                    uint4 za = make_uint4(0, 0, 0, 0), zb = za;
-                    sub_load(sym, B, bl, tid, za, zb);
-                    sub_step<false>(out, win, vec, A, B, bl, rA, rB, za, zb, tid);
-                    __syncthreads();
-                    b0 += bl;
+    uint32_t rA = 0;                                                  // window index of the current segment's first byte
+    for (uint32_t use = 0;; use++) {
+        const uint32_t k = use % kSubStages;
+        sb_wait(full_a + 8u * k, (use / kSubStages) & 1u);
+        const uint4 d = desc[k];
+        if (d.w & kDescExit) break;
+        const uint64_t A = d.x | ((uint64_t)d.y << 32);
+        const uint32_t n = d.z;
+        if (d.w & kDescStart) {
+            rA = d.x & 15u;                                           // base of the window = chain start rounded down to 16
+            if (d.w & kDescWarm) {
+                // warm start (first chain of a later part): the 32 KiB before the segment are final in out -- preload them
+                const uint64_t m0 = S.mem_out_off[d.w >> 3];
+                const uint32_t back = (uint32_t)min((uint64_t)32768u, A - m0);
+                for (uint32_t q = tid; q < back; q += kSubThreads) {  // byte q+1 before A -> window index rA - 1 - q (mod kSubRing)
+                    int32_t r = (int32_t)rA - 1 - (int32_t)q; r += (r >> 31) & (int32_t)kSubRing;
+                    win[r] = out[A - 1 - q];
                 }
-                rA += n - (n / kSubRing) * kSubRing; if (rA >= kSubRing) rA -= kSubRing;
-            } else __syncthreads();                                   // (keeps descriptor reuse ordered for empty slots too)
-            sl++;
-            if (open) consider();                                     // refill the stage that was just released
+                sub_bar();
+            }
         }
-        uses += f - c;
+        const uint32_t bl0 = min(n, sub_cap(A));
+        {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(stage + k * kSubStageBytes) + 2 * tid;
+            const bool mine = tid < ((((uint32_t)A & 15u) + bl0 + 15u) >> 4);
+            const uint4 xa = mine ? sp[0] : make_uint4(0, 0, 0, 0), xb = mine ? sp[1] : make_uint4(0, 0, 0, 0);
+            sub_step<true>(out, win, vec, A, A, bl0, rA, rA, xa, xb, tid);
+        }
+        sub_bar();                                                    // the window is complete; every consumer is done with the stage
+        if (tid == 0) sb_arrive(empty_a + 8u * k);
+        for (uint32_t b0 = bl0; b0 < n;) {                            // (segments longer than one step: highly compressible data)
+            const uint64_t B = A + b0;
+            const uint32_t bl = min(n - b0, sub_cap(B));
+            uint32_t rB = rA + b0; rB -= (rB / kSubRing) * kSubRing;
+            uint4 za = make_uint4(0, 0, 0, 0), zb = za;
+            sub_load(sym, B, bl, tid, za, zb);
+            sub_step<false>(out, win, vec, A, B, bl, rA, rB, za, zb, tid);
+            sub_bar();
+            b0 += bl;
+        }
+        rA += n - (n / kSubRing) * kSubRing; if (rA >= kSubRing) rA -= kSubRing;
     }
 }
 
@@ -739,7 +755,7 @@ cudaError_t spec_launch_segments(const SpecDev &S, uint32_t part, cudaStream_t s
 cudaError_t spec_launch_subst(const SpecDev &S, uint32_t part, cudaStream_t st) {
     if (part >= S.n_parts || S.part_slot0[part + 1] <= S.part_slot0[part]) return cudaSuccess;
     const uint32_t slots = S.part_slot0[part + 1] - S.part_slot0[part];
-    k_seg_subst<<<slots < 148u * 2u ? slots : 148u * 2u, kSubThreads, kSubSmem, st>>>(S, part);      // persistent: one chain at a time per CTA
+    k_seg_subst<<<slots < 148u * 2u ? slots : 148u * 2u, kSubCtaThreads, kSubSmem, st>>>(S, part);      // persistent: one chain at a time per CTA
     return cudaGetLastError();
 }
 

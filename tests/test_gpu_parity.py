@@ -438,6 +438,27 @@ def test_streaming_encoder_decoder_handles(ctx):
     assert list(bad.unread_decoded_data()) == G["zlib_issue71"]["partial"]
 
 
+def test_decoder_read_hands_out_complete_blocks_before_the_error(ctx):
+    """Decoder::read (src/deflate/decode.rs:136-164) decodes block by block: the blocks before a corrupt one are served by read(),
+    the error surfaces when the corrupt block is reached and its partial bytes stay in unread_decoded_data()"""
+    from libflate_b200.deflate import Decoder
+    rng = random.Random(51)
+    d = _text(rng, 300000)
+    enc = orc.encode(0, d, block_size=100000)                      # three 100000-byte blocks + the empty final block
+    enc = enc[: len(enc) - 2000]                                   # cut inside the third block: UnexpectedEof there
+    rc, partial, _, _ = orc.decode(0, bytes(enc))
+    assert rc != 0 and 200000 <= len(partial) < 300000
+    dec = Decoder(ctx, bytes(enc))
+    got = bytearray()
+    with pytest.raises(Exception):
+        while True:
+            c = dec.read(70000)
+            assert c
+            got += c
+    assert bytes(got) == d[:200000]                                # exactly the two complete blocks
+    assert bytes(got) + dec.unread_decoded_data() == partial       # the failing block's partial output
+
+
 # ------------------------------------------------------------------------------------------ BASELINE-shaped cases (reduced sizes; full sizes in bench.py)
 def test_config2_shape_many_streams_raw_deflate(ctx):
     from libflate_b200 import titles

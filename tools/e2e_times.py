@@ -33,3 +33,17 @@ for kind in ("pinned", "pageable"):
     print(f"{kind:9s} encode {e:7.2f} ms  decode {dd:7.2f} ms  round trip {e + dd:7.2f} ms = {n / (e + dd) * 1e3 / 2**30:6.2f} GiB/s")
     print("   encode stages:", " ".join(f"{a}={b:.2f}" for a, b in se["stages"]), f"| device {se['device_ms']:.2f}")
     print("   decode stages:", " ".join(f"{a}={b:.2f}" for a, b in sd["stages"]), f"| device {sd['device_ms']:.2f}")
+
+# decode pipeline depth (B2F_DECODE_PARTS is read when the context is created)
+h_enc, h_dec = native.host_alloc(cap), native.host_alloc(n + 64)
+m = ctx.encode_into(native.FMT_GZIP, d, h_enc, sched, mtime=0)
+ctx.close()
+for parts in (1, 2, 3, 4, 6, 8):
+    os.environ["B2F_DECODE_PARTS"] = str(parts)
+    c2 = native.Context(0)
+    td = []
+    for it in range(6):
+        t = time.perf_counter(); dl, used, st = c2.decode_into(native.FMT_GZIP, h_enc, m, h_dec); td.append(time.perf_counter() - t)
+    sd = c2.stats()
+    print(f"decode parts={parts}: {min(td[2:]) * 1e3:6.2f} ms wall |", " ".join(f"{a}={b:.2f}" for a, b in sd["stages"]))
+    c2.close()

@@ -3,7 +3,7 @@
 set -x
 T=$1
 mkdir -p gpurun_out
-( time timeout -s KILL 700 python -m pytest tests/test_gpu_parity.py -x -q ) > gpurun_out/${T}_parity.log 2>&1
+( time timeout -s KILL 700 python -m pytest tests/test_gpu_parity.py tests/test_gpu_abi_order.py tests/test_gpu_split.py -x -q ) > gpurun_out/${T}_parity.log 2>&1
 tail -3 gpurun_out/${T}_parity.log
 timeout -s KILL 200 python tools/stage_times.py 265 A > gpurun_out/${T}_stage.log 2>&1
 tail -3 gpurun_out/${T}_stage.log

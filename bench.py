@@ -487,7 +487,8 @@ def main():
     # algorithmic bytes per uncompressed byte of every kernel (DESIGN.md "Roofline accounting")
     alg_per_byte = {"lz_find": 1.0, "lz_fixup": 0.0, "lz_chain": 1.0, "lz_match": 1.0, "checksum": 1.0, "parse_emit": 1.0, "parse_exits": 1.0, "bitpack": ratio,
                     "find_blocks": ratio, "spec_parse": ratio, "spec_tokens": ratio, "lz_resolve": 1.0, "lz_subst": 1.0, "inflate_inorder": 1.0 + ratio,
-                    "huff_build": 0.0, "tile_bits": 0.0, "scan": 0.0, "write_headers": 0.0, "framing": 0.0, "parse_stitch": 0.0, "spec_retry": 0.0}
+                    "huff_build": 0.0, "tile_bits": 0.0, "scan": 0.0, "write_headers": 0.0, "framing": 0.0, "parse_stitch": 0.0, "spec_retry": 0.0,
+                    "checksum_final": 0.0}
 
     def roof(name):
         alg = alg_per_byte.get(name, 0.0) * units

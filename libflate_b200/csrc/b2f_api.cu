@@ -414,7 +414,7 @@ int run_checksums(b2f_ctx *ctx, const uint8_t *d_base, const std::vector<uint64_
     C.init_adler = (init && do_adler) ? (const uint32_t *)(dm + o_init) : nullptr;
     C.out_crc = (uint32_t *)(dm + o_oc); C.out_adler = (uint32_t *)(dm + o_oa);
     ctx->tm.mark(ctx->stream, "checksum");
-    CK(checksum_launch(C, do_crc, do_adler, ctx->stream));
+    CK(checksum_launch(C, do_crc, do_adler, ctx->stream, &ctx->tm));
     ctx->stats.kernel_launches += (C.n_spans ? 1 : 0) + 1;
     CK(ctx->pin_res.ensure(n * 8));
     uint32_t *hr = ctx->pin_res.as<uint32_t>();
@@ -663,7 +663,7 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
             CK(cudaEventRecord(ctx->aux_ev[1], ctx->aux[0]));
         } else {
             ctx->tm.mark(ctx->stream, "checksum");
-            CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->stream));
+            CK(checksum_launch(C, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, ctx->stream, &ctx->tm));
         }
         ctx->stats.kernel_launches += (C.n_spans ? 1 : 0) + 1;
         d_crc = C.out_crc; d_adler = C.out_adler;

@@ -39,6 +39,8 @@ inline void checksum_plan(const uint8_t *base, const uint64_t *off, const uint64
     for (size_t s = 0; s < n; s++) span0[s + 1] = span0[s] + (checksum_rows(base, off[s], len[s]) + sr - 1) / sr;
 }
 cudaError_t checksum_init_tables();
-void checksum_free_tables();
-cudaError_t checksum_launch(const ChecksumDev &C, bool do_crc, bool do_adler, cudaStream_t st);
+struct StageTimer;
+// tm (optional): a "checksum_final" mark is placed between the streaming kernel and the per-stream finalisation, so that the
+// stage called "checksum" is the HBM-bound kernel alone
+cudaError_t checksum_launch(const ChecksumDev &C, bool do_crc, bool do_adler, cudaStream_t st, StageTimer *tm = nullptr);
 }

@@ -18,6 +18,7 @@
 // The algebra was checked against zlib on the CPU first (tools/crc_interleave_model.py).
 #include "common.cuh"
 #include "checksum_dev.cuh"
+#include "encode_dev.cuh"
 
 namespace b2f {
 
@@ -269,7 +270,7 @@ cudaError_t checksum_init_tables() {
     return cudaFuncSetAttribute(k_checksum<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCkSmemCrc);
 }
 
-cudaError_t checksum_launch(const ChecksumDev &C, bool do_crc, bool do_adler, cudaStream_t st) {
+cudaError_t checksum_launch(const ChecksumDev &C, bool do_crc, bool do_adler, cudaStream_t st, StageTimer *tm) {
     if (C.n_streams == 0) return cudaSuccess;
     if (C.n_spans) {
         const uint32_t per = kCkThreads / 32;
@@ -279,6 +280,7 @@ cudaError_t checksum_launch(const ChecksumDev &C, bool do_crc, bool do_adler, cu
         else if (do_adler) k_checksum<false, true><<<grid, kCkThreads, 0, st>>>(C);
         cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
     }
+    if (tm) tm->mark(st, "checksum_final");
     k_checksum_final<<<(C.n_streams + 63) / 64, 64, 0, st>>>(C, do_crc ? 1 : 0, do_adler ? 1 : 0);
     return cudaGetLastError();
 }

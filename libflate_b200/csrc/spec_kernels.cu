@@ -570,6 +570,33 @@ __device__ __forceinline__ void sub_step(uint8_t *out, uint8_t *win, bool vec, u
 #pragma unroll
             for (uint32_t q = 0; q < 16; q++) out[p + q] = (uint8_t)v[q];
         }
+    } else if (vec && (lo == 0 || hi == 16)) {
+        // first / last group of the step: only bytes [lo, hi) are this segment's.  The window is private to the CTA: merge and store 16
+        // bytes.  out is shared with the neighbouring chains' CTAs: at most four naturally aligned stores cover exactly [lo, hi).
+        uint4 old = *reinterpret_cast<const uint4 *>(win + rp);
+        uint32_t ow[4] = { old.x, old.y, old.z, old.w };
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t b0 = 4 * k, b1 = 4 * k + 4;                // bytes of word k inside [lo, hi) -> byte mask
+            const uint32_t a = max(lo, b0), e = min(hi, b1);
+            const uint32_t m = a < e ? (e - a == 4 ? 0xFFFFFFFFu : (((1u << (8 * (e - a))) - 1u) << (8 * (a - b0)))) : 0u;
+            ow[k] = (ow[k] & ~m) | (o[k] & m);
+        }
+        *reinterpret_cast<uint4 *>(win + rp) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        uint8_t *g = out + p;
+        if (lo == 0) {                                                // bytes [0, hi): 8 + 4 + 2 + 1
+            uint32_t at = 0;
+            if (hi & 8) { *reinterpret_cast<uint2 *>(g) = make_uint2(o[0], o[1]); at = 8; }
+            if (hi & 4) { *reinterpret_cast<uint32_t *>(g + at) = o[at >> 2]; at += 4; }
+            if (hi & 2) { *reinterpret_cast<uint16_t *>(g + at) = (uint16_t)(o[at >> 2] >> (8 * (at & 3))); at += 2; }
+            if (hi & 1) g[at] = (uint8_t)(o[at >> 2] >> (8 * (at & 3)));
+        } else {                                                      // bytes [lo, 16): 1 + 2 + 4 + 8
+            uint32_t at = lo;
+            if (at & 1) { g[at] = (uint8_t)(o[at >> 2] >> (8 * (at & 3))); at += 1; }
+            if (at & 2) { *reinterpret_cast<uint16_t *>(g + at) = (uint16_t)(o[at >> 2] >> (8 * (at & 3))); at += 2; }
+            if (at & 4) { *reinterpret_cast<uint32_t *>(g + at) = o[at >> 2]; at += 4; }
+            if (at & 8) *reinterpret_cast<uint2 *>(g + at) = make_uint2(o[2], o[3]);
+        }
     } else {
 #pragma unroll
         for (uint32_t q = 0; q < 16; q++)

@@ -444,7 +444,7 @@ def test_decoder_read_hands_out_complete_blocks_before_the_error(ctx):
     from libflate_b200.deflate import Decoder
     rng = random.Random(51)
     d = _text(rng, 300000)
-    enc = orc.encode(0, d, block_size=100000)                      # three 100000-byte blocks + the empty final block
+    enc = orc.encode(0, d, [100000] * 3, block_size=100000)        # three 100000-byte blocks + the empty final block
     enc = enc[: len(enc) - 2000]                                   # cut inside the third block: UnexpectedEof there
     rc, partial, _, _ = orc.decode(0, bytes(enc))
     assert rc != 0 and 200000 <= len(partial) < 300000

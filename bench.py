@@ -441,19 +441,23 @@ def main():
         pageable_step()
     golden_note = check()
 
-    def timed(fn):
+    local = {}
+
+    def timed(fn, key):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             fn()
+        torch.cuda.synchronize()
+        local[key] = (time.perf_counter() - t0) / args.steps          # this rank alone (gathered below)
         barrier()
-        return max_over_ranks(time.perf_counter() - t0) / args.steps
+        return max_over_ranks(time.perf_counter() - t0) / args.steps  # the job: slowest rank, barrier to barrier
 
     launches0 = ctx.stats()["kernel_launches"]
-    t_dev = timed(step_device)
+    t_dev = timed(step_device, "device")
     launches = (ctx.stats()["kernel_launches"] - launches0) // args.steps
-    t_e2e = timed(step_e2e)
-    t_page = timed(pageable_step) if pageable_step else None
+    t_e2e = timed(step_e2e, "e2e")
+    t_page = timed(pageable_step, "pageable") if pageable_step else None
     staged = ctx.stats()
     extra = 0
     while len(sampler.rows) < 3 and extra < 40:          # keep the same load on the GPU (untimed) until nvidia-smi has reported
@@ -473,7 +477,7 @@ def main():
     ctx.set_overlap(True)
 
     # the one collective of the path: every rank's byte / second counters (NCCL all-gather)
-    counters = shard.gather_counters({"bytes": float(units), "seconds_device": t_dev, "seconds_e2e": t_e2e}, world, device="cuda")
+    counters = shard.gather_counters({"bytes": float(units), "seconds_device": local["device"], "seconds_e2e": local["e2e"]}, world, device="cuda")
 
     # ---------------- roofline of the dominant kernel (device time from CUDA events on the library's stream)
     stage_ms = {k: v / n_roof for k, v in stage_acc.items() if k not in ("sync", "results", "clear", "h2d", "spec_retry", "lz_pipeline")}

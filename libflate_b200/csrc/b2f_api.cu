@@ -1255,7 +1255,8 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 const size_t s_st = PS.reserve((size_t)nslots * 8), s_so = PS.reserve((size_t)nslots * 8), s_sn = PS.reserve((size_t)nslots * 4),
                              s_sb = PS.reserve((size_t)nslots * 4), s_sm = PS.reserve((size_t)nslots * 4), s_sr = PS.reserve((size_t)nslots * 4),
                              s_sc = PS.reserve((size_t)nslots), s_rec = PS.reserve(((size_t)nslots + 2) * 16), s_cl = PS.reserve((size_t)nslots * 4),
-                             s_cc = PS.reserve(2 * kMaxParts * 4);
+                             s_cc = PS.reserve(kChainCounters * kMaxParts * 4), s_sl = PS.reserve((size_t)nslots * 4), s_tl = PS.reserve((size_t)nslots * 4),
+                             s_ce = PS.reserve((size_t)nslots * 8), s_cn = PS.reserve((size_t)nslots * 4);
                 const size_t s_err = PS.reserve(n * 4);
                 CK(PS.commit(ctx->stream));
                 CK(ctx->buf[NB_SPEC_SYM].ensure(out_hi * 2 + 256));
@@ -1266,9 +1267,10 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                 S.seg_tok = PS.ptr<uint64_t>(s_st); S.seg_out = PS.ptr<uint64_t>(s_so); S.seg_ntok = PS.ptr<uint32_t>(s_sn); S.seg_nout = PS.ptr<uint32_t>(s_sb);
                 S.seg_member = PS.ptr<uint32_t>(s_sm); S.seg_reach = PS.ptr<uint32_t>(s_sr); S.seg_cut = PS.ptr<uint8_t>(s_sc);
                 S.seg_rec = PS.ptr<uint4>(s_rec); S.chain_list = PS.ptr<uint32_t>(s_cl); S.chain_count = PS.ptr<uint32_t>(s_cc);
+                S.soft_list = PS.ptr<uint32_t>(s_sl); S.tail_list = PS.ptr<uint32_t>(s_tl); S.chain_end = PS.ptr<uint64_t>(s_ce); S.chain_next_soft = PS.ptr<uint32_t>(s_cn);
                 S.sym16 = ctx->buf[NB_SPEC_SYM].as<uint16_t>(); S.mem_err = PS.ptr<uint32_t>(s_err);
                 CK(cudaMemsetAsync(S.mem_err, 0, n * 4, ctx->stream));
-                CK(cudaMemsetAsync(S.chain_count, 0, 2 * kMaxParts * 4, ctx->stream));
+                CK(cudaMemsetAsync(S.chain_count, 0, kChainCounters * kMaxParts * 4, ctx->stream));
                 CK(cudaMemsetAsync(S.seg_rec + nslots, 0, 32, ctx->stream));       // the two read-ahead records behind the last slot
                 // The LZ77 resolution is a pipeline over PARTS (runs of whole blocks): tokens -> segments (markers) -> substitution for
                 // part p, then part p+1, ...; as soon as a part is final its output is copied to the caller's memory on a side stream
@@ -1299,7 +1301,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
                         CK(spec_launch_segments(S, part, ctx->stream));
                         ctx->tm.mark(ctx->stream, "lz_subst");
                         CK(spec_launch_subst(S, part, ctx->stream));
-                        ctx->stats.kernel_launches += 4;
+                        ctx->stats.kernel_launches += 8;
                         if (any_host) CK(cudaEventRecord(ctx->part_ev[part], ctx->stream));
                     }
                     ctx->tm.mark(ctx->stream, "sync");

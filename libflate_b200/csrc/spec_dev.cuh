@@ -15,6 +15,12 @@ constexpr uint32_t kSegBytes = B2F_SEG_BYTES;   // output bytes per segment slot
 constexpr uint32_t kSegRing = 8192;       // symbols of a segment kept in shared memory by k_seg_resolve
 constexpr uint32_t kSegStepMax = 4096;    // output symbols of one 32-token step (a step with more output is cut short)
 constexpr uint32_t kMarker = 0x8000u;
+constexpr uint32_t kChainCounters = 8;
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+// A chain longer than this is cut into SOFT chains at multiples of it (of the offset in out): a soft chain is resolved with its
+// history unknown (markers relative to its own start survive), its last 32 KiB are then fixed up chain after chain and the rest in
+// parallel -- a foreign stream with no natural cut is otherwise ONE serial chain.  libflate's own blocks (1 MiB) are never cut.
+constexpr uint64_t kSuperBytes = 2u << 20;
 constexpr uint32_t kMaxParts = 8;         // pipeline depth of the LZ77 resolution (part p's output is copied out while part p+1 is resolved)
 struct SpecDev {
     const uint8_t *in; const uint64_t *in_off, *in_len;             // members
@@ -41,7 +47,11 @@ struct SpecDev {
     uint8_t *seg_cut;                                               // per slot: 1 = no segment from here on reads anything before this one (chain start)
     uint4 *seg_rec;                                                 // [n_slots + 2] packed copy for k_seg_subst: out offset lo/hi, bytes, cut | member << 1
     uint32_t *chain_list;                                           // [n_slots] chain starts, grouped by part (part p from part_slot0[p])
-    uint32_t *chain_count;                                          // [2 * kMaxParts] zeroed: chains per part | next chain to take per part
+    uint32_t *chain_count;                                          // [kChainCounters * kMaxParts] zeroed; per part: hard chains | next hard chain | soft chains |
+                                                                    // next soft chain | hard chains with soft successors | next of those | rest items taken
+    uint32_t *soft_list, *tail_list;                                // [n_slots] each, grouped by part like chain_list: soft chain starts; hard starts followed by soft ones
+    uint64_t *chain_end;                                            // [n_slots] per chain start: out offset where its chain ends
+    uint32_t *chain_next_soft;                                      // [n_slots] per chain start: slot of the soft chain that continues it (kNoSlot: none)
     uint32_t n_parts, part_slot0[kMaxParts + 1];                    // parts = slot ranges that are resolved, substituted and copied out one after the other
     uint16_t *sym16;                                                // [out span] resolved symbol or marker of every output byte (indexed like out)
     uint32_t *mem_err;                                              // per member: 1 inconsistent size, 2 match reaches before the member's first byte

@@ -15,6 +15,7 @@
 // Nothing here is trusted blindly: the host accepts a block only if its verified EndOfBlock lands exactly on the next
 // block of the chain; otherwise the stream goes to the exact in-order kernel (decode_kernels.cu).
 // Reference behaviour being reproduced: src/deflate/decode.rs:112-130, symbol.rs:193-243, libflate_lz77/src/lib.rs:164-194.
+#include <algorithm>
 #include "common.cuh"
 #include "inflate_core.cuh"
 #include "spec_dev.cuh"
@@ -521,6 +522,43 @@ __global__ void __launch_bounds__(128) k_seg_cuts(SpecDev S, uint32_t part) {
     if (cut || first) S.chain_list[lo + atomicAdd(S.chain_count + part, 1u)] = c;
 }
 
+// Soft chain starts (see kSuperBytes): a non-empty slot that is not a chain start already and whose first byte lies in another
+// kSuperBytes-aligned window of out than its predecessor's.  Every chain start (hard or soft) also learns where its chain ends and
+// whether a soft chain continues it; hard starts with a soft successor go to the tail list (k_soft_tails walks from them).
+__device__ __forceinline__ bool seg_is_soft(uint64_t A, uint64_t A_prev) { return A / kSuperBytes != A_prev / kSuperBytes; }
+__global__ void __launch_bounds__(128) k_seg_soft(SpecDev S, uint32_t part) {
+    const uint32_t lo = S.part_slot0[part], hi = S.part_slot0[part + 1];
+    const uint32_t c = lo + blockIdx.x * 128 + threadIdx.x;
+    if (c >= hi || !S.seg_nout[c]) return;
+    const uint32_t m = S.seg_member[c];
+    const uint64_t A = S.seg_out[c];
+    bool hard = S.seg_cut[c] != 0, soft = false;
+    if (!hard) {
+        uint32_t p = c;                                               // previous non-empty slot (exists: the part's first one is a hard start)
+        while (p > lo && !S.seg_nout[p - 1]) p--;
+        if (p > lo) soft = seg_is_soft(A, S.seg_out[p - 1]);
+    }
+    if (!hard && !soft) return;
+    // walk forward to the next chain start of any kind
+    uint64_t prevA = A, end = A + S.seg_nout[c];
+    uint32_t next_soft = kNoSlot;
+    for (uint32_t s = c + 1; s < hi && S.seg_member[s] == m; s++) {
+        const uint32_t n = S.seg_nout[s];
+        if (!n) continue;
+        const uint64_t a = S.seg_out[s];
+        if (S.seg_cut[s]) break;
+        if (seg_is_soft(a, prevA)) { next_soft = s; break; }
+        prevA = a; end = a + n;
+    }
+    S.chain_end[c] = end; S.chain_next_soft[c] = next_soft;
+    if (soft) {
+        uint4 r = S.seg_rec[c];
+        r.z |= 0x40000000u; r.w |= 1u;                                // soft | chain start
+        S.seg_rec[c] = r;
+        S.soft_list[lo + atomicAdd(S.chain_count + 2 * kMaxParts + part, 1u)] = c;
+    } else if (next_soft != kNoSlot) S.tail_list[lo + atomicAdd(S.chain_count + 4 * kMaxParts + part, 1u)] = c;
+}
+
 // Persistent CTAs take chains (the slots from a cut up to the next cut of the same member) from the part's list.  The last
 // kSubRing final bytes of the chain are kept in shared memory at index (offset - base) mod kSubRing, base = chain start rounded
 // down to 16, so that aligned 16-byte groups of out are aligned groups of the window.  The chain is walked slot by slot, one
@@ -603,6 +641,49 @@ __device__ __forceinline__ void sub_step(uint8_t *out, uint8_t *win, bool vec, u
             if (q >= lo && q < hi) { out[p + q] = (uint8_t)v[q]; uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing; win[r] = (uint8_t)v[q]; }
     }
 }
+// The same step for a SOFT chain (history before S0 unknown): the window holds 16-bit symbols (a byte, or a marker relative to the
+// chain's own start S0), and the step's result goes back into sym16 in place; k_soft_tails / k_soft_rest turn it into bytes.
+template <bool kFirst>
+__device__ __forceinline__ void sub_step16(uint16_t *sym, uint16_t *win, uint64_t S0, uint64_t A, uint64_t B, uint32_t bl, uint32_t rA, uint32_t rB,
+                                           const uint4 xa, const uint4 xb, uint32_t tid) {
+    const uint32_t lead16 = (uint32_t)B & 15u;
+    const uint32_t ng = (lead16 + bl + 15u) >> 4;
+    if (tid >= ng) return;
+    const uint64_t p = (B - lead16) + 16ull * tid;
+    uint32_t rp = rB + 16u * tid + kSubRing - lead16;
+    rp -= rp >= 2 * kSubRing ? 2 * kSubRing : rp >= kSubRing ? kSubRing : 0u;
+    const int32_t thr = kFirst ? 0x7FFF : (int32_t)kSubRing - 1 - (int32_t)(B - A) - (int32_t)bl;
+    const uint32_t w[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
+    const uint32_t lo = tid == 0 ? lead16 : 0u, hi = min(16u, lead16 + bl - 16u * tid);
+    uint32_t o[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+    for (uint32_t q = 0; q < 16; q++) {
+        uint32_t v = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+        int32_t r = (int32_t)rA - 1 - (int32_t)(v & 0x7FFFu);
+        r += (r >> 31) & (int32_t)kSubRing;
+        uint32_t t = win[r];
+        if (!kFirst && (v & kMarker) && (int32_t)(v & 0x7FFFu) > thr && q >= lo && q < hi) {      // the target left the window
+            const uint64_t tg = A - 1 - (uint64_t)(v & 0x7FFFu);
+            t = tg >= S0 ? (uint32_t)sym[tg] : kMarker | (uint32_t)(S0 - 1 - tg);
+        }
+        v = (v & kMarker) ? t : v;
+        o[q >> 1] |= v << (16u * (q & 1u));
+    }
+    if (lo == 0 && hi == 16) {
+        reinterpret_cast<uint4 *>(win + rp)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint4 *>(win + rp)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        reinterpret_cast<uint4 *>(sym + p)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint4 *>(sym + p)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++)
+            if (q >= lo && q < hi) {
+                const uint16_t v = (uint16_t)(o[q >> 1] >> (16u * (q & 1u)));
+                uint32_t r = rp + q; if (r >= kSubRing) r -= kSubRing;
+                win[r] = v; sym[p + q] = v;
+            }
+    }
+}
 __device__ __forceinline__ void sub_load(const uint16_t *__restrict__ sym, uint64_t B, uint32_t bl, uint32_t tid, uint4 &xa, uint4 &xb) {
     const uint32_t lead16 = (uint32_t)B & 15u;
     if (tid < ((lead16 + bl + 15u) >> 4)) {
@@ -626,7 +707,8 @@ __device__ __forceinline__ void sb_wait(uint32_t a, uint32_t parity) {
 
 constexpr uint32_t kSubStages = 3;                                    // segments in flight (symbols prefetched by the copy engine)
 constexpr uint32_t kSubStageBytes = kSubGroups * 32;                  // 16 symbols (32 bytes) per consumer thread
-constexpr uint32_t kSubSmem = kSubRing + kSubStages * kSubStageBytes + kSubStages * 16 + 2 * kSubStages * 8;   // window | stages | descriptors | full + empty barriers
+constexpr uint32_t kSubTail = kSubStages * kSubStageBytes + kSubStages * 16 + 2 * kSubStages * 8;   // stages | descriptors | full + empty barriers
+constexpr uint32_t kSubSmem = kSubRing + kSubTail, kSubSmemSoft = 2 * kSubRing + kSubTail;              // window of bytes / of 16-bit symbols
 constexpr uint32_t kSubCtaThreads = kSubThreads + 32;                 // 16 consumer warps + 1 producer warp
 constexpr uint32_t kDescStart = 1u, kDescWarm = 2u, kDescExit = 4u;   // descriptor flags (word w; the member index sits above bit 3)
 __device__ __forceinline__ void sb_arrive(uint32_t a) { asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(a) : "memory"); }
@@ -638,12 +720,14 @@ __device__ __forceinline__ void sub_bar() { asm volatile("bar.sync 1, %0;" :: "n
 // (second set of mbarriers).  The producer runs up to four segments ahead -- across chain ends too -- so neither the slot records
 // (dependent L2 reads) nor the symbols (HBM) are ever waited for on the consumers' critical path: a step is ~100 instructions per
 // warp plus one barrier.
-__global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint32_t part) {
+template <bool kSoft>
+__global__ void __launch_bounds__(kSubCtaThreads, kSoft ? 1 : 2) k_seg_subst(SpecDev S, uint32_t part) {
     extern __shared__ __align__(128) uint8_t ssm[];
+    constexpr uint32_t kWinBytes = kSoft ? 2 * kSubRing : kSubRing;
     uint8_t *win = ssm;
-    uint8_t *stage = ssm + kSubRing;
-    uint4 *desc = reinterpret_cast<uint4 *>(ssm + kSubRing + kSubStages * kSubStageBytes);          // what each stage holds
-    const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(ssm + kSubRing + kSubStages * kSubStageBytes + kSubStages * 16);
+    uint8_t *stage = ssm + kWinBytes;
+    uint4 *desc = reinterpret_cast<uint4 *>(ssm + kWinBytes + kSubStages * kSubStageBytes);          // what each stage holds
+    const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(ssm + kWinBytes + kSubStages * kSubStageBytes + kSubStages * 16);
     const uint32_t empty_a = full_a + kSubStages * 8;
     const uint32_t stage_a = (uint32_t)__cvta_generic_to_shared(stage);
     const uint32_t tid = threadIdx.x;
@@ -657,8 +741,8 @@ __global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint
         if (tid != kSubThreads) return;
         const uint16_t *__restrict__ sym = S.sym16;
         const uint4 *__restrict__ rec = S.seg_rec;                   // n_slots + 2 entries
-        const uint32_t *__restrict__ list = S.chain_list + S.part_slot0[part];
-        const uint32_t nchains = S.chain_count[part];
+        const uint32_t *__restrict__ list = (kSoft ? S.soft_list : S.chain_list) + S.part_slot0[part];
+        const uint32_t nchains = S.chain_count[(kSoft ? 2 : 0) * kMaxParts + part];
         const uint32_t part_hi = S.part_slot0[part + 1];
         uint32_t use = 0;
         auto post = [&](uint32_t x, uint32_t y, uint32_t n, uint32_t flags) {
@@ -676,13 +760,13 @@ __global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint
             use++;
         };
         for (;;) {
-            const uint32_t ci = atomicAdd(S.chain_count + kMaxParts + part, 1u);
+            const uint32_t ci = atomicAdd(S.chain_count + (kSoft ? 3 : 1) * kMaxParts + part, 1u);
             if (ci >= nchains) break;
             uint32_t s = list[ci];
             uint4 r0 = rec[s], r1 = rec[s + 1], r2 = rec[s + 2];
             const uint32_t mem = r0.w >> 1;
             if (S.mem_err[mem]) continue;                             // the member goes to the in-order kernel: markers may point anywhere
-            post(r0.x, r0.y, r0.z & 0x7FFFFFFFu, kDescStart | ((r0.z & 0x80000000u) ? kDescWarm : 0u) | (mem << 3));
+            post(r0.x, r0.y, r0.z & 0x3FFFFFFFu, kDescStart | ((r0.z & 0x80000000u) ? kDescWarm : 0u) | (mem << 3));
             for (;;) {
                 s++;
                 r0 = r1; r1 = r2; r2 = rec[s + 2];                   // (two records are always on their way)
@@ -696,8 +780,10 @@ __global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint
     // ---------------------------------------------------------------------- consumers
     uint8_t *out = S.out;                                             // read back by later segments of the chain: no __restrict__
     const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    const uint16_t *__restrict__ sym = S.sym16;
+    uint16_t *sym = S.sym16;
+    uint16_t *win16 = reinterpret_cast<uint16_t *>(win);
     uint32_t rA = 0;                                                  // window index of the current segment's first byte
+    uint64_t S0 = 0;                                                  // soft chains: the chain's first byte
     for (uint32_t use = 0;; use++) {
         const uint32_t k = use % kSubStages;
         sb_wait(full_a + 8u * k, (use / kSubStages) & 1u);
@@ -707,7 +793,15 @@ __global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint
         const uint32_t n = d.z;
         if (d.w & kDescStart) {
             rA = d.x & 15u;                                           // base of the window = chain start rounded down to 16
-            if (d.w & kDescWarm) {
+            if (kSoft) {
+                // nothing is known about the bytes before the chain: the window answers "marker relative to the chain start"
+                S0 = A;
+                for (uint32_t q = tid; q < 32768u; q += kSubThreads) {
+                    int32_t r = (int32_t)rA - 1 - (int32_t)q; r += (r >> 31) & (int32_t)kSubRing;
+                    win16[r] = (uint16_t)(kMarker | q);
+                }
+                sub_bar();
+            } else if (d.w & kDescWarm) {
                 // warm start (first chain of a later part): the 32 KiB before the segment are final in out -- preload them
                 const uint64_t m0 = S.mem_out_off[d.w >> 3];
                 const uint32_t back = (uint32_t)min((uint64_t)32768u, A - m0);
@@ -723,7 +817,8 @@ __global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint
             const uint4 *sp = reinterpret_cast<const uint4 *>(stage + k * kSubStageBytes) + 2 * tid;
             const bool mine = tid < ((((uint32_t)A & 15u) + bl0 + 15u) >> 4);
             const uint4 xa = mine ? sp[0] : make_uint4(0, 0, 0, 0), xb = mine ? sp[1] : make_uint4(0, 0, 0, 0);
-            sub_step<true>(out, win, vec, A, A, bl0, rA, rA, xa, xb, tid);
+            if (kSoft) sub_step16<true>(sym, win16, S0, A, A, bl0, rA, rA, xa, xb, tid);
+            else sub_step<true>(out, win, vec, A, A, bl0, rA, rA, xa, xb, tid);
         }
         sub_bar();                                                    // the window is complete; every consumer is done with the stage
         if (tid == 0) sb_arrive(empty_a + 8u * k);
@@ -733,11 +828,75 @@ __global__ void __launch_bounds__(kSubCtaThreads, 2) k_seg_subst(SpecDev S, uint
             uint32_t rB = rA + b0; rB -= (rB / kSubRing) * kSubRing;
             uint4 za = make_uint4(0, 0, 0, 0), zb = za;
             sub_load(sym, B, bl, tid, za, zb);
-            sub_step<false>(out, win, vec, A, B, bl, rA, rB, za, zb, tid);
+            if (kSoft) sub_step16<false>(sym, win16, S0, A, B, bl, rA, rB, za, zb, tid);
+            else sub_step<false>(out, win, vec, A, B, bl, rA, rB, za, zb, tid);
             sub_bar();
             b0 += bl;
         }
         rA += n - (n / kSubRing) * kSubRing; if (rA >= kSubRing) rA -= kSubRing;
+    }
+}
+
+// sym16 of a soft chain after k_seg_subst<true> -> bytes: a byte as it is, a marker d = the byte d+1 before the chain's start S0.
+// The markers of a chain can only point into the last 32 KiB before S0, i.e. into the TAIL of the chain before it.
+__device__ __forceinline__ void soft_finish_range(const SpecDev &S, uint64_t S0, uint64_t lo, uint64_t hi, uint32_t tid, uint32_t nthreads) {
+    uint8_t *out = S.out;
+    const uint16_t *__restrict__ sym = S.sym16;
+    const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    const uint64_t g0 = lo & ~15ull;
+    const uint64_t ng = (hi + 15 - g0) >> 4;
+    for (uint64_t g = tid; g < ng; g += nthreads) {
+        const uint64_t p = g0 + 16 * g;
+        const uint4 xa = __ldg(reinterpret_cast<const uint4 *>(sym + p)), xb = __ldg(reinterpret_cast<const uint4 *>(sym + p) + 1);
+        const uint32_t w[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
+        uint32_t o[4] = { 0, 0, 0, 0 }, v[16];
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++) {
+            v[q] = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+            if ((v[q] & kMarker) && p + q >= lo && p + q < hi) v[q] = out[S0 - 1 - (uint64_t)(v[q] & 0x7FFFu)];
+            v[q] &= 0xFFu;
+            o[q >> 2] |= v[q] << (8u * (q & 3u));
+        }
+        if (vec && p >= lo && p + 16 <= hi) *reinterpret_cast<uint4 *>(out + p) = make_uint4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (uint32_t q = 0; q < 16; q++) if (p + q >= lo && p + q < hi) out[p + q] = (uint8_t)v[q];
+        }
+    }
+}
+// Serial part of the soft chains: one CTA per hard chain that is continued by soft chains walks them in order and finishes the
+// last 32 KiB of each (whose markers point into the previous chain's last 32 KiB, final by then).
+__global__ void __launch_bounds__(512) k_soft_tails(SpecDev S, uint32_t part) {
+    __shared__ uint32_t item;
+    const uint32_t n = S.chain_count[4 * kMaxParts + part];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) item = atomicAdd(S.chain_count + 5 * kMaxParts + part, 1u);
+        __syncthreads();
+        if (item >= n) return;
+        const uint32_t c0 = S.tail_list[S.part_slot0[part] + item];
+        if (S.mem_err[S.seg_member[c0]]) continue;
+        for (uint32_t c = S.chain_next_soft[c0]; c != kNoSlot; c = S.chain_next_soft[c]) {
+            const uint64_t S0 = S.seg_out[c], S1 = S.chain_end[c];
+            soft_finish_range(S, S0, S1 - S0 > 32768u ? S1 - 32768u : S0, S1, threadIdx.x, 512);
+            __syncthreads();                                          // this tail is what the next chain's markers read
+        }
+    }
+}
+// Parallel part: everything of a soft chain before its last 32 KiB, 64 KiB per work item.
+__global__ void __launch_bounds__(256) k_soft_rest(SpecDev S, uint32_t part) {
+    const uint32_t ns = S.chain_count[2 * kMaxParts + part];
+    constexpr uint32_t kItem = 65536, kItems = (uint32_t)(kSuperBytes / kItem) + 4;     // a soft chain is at most ~kSuperBytes + one segment long
+    for (uint64_t it = blockIdx.x; it < (uint64_t)ns * kItems; it += gridDim.x) {
+        const uint32_t c = S.soft_list[S.part_slot0[part] + (uint32_t)(it / kItems)], j = (uint32_t)(it % kItems);
+        if (S.mem_err[S.seg_member[c]]) continue;
+        const uint64_t S0 = S.seg_out[c], S1 = S.chain_end[c];
+        const uint64_t end = S1 - S0 > 32768u ? S1 - 32768u : S0;     // the tail belongs to k_soft_tails
+        uint64_t lo = S0 + (uint64_t)j * kItem;
+        if (lo >= end) continue;
+        // (a chain much longer than kSuperBytes -- one giant segment -- is finished by its last item)
+        const uint64_t hi = j + 1 == kItems ? end : min(end, lo + kItem);
+        soft_finish_range(S, S0, lo, hi, threadIdx.x, 256);
     }
 }
 
@@ -747,7 +906,9 @@ cudaError_t spec_init_attributes() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_seg_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_seg_subst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubSmem);
+    e = cudaFuncSetAttribute(k_seg_subst<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubSmemSoft);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_seg_subst<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubSmem);
 }
 cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st) {
     if (!S.n_blocks) return cudaSuccess;
@@ -777,12 +938,22 @@ cudaError_t spec_launch_segments(const SpecDev &S, uint32_t part, cudaStream_t s
     k_seg_resolve<<<hi - lo, 32, kSegSmem, st>>>(S, lo);
     e = cudaGetLastError(); if (e != cudaSuccess) return e;
     k_seg_cuts<<<(hi - lo + 127) / 128, 128, 0, st>>>(S, part);
+    e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_seg_soft<<<(hi - lo + 127) / 128, 128, 0, st>>>(S, part);
     return cudaGetLastError();
 }
 cudaError_t spec_launch_subst(const SpecDev &S, uint32_t part, cudaStream_t st) {
     if (part >= S.n_parts || S.part_slot0[part + 1] <= S.part_slot0[part]) return cudaSuccess;
     const uint32_t slots = S.part_slot0[part + 1] - S.part_slot0[part];
-    k_seg_subst<<<slots < 148u * 2u ? slots : 148u * 2u, kSubCtaThreads, kSubSmem, st>>>(S, part);      // persistent: one chain at a time per CTA
+    k_seg_subst<false><<<slots < 148u * 2u ? slots : 148u * 2u, kSubCtaThreads, kSubSmem, st>>>(S, part);      // persistent: one chain at a time per CTA
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    // soft chains (streams without natural cuts only; the three kernels return at once when there are none)
+    const uint32_t nsoft_max = (uint32_t)std::min<uint64_t>(148, (uint64_t)slots * kSegBytes / kSuperBytes + 1);
+    k_seg_subst<true><<<nsoft_max, kSubCtaThreads, kSubSmemSoft, st>>>(S, part);
+    e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_soft_tails<<<std::min<uint32_t>(148u, nsoft_max), 512, 0, st>>>(S, part);
+    e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_soft_rest<<<148 * 4, 256, 0, st>>>(S, part);
     return cudaGetLastError();
 }
 

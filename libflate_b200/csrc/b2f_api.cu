@@ -129,10 +129,13 @@ struct b2f_ctx {
     bool last_is_decode = false;
     uint64_t n_spec_members = 0, n_inorder_members = 0;
     cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t copy_st = nullptr;   // early D2H of an encode's finished slices (the aux streams are busy with the slices themselves)
     cudaEvent_t aux_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t part_ev[b2f::kMaxParts] = {};
     int overlap = 1;               // run independent chunk slices of the LZ77 stage on separate streams
     CopyPool pool; Stager st_in, st_out; unsigned copy_threads = 4; size_t stage_rr = 0;
+    SlicePipe pipe;                // events of the encode's per-slice entropy stage
+    PinBuf pin_pos;                // bit positions after each slice (single-stream encodes: the packed bytes leave slice by slice)
     uint32_t max_parts = 4;        // pipeline depth of the decode's LZ77 resolution + device->host copies (B2F_DECODE_PARTS, <= kMaxParts)
     uint64_t staged_h2d = 0, staged_d2h = 0;     // bytes that went through the internal staging (pageable caller memory)
     std::vector<uint64_t> last_good;             // per stream of the last decode call: bytes of the blocks that completed before an error
@@ -227,8 +230,12 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     }
     ctx->tm.create();
     for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking);
     for (auto &ev : ctx->aux_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : ctx->part_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (int i = 0; i < 4; i++) { cudaEventCreateWithFlags(&ctx->pipe.ev_scan[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->pipe.ev_pack[i], cudaEventDisableTiming); }
+    ctx->pipe.h_pos = nullptr; ctx->pipe.n_slices = 0;
+    ctx->pin_pos.ensure(64);
     if (const char *o = getenv("B2F_OVERLAP")) ctx->overlap = atoi(o);
     if (const char *o = getenv("B2F_COPY_THREADS")) ctx->copy_threads = (unsigned)std::max(1, atoi(o));
     if (const char *o = getenv("B2F_DECODE_PARTS")) ctx->max_parts = (uint32_t)std::min<int>(kMaxParts, std::max(1, atoi(o)));
@@ -247,8 +254,11 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     ctx->pin_meta.release(); ctx->pin_res.release(); ctx->pin_ck.release(); ctx->pin_win.release(); ctx->pin_cand.release(); ctx->pin_blk.release(); ctx->pin_ser.release(); ctx->pin_sel.release();
     ctx->tm.destroy();
     for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     for (auto &ev : ctx->aux_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->part_ev) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 4; i++) { if (ctx->pipe.ev_scan[i]) cudaEventDestroy(ctx->pipe.ev_scan[i]); if (ctx->pipe.ev_pack[i]) cudaEventDestroy(ctx->pipe.ev_pack[i]); }
+    ctx->pin_pos.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -531,6 +541,8 @@ struct EncodeJob {
     const uint8_t *d_in; std::vector<uint64_t> in_off; std::vector<uint64_t> in_len;
     const uint8_t *const *h_in = nullptr;     // when set, the inputs still live on the host: encode_on_device copies them slice by slice
     std::vector<char> h_pinned;               // per stream: the host input is page-locked (DMA in place) or pageable (staged)
+    uint8_t *h_out = nullptr; bool h_out_pinned = false; size_t h_out_cap = 0;   // single-stream host encode: destination of the early copies
+    uint64_t h_copied = 0;                    // bytes of the stream already copied to h_out when encode_on_device returns
     bool part = false, part_last = true;      // b2f_encode_part_device: raw blocks of one part of a stream (no container framing)
     std::vector<uint64_t> out_bits;           // per stream: length of the DEFLATE bits (parts are not byte aligned)
     // results
@@ -631,8 +643,13 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         }
         return cudaSuccess; } };
     bool sliced = false;
+    const bool early_out = job.h_out && n_streams == 1;      // the packed bytes of a slice are copied out while the next slices are matched
+    ctx->pipe.n_slices = 0;
+    ctx->pipe.h_pos = early_out ? ctx->pin_pos.as<uint64_t>() : nullptr;
+    if (early_out && !hdr.empty()) CK(cudaMemcpyAsync(ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[0], d_hdr, hdr.size(), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u,
-                     job.h_in ? &feed : nullptr, P.chunks.data(), &sliced));
+                     job.h_in ? &feed : nullptr, P.chunks.data(), &sliced, ctx->overlap ? &ctx->pipe : nullptr));
+    const bool piped = sliced && ctx->pipe.n_slices > 0;
     if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz(sliced) * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
     // checksums over the inputs (C1/C2) -> trailers
     const bool ck_async = ctx->overlap && ctx->aux[0] != nullptr;
@@ -668,8 +685,10 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         ctx->stats.kernel_launches += (C.n_spans ? 1 : 0) + 1;
         d_crc = C.out_crc; d_adler = C.out_adler;
     }
-    CK(enc_launch_entropy(E, ctx->stream, &ctx->tm, sliced));
-    ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0, sliced);
+    if (!piped) {
+        CK(enc_launch_entropy(E, ctx->stream, &ctx->tm, sliced));
+        ctx->stats.kernel_launches += enc_launch_count_entropy(n_tiles != 0, sliced);
+    } else ctx->stats.kernel_launches += 4 * ctx->pipe.n_slices;
     if (ck_async && (fmt == B2F_FMT_GZIP || fmt == B2F_FMT_ZLIB)) CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
     ctx->tm.mark(ctx->stream, "framing");
     k_write_framing<<<(unsigned)((n_streams + 63) / 64), 64, 0, ctx->stream>>>(ctx->buf[NB_OUT].as<uint8_t>(), E.out_base, E.stream_end_bits, d_hdr,
@@ -681,6 +700,22 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     uint64_t *h_out_len = ctx->pin_res.as<uint64_t>();
     CK(cudaMemcpyAsync(h_out_len, d_out_len, n_streams * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_out_len + n_streams, E.stream_end_bits, n_streams * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    job.h_copied = 0;
+    if (piped && early_out) {
+        // Everything is queued; now follow the slices: as soon as the bit position after slice k is known, the bytes below it (minus the
+        // byte shared with the next slice) are final once slice k is packed -- copy them out on a side stream while later slices run.
+        const uint64_t *h_pos = ctx->pin_pos.as<uint64_t>();
+        const uint8_t *d_stream = ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[0];
+        for (uint32_t k = 0; k + 1 < ctx->pipe.n_slices; k++) {          // (the last slice leaves with the trailer, below)
+            CK(cudaEventSynchronize(ctx->pipe.ev_scan[k]));
+            const uint64_t upto = std::min<uint64_t>(h_pos[k] >> 3, job.h_out_cap);
+            CK(cudaStreamWaitEvent(ctx->copy_st, ctx->pipe.ev_pack[k], 0));
+            if (upto > job.h_copied) {
+                CK(d2h_copy(ctx, job.h_out + job.h_copied, d_stream + job.h_copied, upto - job.h_copied, ctx->copy_st, job.h_out_pinned));
+                job.h_copied = upto;
+            }
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     job.out_bits.resize(n_streams);
     for (size_t s = 0; s < n_streams; s++) { job.out_len[s] = h_out_len[s]; job.out_bits[s] = h_out_len[n_streams + s] - 8ull * hdr.size(); }
@@ -804,6 +839,7 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
     job.h_in = in;                         // the H2D copies are issued per slice inside the LZ77 stage
     job.h_pinned.resize(n_streams);
     for (size_t s = 0; s < n_streams; s++) job.h_pinned[s] = is_pinned_host(in[s]) ? 1 : 0;
+    if (n_streams == 1 && out[0]) { job.h_out = out[0]; job.h_out_pinned = is_pinned_host(out[0]); job.h_out_cap = out_cap[0]; }
     rc = encode_on_device(ctx, fmt, *opts, n_streams, sched, n_sched, job);
     if (rc) return rc;
     collect_stats(ctx, false);
@@ -811,9 +847,11 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
         out_len[s] = (size_t)job.out_len[s];
         if (job.out_len[s] > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
         status[s] = B2F_OK;
-        CK(d2h_copy(ctx, out[s], ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s], job.out_len[s], ctx->stream, is_pinned_host(out[s])));
+        const size_t have = n_streams == 1 ? (size_t)std::min<uint64_t>(job.h_copied, job.out_len[s]) : 0;     // copied while the encode was still running
+        CK(d2h_copy(ctx, out[s] + have, ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[s] + have, job.out_len[s] - have, ctx->stream, is_pinned_host(out[s])));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_st));
     return B2F_OK;
 }
 

@@ -75,10 +75,15 @@ struct StageTimer {
 // optional host->device feed of the input, one call per slice of chunks [c0, c1), on the stream that will process the slice
 struct SliceFeed { void *self; cudaError_t (*copy)(void *self, uint32_t c0, uint32_t c1, cudaStream_t st); };
 
+// optional pipelined entropy stage: every slice scans / packs its own blocks as soon as its LZ77 stage is done.  ev_scan[g] fires
+// when the bit position after slice g's blocks is known (copied to h_pos[g] when h_pos is set: single-stream batches), ev_pack[g]
+// when the slice's bytes are packed.
+struct SlicePipe { cudaEvent_t ev_scan[4], ev_pack[4]; uint64_t *h_pos; uint32_t n_slices; };
+
 cudaError_t enc_init_attributes();
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
                           cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed,
-                          const ChunkDesc *h_chunks, bool *sliced);   // h_chunks (host copy of E.chunks) lets slices end on DEFLATE block boundaries and
+                          const ChunkDesc *h_chunks, bool *sliced, SlicePipe *pipe = nullptr);   // h_chunks (host copy of E.chunks) lets slices end on DEFLATE block boundaries and
                                                                       // run k_huff_build / k_tile_bits for their own blocks; *sliced tells the entropy stage
 cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm, bool sliced);
 cudaError_t enc_launch_compact(const EncDev &E, uint64_t *tile_symoff, uint64_t *total, uint32_t *dst, cudaStream_t st);

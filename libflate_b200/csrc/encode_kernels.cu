@@ -901,10 +901,10 @@ __global__ void __launch_bounds__(256) k_tile_bits(EncDev E, uint32_t t_off, uin
 }
 
 // =============================================================================== K8a scan_tiles (CTA per block)
-__global__ void __launch_bounds__(256) k_scan_tiles(EncDev E) {
+__global__ void __launch_bounds__(256) k_scan_tiles(EncDev E, uint32_t b_off) {
     __shared__ uint64_t wsum[8];
     __shared__ uint64_t carry_s;
-    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t b = blockIdx.x + b_off, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const BlockDesc bd = E.blocks[b];
     if (tid == 0) carry_s = 0;
     __syncthreads();
@@ -930,11 +930,15 @@ __global__ void __launch_bounds__(256) k_scan_tiles(EncDev E) {
 }
 
 // =============================================================================== K8b scan_blocks (thread per stream)
-__global__ void __launch_bounds__(64) k_scan_blocks(EncDev E) {
+// Blocks [b0, b1) only: a stream's running bit position is carried in stream_end_bits from one range (slice) to the next, so the
+// ranges must be scanned in order (the slices' streams are chained by events).
+__global__ void __launch_bounds__(64) k_scan_blocks(EncDev E, uint32_t b0, uint32_t b1) {
     const uint32_t s = blockIdx.x * 64 + threadIdx.x;
     if (s >= E.n_streams) return;
-    uint64_t pos = (uint64_t)E.hdr_len[s] * 8;
-    for (uint32_t b = E.stream_blk0[s]; b < E.stream_blk0[s + 1]; b++) {
+    const uint32_t lo = max(b0, E.stream_blk0[s]), hi = min(b1, E.stream_blk0[s + 1]);
+    if (lo >= hi) return;
+    uint64_t pos = lo == E.stream_blk0[s] ? (uint64_t)E.hdr_len[s] * 8 : E.stream_end_bits[s];
+    for (uint32_t b = lo; b < hi; b++) {
         E.blk_bitoff[b] = pos;
         pos += E.blk_bits[b];
         if (E.blocks[b].sync_after) {       // empty stored block, byte aligned (encode.rs:225-234)
@@ -955,10 +959,10 @@ __device__ __forceinline__ void put_bits_global(uint32_t *__restrict__ out, uint
 }
 
 // =============================================================================== K9 write_headers (warp per block)
-__global__ void __launch_bounds__(128) k_write_headers(EncDev E) {
-    const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(128) k_write_headers(EncDev E, uint32_t b_off, uint32_t b_lim) {
+    const uint32_t b = b_off + blockIdx.x * 4 + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
-    if (b >= E.n_blocks) return;
+    if (b >= b_lim) return;
     const BlockDesc bd = E.blocks[b];
     const uint64_t abs0 = E.out_base[bd.stream] * 8 + E.blk_bitoff[b];
     const uint32_t hb = E.hdr_bits[b];
@@ -980,11 +984,11 @@ __global__ void __launch_bounds__(128) k_write_headers(EncDev E) {
 
 // =============================================================================== K10 bitpack (warp per tile)
 constexpr uint32_t kPackWords = 1040;
-__global__ void __launch_bounds__(256) k_bitpack(EncDev E) {
+__global__ void __launch_bounds__(256) k_bitpack(EncDev E, uint32_t t_off, uint32_t t_lim) {
     extern __shared__ uint32_t pk[];
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile = blockIdx.x * 8 + wid;
-    if (tile >= E.n_tiles) return;
+    const uint32_t tile = t_off + blockIdx.x * 8 + wid;
+    if (tile >= t_lim) return;
     const uint32_t nbits = E.tile_bits[tile];
     if (!nbits) return;
     const uint32_t c = find_owner(E.tile0, E.n_chunks, tile);
@@ -1118,7 +1122,7 @@ static cudaError_t enc_launch_lz_slice(const EncDev &E, const uint32_t *h_seg0, 
 // latency bound (one warp per segment / thread per tile) and leave most issue slots free for the match kernel of another slice.
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,
                           cudaStream_t st, StageTimer *tm, cudaStream_t *aux, cudaEvent_t *ev, uint32_t n_aux, const SliceFeed *feed,
-                          const ChunkDesc *h_chunks, bool *sliced) {
+                          const ChunkDesc *h_chunks, bool *sliced, SlicePipe *pipe) {
     if (sliced) *sliced = false;
     if (E.n_chunks == 0) return cudaSuccess;
     if (n_aux < 2 || E.n_chunks < 2 * n_aux) {
@@ -1141,11 +1145,28 @@ cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_
         if (h_chunks && c1 > c0) {
             // the histograms of this slice's blocks are complete: their code construction (one thread per block, pure latency) runs
             // here, under the other slices' LZ77 kernels, instead of on the critical path after the join
-            const uint32_t b0 = h_chunks[c0].block, b1 = c1 < E.n_chunks ? h_chunks[c1].block : h_chunks[c1 - 1].block + 1;
+            // (with the pipelined entropy stage the slices own ALL blocks: empty ones before the first / after the last chunk too)
+            const uint32_t b0 = (pipe && pipe->n_slices == 0) ? 0u : h_chunks[c0].block;
+            const uint32_t b1 = c1 < E.n_chunks ? h_chunks[c1].block : (pipe ? E.n_blocks : h_chunks[c1 - 1].block + 1);
             if (b1 > b0) { k_huff_build<<<b1 - b0, 32, 0, aux[g]>>>(E, b0, 0u); B2F_LAUNCH_CHECK(); }
             const uint32_t t0 = h_tile0[c0], t1 = h_tile0[c1];
             if (t1 > t0) { k_tile_bits<<<(t1 - t0 + 7) / 8, 256, 0, aux[g]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
             if (sliced) *sliced = true;
+            if (pipe && b1 > b0) {
+                // The whole entropy stage of the slice's blocks runs here as well, under the other slices' LZ77 kernels: only the bit
+                // position of the slice's first block depends on the previous slice (event chain), and the packed bytes of a slice
+                // can leave for the host while the next slices are still being matched (pipe->h_pos = that position, for the copy).
+                const uint32_t k = pipe->n_slices;                       // (a slice without chunks does not take part)
+                k_scan_tiles<<<b1 - b0, 256, 0, aux[g]>>>(E, b0); B2F_LAUNCH_CHECK();
+                if (k > 0) { e = cudaStreamWaitEvent(aux[g], pipe->ev_scan[k - 1], 0); if (e != cudaSuccess) return e; }
+                k_scan_blocks<<<(E.n_streams + 63) / 64, 64, 0, aux[g]>>>(E, b0, b1); B2F_LAUNCH_CHECK();
+                if (pipe->h_pos) { e = cudaMemcpyAsync(pipe->h_pos + k, E.stream_end_bits, 8, cudaMemcpyDeviceToHost, aux[g]); if (e != cudaSuccess) return e; }
+                e = cudaEventRecord(pipe->ev_scan[k], aux[g]); if (e != cudaSuccess) return e;
+                k_write_headers<<<(b1 - b0 + 3) / 4, 128, 0, aux[g]>>>(E, b0, b1); B2F_LAUNCH_CHECK();
+                if (t1 > t0) { k_bitpack<<<(t1 - t0 + 7) / 8, 256, 8 * kPackWords * 4, aux[g]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
+                e = cudaEventRecord(pipe->ev_pack[k], aux[g]); if (e != cudaSuccess) return e;
+                pipe->n_slices = k + 1;
+            }
         }
         e = cudaEventRecord(ev[1 + g], aux[g]); if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st, ev[1 + g], 0); if (e != cudaSuccess) return e;
@@ -1161,13 +1182,13 @@ cudaError_t enc_launch_entropy(const EncDev &E, cudaStream_t st, StageTimer *tm,
         k_tile_bits<<<(E.n_tiles + 7) / 8, 256, 0, st>>>(E, 0u, E.n_tiles); B2F_LAUNCH_CHECK();
     }
     if (tm) tm->mark(st, "scan");
-    k_scan_tiles<<<E.n_blocks, 256, 0, st>>>(E); B2F_LAUNCH_CHECK();
-    k_scan_blocks<<<(E.n_streams + 63) / 64, 64, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    k_scan_tiles<<<E.n_blocks, 256, 0, st>>>(E, 0u); B2F_LAUNCH_CHECK();
+    k_scan_blocks<<<(E.n_streams + 63) / 64, 64, 0, st>>>(E, 0u, E.n_blocks); B2F_LAUNCH_CHECK();
     if (tm) tm->mark(st, "write_headers");
-    k_write_headers<<<(E.n_blocks + 3) / 4, 128, 0, st>>>(E); B2F_LAUNCH_CHECK();
+    k_write_headers<<<(E.n_blocks + 3) / 4, 128, 0, st>>>(E, 0u, E.n_blocks); B2F_LAUNCH_CHECK();
     if (E.n_tiles) {
         if (tm) tm->mark(st, "bitpack");
-        k_bitpack<<<(E.n_tiles + 7) / 8, 256, 8 * kPackWords * 4, st>>>(E); B2F_LAUNCH_CHECK();
+        k_bitpack<<<(E.n_tiles + 7) / 8, 256, 8 * kPackWords * 4, st>>>(E, 0u, E.n_tiles); B2F_LAUNCH_CHECK();
     }
     return cudaSuccess;
 }

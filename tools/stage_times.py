@@ -11,8 +11,10 @@ mib = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 mode = sys.argv[2] if len(sys.argv) > 2 else "A"
 ctx = native.Context(0)
 d = titles.generate(mib << 20, seed=42)
-sched = [8192] * (d.size // 8192 + 1) if mode == "A" else None
-for it in range(3):
+sched = [8192] * (d.size // 8192 + 1) if mode in ("A", "P") else None
+if mode == "P":                       # profiling pass (ncu): every kernel once, serialised, whole-input launches
+    ctx.set_overlap(False)
+for it in range(1 if mode == "P" else 3):
     t = time.time(); enc = ctx.encode(native.FMT_GZIP, d, sched, mtime=0); te = time.time() - t
     se = ctx.stats()
     t = time.time(); st, out, used, _ = ctx.decode(native.FMT_GZIP, enc, cap=d.size + 64); td = time.time() - t

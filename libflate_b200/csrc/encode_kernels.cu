@@ -256,7 +256,8 @@ constexpr uint32_t kFindMirror = 384;                              // the first 
 constexpr uint32_t kFindLoadDepth = 8;                             // blocks per loader step (two steps in flight)
 constexpr uint32_t kFindLane = 16;                                 // bytes of a match compared by its own lane before the warp takes over
 constexpr uint32_t kFindCtrl = (4u << kHashBits) + 2 * kFindRing + kFindRing + kFindMirror;   // offset of the control words
-constexpr uint32_t kFindSmem = kFindCtrl + 16 + 4 * 32 + 8 * 2 * kFindSlots + 4 * 32;   // ctrl | cur_blk | turn + publication barriers | dummies
+constexpr uint32_t kFindQueue = kFindCtrl + 16 + 4 * 32 + 8 * 2 * kFindSlots + 4 * 32;   // ctrl | cur_blk | turn + publication barriers | dummies
+constexpr uint32_t kFindSmem = kFindQueue + 4 * 128 * kFindWarps;                     // | per-warp queue of the positions that need more than one hop
 static_assert(kFindWarps >= 1 && kFindWarps < kFindSlots && kFindCap >= 16 && kFindMirror >= 3 + 258 + 31 + 8 && kFindMirror % 128 == 0, "lz_find geometry");
 
 __device__ __forceinline__ uint32_t lds_acquire(uint32_t saddr) {
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
     uint32_t *ctrl = reinterpret_cast<uint32_t *>(fsm + kFindCtrl);                // [0] next block to claim, [1] blocks staged, [4..36) cur_blk
     const uint32_t ctrl_a = (uint32_t)__cvta_generic_to_shared(ctrl);
     const uint32_t staged_a = ctrl_a + 4, cur_a = ctrl_a + 16, mb_a = ctrl_a + 16 + 4 * 32, dummy_a = mb_a + 8 * 2 * kFindSlots;
-    const uint32_t head_a = (uint32_t)__cvta_generic_to_shared(head);
+    const uint32_t head_a = (uint32_t)__cvta_generic_to_shared(head), queue_a = head_a + kFindQueue;
     const uint32_t lring_a = (uint32_t)__cvta_generic_to_shared(lring), bring_a = (uint32_t)__cvta_generic_to_shared(bring);
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t seg = blockIdx.x + off;
@@ -423,6 +424,16 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
         if (lane == 0) mbar_arrive(mb_a + 8u * (kFindSlots + ((b + 1) & (kFindSlots - 1))));
         // ---- unordered part: the matches of this block's positions that belong to the segment (warp-uniform control flow)
         if (bpos + 127 < (int32_t)s_start) continue;
+#ifdef B2F_FIND_NOMATCH
+        continue;                                                                  // timing experiment: the ordered chain alone
+#endif
+        // Phase 1, straight-line per step: the first chain hop and the first kFindLane bytes of the comparison are ONE pass over
+        // aligned words of the position's and the candidate's bytes (five loads + four funnel shifts each): the candidate is the
+        // match iff the first three bytes agree (93 % of the positions that have a link at all), and the same XOR words give the
+        // length.  Positions whose first hop lands on another trigram of the bucket and has a successor (6 %) go to this warp's
+        // queue and are finished in phase 2 as a dense set of lanes -- the divergent walk no longer holds 32 lanes for one.
+        uint32_t qn = 0;
+        const uint32_t q_a = queue_a + 4u * 128u * w;
 #pragma unroll kFindUnroll
         for (uint32_t s4 = 0; s4 < 4; s4++) {
             const int32_t posi = bpos + (int32_t)(32 * s4 + lane);
@@ -430,49 +441,41 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
             if (!__any_sync(0xFFFFFFFFu, valid)) continue;
             const uint32_t pos = (uint32_t)posi;
             const uint32_t ri = rb + 32 * s4 + lane;
-            const uint32_t tt = s4 == 0 ? t[0] : s4 == 1 ? t[1] : s4 == 2 ? t[2] : t[3];
             const uint32_t d0 = s4 == 0 ? dd[0] : s4 == 1 ? dd[1] : s4 == 2 ? dd[2] : dd[3];
             if (valid) glk[pos] = (uint16_t)d0;                                    // written through for k_lz_fixup
-            // chain walk, at most kFindHops hops.  res: 0 no match, 1 found at ring index jx (distance total), 2 deferred
-            uint32_t d = valid ? d0 : 0u, total = 0, hops = kFindHops, jx = ri, res = 0;
-            while (d) {
-                total += d;
-                if (total > E.window) break;
-                jx = jx >= d ? jx - d : jx + kFindRing - d;
-                const uint32_t dn = s_ld16(lring_a + 2u * jx);
-                const uint32_t tj = s_ld32u(bring_a, jx) & 0xFFFFFFu;
-                if (tj == tt) { res = 1; break; }
-                d = dn;
-                if (--hops == 0) { if (d) res = 2; break; }
-            }
-            const bool found = res == 1;
-            // the first kFindLane bytes of every match by its own lane
-            const uint32_t limit = found ? min(E.max_len - 3, n - (pos + 3)) : 0u;
-            const uint32_t a = ri + 3, s = jx + 3;                                 // forward reads run into the mirror instead of wrapping
-            uint32_t k = 0;
-            bool open = found && limit != 0;
-#pragma unroll
-            for (uint32_t it = 0; it < kFindLane / 4; it++) {
-                if (open) {
-                    const uint32_t x = s_ld32u(bring_a, a + k) ^ s_ld32u(bring_a, s + k);
-                    if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; open = false; }
-                    else { k += 4; if (k >= limit) open = false; }
-                }
-            }
+            const bool linked = valid && d0 != 0u && d0 <= E.window;
+            const uint32_t jx = ri >= d0 ? ri - d0 : ri + kFindRing - d0;          // d0 == 0: the position itself (unused)
+            const uint32_t oa = bring_a + (ri & ~3u), osh = (ri & 3u) * 8u;        // forward reads run into the mirror instead of wrapping
+            const uint32_t ca = bring_a + (jx & ~3u), csh = (jx & 3u) * 8u;
+            const uint32_t ow0 = s_ld32(oa), ow1 = s_ld32(oa + 4u), ow2 = s_ld32(oa + 8u), ow3 = s_ld32(oa + 12u), ow4 = s_ld32(oa + 16u);
+            const uint32_t cw0 = s_ld32(ca), cw1 = s_ld32(ca + 4u), cw2 = s_ld32(ca + 8u), cw3 = s_ld32(ca + 12u), cw4 = s_ld32(ca + 16u);
+            const uint32_t dn = s_ld16(lring_a + 2u * jx);
+            const uint32_t o0 = __funnelshift_r(ow0, ow1, osh);
+            const uint32_t x0 = o0 ^ __funnelshift_r(cw0, cw1, csh);
+            const uint32_t x1 = __funnelshift_r(ow1, ow2, osh) ^ __funnelshift_r(cw1, cw2, csh);
+            const uint32_t x2 = __funnelshift_r(ow2, ow3, osh) ^ __funnelshift_r(cw2, cw3, csh);
+            const uint32_t x3 = __funnelshift_r(ow3, ow4, osh) ^ __funnelshift_r(cw3, cw4, csh);
+            const bool found = linked && (x0 & 0xFFFFFFu) == 0u;
+            const bool more = linked && !found && dn != 0u && kFindHops > 1;
+            uint32_t xf = x0, mb = 0;                                              // equal bytes from the position itself, 0..kFindLane
+            if (!x0) { xf = x1; mb = 4; if (!x1) { xf = x2; mb = 8; if (!x2) { xf = x3; mb = 12; } } }
+            uint32_t k = xf ? mb + ((uint32_t)(__ffs((int)xf) - 1) >> 3) : kFindLane;
+            const uint32_t limit = min(E.max_len, n - pos);                        // longest match the position may take
+            const bool open = found && k == kFindLane && limit > kFindLane;
             // longer matches: one cooperative extension per run of consecutive lanes with the same distance
             const uint32_t U = __ballot_sync(0xFFFFFFFFu, open);
             if (U) {
-                const uint32_t pd = __shfl_up_sync(0xFFFFFFFFu, total, 1);
-                const bool follower = open && lane > 0 && ((U >> (lane - 1)) & 1u) && pd == total;
+                const uint32_t pd = __shfl_up_sync(0xFFFFFFFFu, d0, 1);
+                const bool follower = open && lane > 0 && ((U >> (lane - 1)) & 1u) && pd == d0;
                 const uint32_t F = __ballot_sync(0xFFFFFFFFu, follower);
                 const uint32_t H = U & ~F;
-                uint32_t ext = 0;                                                  // head lanes: matching bytes from their a (not capped by max_len)
+                uint32_t ext = 0;                                                  // head lanes: matching bytes from their position (not capped by max_len)
                 for (uint32_t hm = H; hm; hm &= hm - 1u) {
                     const uint32_t h = (uint32_t)__ffs((int)hm) - 1u;
-                    const uint32_t ah = __shfl_sync(0xFFFFFFFFu, a, h), sh = __shfl_sync(0xFFFFFFFFu, s, h), ph = __shfl_sync(0xFFFFFFFFu, pos, h);
+                    const uint32_t ah = __shfl_sync(0xFFFFFFFFu, ri, h), sh = __shfl_sync(0xFFFFFFFFu, jx, h), ph = __shfl_sync(0xFFFFFFFFu, pos, h);
                     const uint32_t fr = ~((F >> h) >> 1);                          // followers directly after h
                     const uint32_t run = h == 31 ? 0u : (fr ? (uint32_t)__ffs((int)fr) - 1u : 31u - h);
-                    const uint32_t lim_ext = min(E.max_len - 3 + run, n - (ph + 3));
+                    const uint32_t lim_ext = min(E.max_len + run, n - ph);
                     uint32_t e = kFindLane, eh;
                     for (;;) {
                         const uint32_t o = e + 4u * lane;
@@ -480,9 +483,9 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
                         const uint32_t mm = __ballot_sync(0xFFFFFFFFu, x != 0);
                         if (mm) {
                             const uint32_t l0 = (uint32_t)__ffs((int)mm) - 1u;
-                            const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, x, l0);
-                            const uint32_t o0 = e + 4u * l0;
-                            eh = o0 >= lim_ext ? lim_ext : min(lim_ext, o0 + ((uint32_t)(__ffs((int)x0) - 1) >> 3));
+                            const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, l0);
+                            const uint32_t ol = e + 4u * l0;
+                            eh = ol >= lim_ext ? lim_ext : min(lim_ext, ol + ((uint32_t)(__ffs((int)xl) - 1) >> 3));
                             break;
                         }
                         e += 128u;
@@ -494,8 +497,39 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
                 const uint32_t eh = __shfl_sync(0xFFFFFFFFu, ext, hl);
                 if (open) k = eh - (lane - hl);
             }
-            uint32_t out = tt & 0xFFu;                                             // literal: the byte itself (length field 0)
-            if (found) { if (k > limit) k = limit; out = ((3 + k) << 16) | total; }
+            uint32_t out = o0 & 0xFFu;                                             // literal: the byte itself (length field 0)
+            if (found) out = (min(k, limit) << 16) | d0;
+            if (valid && !more) md[pos] = out;
+            const uint32_t qm = __ballot_sync(0xFFFFFFFFu, more);
+            if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_a + 4u * (qn + (uint32_t)__popc(qm & ((1u << lane) - 1u)))), "r"((32u * s4 + lane) | (d0 << 7)) : "memory");
+            qn += (uint32_t)__popc(qm);
+        }
+        // Phase 2: the queued positions, one per lane: the rest of the walk (at most kFindHops - 1 more hops), the comparison,
+        // or the hand-over to k_lz_fixup.
+        __syncwarp();
+#ifdef B2F_FIND_NOQUEUE
+        qn = 0;                                                                    // timing experiment: phase 1 alone
+#endif
+        for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+            const bool has = q0 + lane < qn;
+            const uint32_t ent = has ? s_ld32(q_a + 4u * (q0 + lane)) : 0u;
+            const uint32_t ix = ent & 127u;
+            const uint32_t pos = (uint32_t)(bpos + (int32_t)ix), ri = rb + ix;
+            const uint32_t tt = s_ld32u(bring_a, ri) & 0xFFFFFFu;
+            uint32_t total = ent >> 7, hops = kFindHops - 1, res = 0;
+            uint32_t jx = ri >= total ? ri - total : ri + kFindRing - total;
+            uint32_t d = has ? s_ld16(lring_a + 2u * jx) : 0u;
+            // res: 0 no match, 1 found at ring index jx (distance total), 2 deferred
+            while (d) {
+                total += d;
+                if (total > E.window) break;
+                jx = jx >= d ? jx - d : jx + kFindRing - d;
+                const uint32_t dn = s_ld16(lring_a + 2u * jx);
+                const uint32_t tj = s_ld32u(bring_a, jx) & 0xFFFFFFu;
+                if (tj == tt) { res = 1; break; }
+                d = dn;
+                if (--hops == 0) { if (d) res = 2; break; }
+            }
             // deferred positions go to the fix-up queue of this slice (or, should it be full, are finished here)
             bool deferred = res == 2;
             const uint32_t dm = __ballot_sync(0xFFFFFFFFu, deferred);
@@ -507,34 +541,33 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
                 if (deferred) {
                     if (slot < E.fix_cap) E.fix_pos[(uint64_t)slice * E.fix_cap + slot] = cd.off + pos;
                     else {
-                        bool f2 = false;
                         while (d) {
                             total += d;
                             if (total > E.window) break;
                             jx = jx >= d ? jx - d : jx + kFindRing - d;
                             const uint32_t dn = s_ld16(lring_a + 2u * jx);
                             const uint32_t tj = s_ld32u(bring_a, jx) & 0xFFFFFFu;
-                            if (tj == tt) { f2 = true; break; }
+                            if (tj == tt) { res = 1; break; }
                             d = dn;
-                        }
-                        if (f2) {
-                            const uint32_t lim2 = min(E.max_len - 3, n - (pos + 3));
-                            const uint32_t s2 = jx + 3;
-                            uint32_t k2 = 0;
-                            while (k2 < lim2) {
-                                const uint32_t x = s_ld32u(bring_a, a + k2) ^ s_ld32u(bring_a, s2 + k2);
-                                if (x) { k2 += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                                k2 += 4;
-                            }
-                            if (k2 > lim2) k2 = lim2;
-                            out = ((3 + k2) << 16) | total;
                         }
                         deferred = false;
                     }
                 }
             }
-            if (valid && !deferred) md[pos] = out;
+            uint32_t out = tt & 0xFFu;
+            if (res == 1) {
+                const uint32_t limit = min(E.max_len, n - pos);
+                uint32_t k = 3;
+                while (k < limit) {
+                    const uint32_t x = s_ld32u(bring_a, ri + k) ^ s_ld32u(bring_a, jx + k);
+                    if (x) { k += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    k += 4;
+                }
+                out = (min(k, limit) << 16) | total;
+            }
+            if (has && !deferred) md[pos] = out;
         }
+        __syncwarp();
     }
     if (lane == 0) sts_release(cur_a + 4u * w, 0xFFFFFFFFu);
 }

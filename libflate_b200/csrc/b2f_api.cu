@@ -130,7 +130,8 @@ struct b2f_ctx {
     uint64_t n_spec_members = 0, n_inorder_members = 0;
     cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t copy_st = nullptr;   // early D2H of an encode's finished slices (the aux streams are busy with the slices themselves)
-    cudaEvent_t aux_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t aux_ev[kMaxSlices + 1] = {};
+    uint32_t enc_slices = 4;       // slices of the encode pipeline (B2F_ENC_SLICES, 2..kMaxSlices)
     cudaEvent_t part_ev[b2f::kMaxParts] = {};
     int overlap = 1;               // run independent chunk slices of the LZ77 stage on separate streams
     CopyPool pool; Stager st_in, st_out; unsigned copy_threads = 4; size_t stage_rr = 0;
@@ -233,7 +234,8 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking);
     for (auto &ev : ctx->aux_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : ctx->part_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    for (int i = 0; i < 4; i++) { cudaEventCreateWithFlags(&ctx->pipe.ev_scan[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->pipe.ev_pack[i], cudaEventDisableTiming); }
+    for (uint32_t i = 0; i < kMaxSlices; i++) { cudaEventCreateWithFlags(&ctx->pipe.ev_scan[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->pipe.ev_pack[i], cudaEventDisableTiming); }
+    if (const char *e = getenv("B2F_ENC_SLICES")) { const int v = atoi(e); if (v >= 2 && v <= (int)kMaxSlices) ctx->enc_slices = (uint32_t)v; }
     ctx->pipe.h_pos = nullptr; ctx->pipe.n_slices = 0;
     ctx->pin_pos.ensure(64);
     if (const char *o = getenv("B2F_OVERLAP")) ctx->overlap = atoi(o);
@@ -257,7 +259,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     for (auto &ev : ctx->aux_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->part_ev) if (ev) cudaEventDestroy(ev);
-    for (int i = 0; i < 4; i++) { if (ctx->pipe.ev_scan[i]) cudaEventDestroy(ctx->pipe.ev_scan[i]); if (ctx->pipe.ev_pack[i]) cudaEventDestroy(ctx->pipe.ev_pack[i]); }
+    for (uint32_t i = 0; i < kMaxSlices; i++) { if (ctx->pipe.ev_scan[i]) cudaEventDestroy(ctx->pipe.ev_scan[i]); if (ctx->pipe.ev_pack[i]) cudaEventDestroy(ctx->pipe.ev_pack[i]); }
     ctx->pin_pos.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -647,10 +649,10 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     ctx->pipe.n_slices = 0;
     ctx->pipe.h_pos = early_out ? ctx->pin_pos.as<uint64_t>() : nullptr;
     if (early_out && !hdr.empty()) CK(cudaMemcpyAsync(ctx->buf[NB_OUT].as<uint8_t>() + job.out_base[0], d_hdr, hdr.size(), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? 4u : 0u,
+    CK(enc_launch_lz(E, P.seg0.data(), P.pt0.data(), P.tile0.data(), P.grp0.data(), ctx->stream, &ctx->tm, ctx->aux, ctx->aux_ev, ctx->overlap ? ctx->enc_slices : 0u,
                      job.h_in ? &feed : nullptr, P.chunks.data(), &sliced, ctx->overlap ? &ctx->pipe : nullptr));
     const bool piped = sliced && ctx->pipe.n_slices > 0;
-    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz(sliced) * ((ctx->overlap && n_chunks >= 8) ? 4 : 1);
+    if (n_chunks) ctx->stats.kernel_launches += enc_launch_count_lz(sliced) * (sliced ? ctx->enc_slices : 1);
     // checksums over the inputs (C1/C2) -> trailers
     const bool ck_async = ctx->overlap && ctx->aux[0] != nullptr;
     const uint32_t *d_crc = nullptr, *d_adler = nullptr;
@@ -717,6 +719,13 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    if (getenv("B2F_DEBUG_FIX")) {                    // developer aid: how many positions k_lz_find handed to the fix-up levels
+        uint32_t fc[2 * kFixSlices];
+        cudaMemcpy(fc, E.fix_count, sizeof fc, cudaMemcpyDeviceToHost);
+        uint64_t a = 0, b = 0;
+        for (uint32_t i = 0; i < kFixSlices; i++) { a += fc[i]; b += fc[kFixSlices + i]; }
+        fprintf(stderr, "[b2f] deferred positions: level 1 %llu, level 2 %llu (of %llu)\n", (unsigned long long)a, (unsigned long long)b, (unsigned long long)in_span);
+    }
     job.out_bits.resize(n_streams);
     for (size_t s = 0; s < n_streams; s++) { job.out_len[s] = h_out_len[s]; job.out_bits[s] = h_out_len[n_streams + s] - 8ull * hdr.size(); }
     return B2F_OK;

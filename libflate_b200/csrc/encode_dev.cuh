@@ -78,7 +78,9 @@ struct SliceFeed { void *self; cudaError_t (*copy)(void *self, uint32_t c0, uint
 // optional pipelined entropy stage: every slice scans / packs its own blocks as soon as its LZ77 stage is done.  ev_scan[g] fires
 // when the bit position after slice g's blocks is known (copied to h_pos[g] when h_pos is set: single-stream batches), ev_pack[g]
 // when the slice's bytes are packed.
-struct SlicePipe { cudaEvent_t ev_scan[4], ev_pack[4]; uint64_t *h_pos; uint32_t n_slices; };
+constexpr uint32_t kAuxStreams = 4;      // side streams of a context; slice g of an encode runs on stream g mod kAuxStreams
+constexpr uint32_t kMaxSlices = 8;       // = kFixSlices
+struct SlicePipe { cudaEvent_t ev_scan[kMaxSlices], ev_pack[kMaxSlices]; uint64_t *h_pos; uint32_t n_slices; };
 
 cudaError_t enc_init_attributes();
 cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_t *h_pt0, const uint32_t *h_tile0, const uint32_t *h_grp0,

@@ -233,14 +233,20 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
 #ifndef B2F_FIND_WARPS
 #define B2F_FIND_WARPS 31
 #endif
+#ifndef B2F_FIND_TURN
+#define B2F_FIND_TURN 1
+#endif
+#ifndef B2F_FIND_LOADDEPTH
+#define B2F_FIND_LOADDEPTH 8
+#endif
 #ifndef B2F_FIND_CAP
-#define B2F_FIND_CAP 64
+#define B2F_FIND_CAP (B2F_FIND_TURN > 1 ? 72 : 64)
 #endif
 #ifndef B2F_FIND_HOPS
 #define B2F_FIND_HOPS 16
 #endif
 #ifndef B2F_FIND_UNROLL
-#define B2F_FIND_UNROLL 1
+#define B2F_FIND_UNROLL 4
 #endif
 #ifndef B2F_FIND_WAIT_NS
 #define B2F_FIND_WAIT_NS 20000u
@@ -248,17 +254,20 @@ __global__ void __launch_bounds__(512) k_lz_match(EncDev E, uint32_t off) {
 constexpr int kFindUnroll = B2F_FIND_UNROLL;                          // 1: one copy of the match code, 4: one per step of a block
 constexpr uint32_t kFindWarps = B2F_FIND_WARPS;                    // worker warps; one more warp loads
 constexpr uint32_t kFindCap = B2F_FIND_CAP;
+constexpr uint32_t kFindTurn = B2F_FIND_TURN;                      // 128-byte blocks per claim = per turn of the ordered table update
+constexpr uint32_t kFindSteps = 4 * kFindTurn;                     // warp steps (32 positions) per turn
 constexpr uint32_t kFindHops = B2F_FIND_HOPS;                      // chain hops per position before it is deferred to k_lz_fixup
 constexpr uint32_t kFindSlots = 32;                                // turn mbarriers (> kFindWarps: at most kFindWarps blocks wait for their turn)
 constexpr uint32_t kFindRing = kLookback + 128 * kFindCap;
 constexpr uint32_t kFindRingBlocks = kFindRing / 128;
 constexpr uint32_t kFindMirror = 384;                              // the first bytes of the ring repeated after its end: forward reads never wrap
-constexpr uint32_t kFindLoadDepth = 8;                             // blocks per loader step (two steps in flight)
+constexpr uint32_t kFindLoadDepth = B2F_FIND_LOADDEPTH;                             // blocks per loader step (two steps in flight)
 constexpr uint32_t kFindLane = 16;                                 // bytes of a match compared by its own lane before the warp takes over
 constexpr uint32_t kFindCtrl = (4u << kHashBits) + 2 * kFindRing + kFindRing + kFindMirror;   // offset of the control words
 constexpr uint32_t kFindQueue = kFindCtrl + 16 + 4 * 32 + 8 * 2 * kFindSlots + 4 * 32;   // ctrl | cur_blk | turn + publication barriers | dummies
-constexpr uint32_t kFindSmem = kFindQueue + 4 * 128 * kFindWarps;                     // | per-warp queue of the positions that need more than one hop
+constexpr uint32_t kFindSmem = kFindQueue + 4 * 128 * kFindTurn * kFindWarps;         // | per-warp queue of the positions that need more than one hop
 static_assert(kFindWarps >= 1 && kFindWarps < kFindSlots && kFindCap >= 16 && kFindMirror >= 3 + 258 + 31 + 8 && kFindMirror % 128 == 0, "lz_find geometry");
+static_assert(kFindRingBlocks % kFindTurn == 0 && kFindCap >= kFindTurn * kFindWarps + kFindTurn + 3 && kFindSmem <= 232448 && kFindTurn <= 2, "lz_find geometry");
 
 __device__ __forceinline__ uint32_t lds_acquire(uint32_t saddr) {
     uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v;
@@ -285,7 +294,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     } while (!ok);
 }
 
+#ifdef B2F_FIND_MAXREG
+__global__ void __maxnreg__(B2F_FIND_MAXREG) k_lz_find(EncDev E, uint32_t off, uint32_t slice) {
+#else
 __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uint32_t off, uint32_t slice) {
+#endif
     extern __shared__ __align__(16) uint8_t fsm[];
     uint32_t *head = reinterpret_cast<uint32_t *>(fsm);                            // last position + 1 per hash bucket
     uint16_t *lring = reinterpret_cast<uint16_t *>(fsm + (4u << kHashBits));       // link of position q at q mod kFindRing
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
     const int64_t a0 = (int64_t)ws - (int64_t)((cd.off + ws) & 3u);
     const uint64_t g0 = (uint64_t)((int64_t)cd.off + a0);
     const uint32_t nblk = (uint32_t)(((int64_t)s_end - a0 + 127) >> 7);
+    const uint32_t n_staged = (nblk + 3 + kFindLoadDepth - 1) / kFindLoadDepth * kFindLoadDepth;   // what the loader stages in all
     for (uint32_t i = threadIdx.x; i < (1u << kHashBits); i += (kFindWarps + 1) * 32) head[i] = 0;
     if (threadIdx.x < 36) ctrl[threadIdx.x] = 0;
     if (threadIdx.x < 32) ctrl[36 + 4 * kFindSlots + threadIdx.x] = 0;             // dummy words
@@ -356,39 +370,45 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
     uint32_t *__restrict__ md = E.md + cd.off;
     uint16_t *__restrict__ glk = E.link + cd.off;
     for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(&ctrl[0], 1u);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        uint32_t tc = 0;                                                           // turn = kFindTurn consecutive blocks
+        if (lane == 0) tc = atomicAdd(&ctrl[0], 1u);
+        tc = __shfl_sync(0xFFFFFFFFu, tc, 0);
+        const uint32_t b = tc * kFindTurn;                                         // first block of the turn
         if (b >= nblk) break;
         if (lane == 0) sts_release(cur_a + 4u * w, b);                             // from now on this warp reads positions >= 128 b - 32768 only
-        const int32_t bpos = (int32_t)a0 + (int32_t)(128u * b);                    // chunk position of the block's first byte (>= -3)
-        const uint32_t rb = (b % kFindRingBlocks) * 128u;                          // ring index of the block
-        while (lds_acquire(staged_a) < b + 4u) { }                                 // blocks <= b+3 are in the ring
+        const int32_t bpos = (int32_t)a0 + (int32_t)(128u * b);                    // chunk position of the turn's first byte (>= -3)
+        const uint32_t rb = (b % kFindRingBlocks) * 128u;                          // ring index of the turn (a turn never wraps)
+        const uint32_t need = min(b + kFindTurn + 3u, n_staged);                   // the turn's blocks and the three after them are in the ring
+        while (lds_acquire(staged_a) < need) { }
         // Everything the ordered section needs is prepared first: bucket address and pos+1 per position.  Positions that are not
         // inserted (alignment lead-in, the last three bytes of the chunk, beyond the segment) go to a per-lane dummy word with
         // value 0, so the section is four unconditional shared-memory atomics.
-        uint32_t t[4], hh[4], ha[4], p1[4], oo[4], dd[4];
+        uint32_t tg[kFindSteps], hh[kFindSteps], ha[kFindSteps], p1[kFindSteps], oo[kFindSteps], dd[kFindSteps];
 #pragma unroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) {
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) {
             const int32_t pos = bpos + (int32_t)(32 * s4 + lane);
-            t[s4] = s_ld32u(bring_a, rb + 32 * s4 + lane) & 0xFFFFFFu;
+            const uint32_t t = s_ld32u(bring_a, rb + 32 * s4 + lane) & 0xFFFFFFu;
             const bool v = pos >= (int32_t)ws && pos < (int32_t)lim;
-            hh[s4] = (t[s4] * 0x9E3779B1u) >> (32 - kHashBits);
+            tg[s4] = t;
+            hh[s4] = (t * 0x9E3779B1u) >> (32 - kHashBits);
             ha[s4] = v ? head_a + 4u * hh[s4] : dummy_a + 4u * lane;
             p1[s4] = v ? (uint32_t)pos + 1u : 0u;
         }
-        asm volatile("" :: "r"(ha[0]), "r"(ha[1]), "r"(ha[2]), "r"(ha[3]), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]));
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) asm volatile("" :: "r"(ha[s4]), "r"(p1[s4]));
         // ---- stage A, ordered: the table update.  The turn is passed on as soon as the atomics are issued (the arrive is a release,
         // so they are performed before the next owner's); everything that only consumes their results comes after.
-        mbar_wait(mb_a + 8u * (b & (kFindSlots - 1)), (b / kFindSlots) & 1u);
+#ifndef B2F_FIND_NOCHAIN
+        mbar_wait(mb_a + 8u * (tc & (kFindSlots - 1)), (tc / kFindSlots) & 1u);
+#endif
 #pragma unroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) asm volatile("atom.shared.max.u32 %0, [%1], %2;" : "=r"(oo[s4]) : "r"(ha[s4]), "r"(p1[s4]) : "memory");
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) asm volatile("atom.shared.max.u32 %0, [%1], %2;" : "=r"(oo[s4]) : "r"(ha[s4]), "r"(p1[s4]) : "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(mb_a + 8u * ((b + 1) & (kFindSlots - 1)));
+        if (lane == 0) mbar_arrive(mb_a + 8u * ((tc + 1) & (kFindSlots - 1)));
         // ---- stage B: links from the returned heads
         bool bad = false;
 #pragma unroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) {
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) {
 #ifdef B2F_CHAIN_FORCE_REPAIR
             bad = true;
 #else
@@ -397,7 +417,7 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
         }
         if (__any_sync(0xFFFFFFFFu, bad)) {                                        // exact repair, see k_lz_chain
 #pragma unroll
-            for (uint32_t s4 = 0; s4 < 4; s4++) {
+            for (uint32_t s4 = 0; s4 < kFindSteps; s4++) {
                 const uint32_t key = p1[s4] ? hh[s4] : (0x80000000u | lane);
                 const uint32_t m = __match_any_sync(0xFFFFFFFFu, key);
                 const uint32_t lower = m & ((1u << lane) - 1u);
@@ -411,7 +431,7 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
             }
         }
 #pragma unroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) {
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) {
             uint32_t d = (p1[s4] && oo[s4]) ? p1[s4] - oo[s4] : 0u;
             if (d > kLookback) d = 0;
             dd[s4] = d;
@@ -420,10 +440,27 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
         __syncwarp();
         // links are published in block order (second, much shorter hand-off chain): once this warp holds the publication turn, the
         // links of every earlier block are in the ring
-        mbar_wait(mb_a + 8u * (kFindSlots + (b & (kFindSlots - 1))), (b / kFindSlots) & 1u);
-        if (lane == 0) mbar_arrive(mb_a + 8u * (kFindSlots + ((b + 1) & (kFindSlots - 1))));
+#ifndef B2F_FIND_NOCHAIN
+        mbar_wait(mb_a + 8u * (kFindSlots + (tc & (kFindSlots - 1))), (tc / kFindSlots) & 1u);
+#endif
+        if (lane == 0) mbar_arrive(mb_a + 8u * (kFindSlots + ((tc + 1) & (kFindSlots - 1))));
+        // ---- skip links.  Where the first node of a position's chain (its candidate c) has the position's own trigram, a walk that
+        // arrives at the position looking for ANOTHER trigram may go on from c's link at once: link := d + link(c).  Any link that
+        // only skips nodes of the node's own trigram keeps every walk exact, so the upgrade needs no ordering -- a walker reads the
+        // plain link or the upgraded one (16-bit stores do not tear); done right after publication, nearly every node a later walk
+        // meets is already upgraded.  Runs of a frequent trigram that share a bucket with rare ones -- chains of thousands of nodes,
+        // the reason k_lz_fixup exists -- collapse to one hop (deferred positions on titles-shaped text: 0.32 % -> 0.0x %).
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) {
+            const uint32_t ri = rb + 32 * s4 + lane, d = dd[s4];
+            const uint32_t jx = ri >= d ? ri - d : ri + kFindRing - d;
+            const uint32_t tj = s_ld32u(bring_a, jx) & 0xFFFFFFu;
+            const uint32_t dn = s_ld16(lring_a + 2u * jx);
+            const uint32_t up = d + dn;
+            if (d != 0u && tj == tg[s4]) asm volatile("st.shared.u16 [%0], %1;" :: "r"(lring_a + 2u * ri), "h"((uint16_t)((dn != 0u && up <= kLookback) ? up : 0u)) : "memory");
+        }
         // ---- unordered part: the matches of this block's positions that belong to the segment (warp-uniform control flow)
-        if (bpos + 127 < (int32_t)s_start) continue;
+        if (bpos + (int32_t)(128u * kFindTurn) - 1 < (int32_t)s_start) continue;
 #ifdef B2F_FIND_NOMATCH
         continue;                                                                  // timing experiment: the ordered chain alone
 #endif
@@ -433,16 +470,17 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
         // length.  Positions whose first hop lands on another trigram of the bucket and has a successor (6 %) go to this warp's
         // queue and are finished in phase 2 as a dense set of lanes -- the divergent walk no longer holds 32 lanes for one.
         uint32_t qn = 0;
-        const uint32_t q_a = queue_a + 4u * 128u * w;
+        const uint32_t q_a = queue_a + 4u * 128u * kFindTurn * w;
+        uint32_t *const md_l = md + ((int64_t)bpos + (int64_t)lane);               // this lane's first position of the turn: the stores of the
+        uint16_t *const glk_l = glk + ((int64_t)bpos + (int64_t)lane);             // steps are immediate offsets from these
 #pragma unroll kFindUnroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) {
+        for (uint32_t s4 = 0; s4 < kFindSteps; s4++) {
             const int32_t posi = bpos + (int32_t)(32 * s4 + lane);
             const bool valid = posi >= (int32_t)s_start && posi < (int32_t)s_end;
             if (!__any_sync(0xFFFFFFFFu, valid)) continue;
             const uint32_t pos = (uint32_t)posi;
             const uint32_t ri = rb + 32 * s4 + lane;
-            const uint32_t d0 = s4 == 0 ? dd[0] : s4 == 1 ? dd[1] : s4 == 2 ? dd[2] : dd[3];
-            if (valid) glk[pos] = (uint16_t)d0;                                    // written through for k_lz_fixup
+            const uint32_t d0 = dd[s4];                                            // the plain link: the candidate
             const bool linked = valid && d0 != 0u && d0 <= E.window;
             const uint32_t jx = ri >= d0 ? ri - d0 : ri + kFindRing - d0;          // d0 == 0: the position itself (unused)
             const uint32_t oa = bring_a + (ri & ~3u), osh = (ri & 3u) * 8u;        // forward reads run into the mirror instead of wrapping
@@ -456,6 +494,8 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
             const uint32_t x2 = __funnelshift_r(ow2, ow3, osh) ^ __funnelshift_r(cw2, cw3, csh);
             const uint32_t x3 = __funnelshift_r(ow3, ow4, osh) ^ __funnelshift_r(cw3, cw4, csh);
             const bool found = linked && (x0 & 0xFFFFFFu) == 0u;
+            const uint32_t sk = s_ld16(lring_a + 2u * ri);                         // own link after the upgrade
+            if (valid) glk_l[32 * s4] = (uint16_t)sk;                              // written through for k_lz_fixup
             const bool more = linked && !found && dn != 0u && kFindHops > 1;
             uint32_t xf = x0, mb = 0;                                              // equal bytes from the position itself, 0..kFindLane
             if (!x0) { xf = x1; mb = 4; if (!x1) { xf = x2; mb = 8; if (!x2) { xf = x3; mb = 12; } } }
@@ -499,9 +539,9 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
             }
             uint32_t out = o0 & 0xFFu;                                             // literal: the byte itself (length field 0)
             if (found) out = (min(k, limit) << 16) | d0;
-            if (valid && !more) md[pos] = out;
+            if (valid && !more) md_l[32 * s4] = out;
             const uint32_t qm = __ballot_sync(0xFFFFFFFFu, more);
-            if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_a + 4u * (qn + (uint32_t)__popc(qm & ((1u << lane) - 1u)))), "r"((32u * s4 + lane) | (d0 << 7)) : "memory");
+            if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_a + 4u * (qn + (uint32_t)__popc(qm & ((1u << lane) - 1u)))), "r"((32u * s4 + lane) | (d0 << 8)) : "memory");
             qn += (uint32_t)__popc(qm);
         }
         // Phase 2: the queued positions, one per lane: the rest of the walk (at most kFindHops - 1 more hops), the comparison,
@@ -513,10 +553,10 @@ __global__ void __launch_bounds__((kFindWarps + 1) * 32) k_lz_find(EncDev E, uin
         for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
             const bool has = q0 + lane < qn;
             const uint32_t ent = has ? s_ld32(q_a + 4u * (q0 + lane)) : 0u;
-            const uint32_t ix = ent & 127u;
+            const uint32_t ix = ent & 255u;
             const uint32_t pos = (uint32_t)(bpos + (int32_t)ix), ri = rb + ix;
             const uint32_t tt = s_ld32u(bring_a, ri) & 0xFFFFFFu;
-            uint32_t total = ent >> 7, hops = kFindHops - 1, res = 0;
+            uint32_t total = ent >> 8, hops = kFindHops - 1, res = 0;
             uint32_t jx = ri >= total ? ri - total : ri + kFindRing - total;
             uint32_t d = has ? s_ld16(lring_a + 2u * jx) : 0u;
             // res: 0 no match, 1 found at ring index jx (distance total), 2 deferred
@@ -1172,36 +1212,36 @@ cudaError_t enc_launch_lz(const EncDev &E, const uint32_t *h_seg0, const uint32_
         const uint32_t want = (uint32_t)((uint64_t)total * (g + 1) / n_aux);
         while (c1 < E.n_chunks && (h_pt0[c1] < want || g + 1 == n_aux)) c1++;
         if (h_chunks) while (c1 > c0 && c1 < E.n_chunks && h_chunks[c1].block == h_chunks[c1 - 1].block) c1++;   // whole DEFLATE blocks per slice
-        e = cudaStreamWaitEvent(aux[g], ev[0], 0); if (e != cudaSuccess) return e;
-        if (feed) { e = feed->copy(feed->self, c0, c1, aux[g]); if (e != cudaSuccess) return e; }   // this slice's H2D overlaps the previous slices' kernels
-        e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g], nullptr, g); if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(aux[g % kAuxStreams], ev[0], 0); if (e != cudaSuccess) return e;
+        if (feed) { e = feed->copy(feed->self, c0, c1, aux[g % kAuxStreams]); if (e != cudaSuccess) return e; }   // this slice's H2D overlaps the previous slices' kernels
+        e = enc_launch_lz_slice(E, h_seg0, h_pt0, h_tile0, h_grp0, c0, c1, aux[g % kAuxStreams], nullptr, g); if (e != cudaSuccess) return e;
         if (h_chunks && c1 > c0) {
             // the histograms of this slice's blocks are complete: their code construction (one thread per block, pure latency) runs
             // here, under the other slices' LZ77 kernels, instead of on the critical path after the join
             // (with the pipelined entropy stage the slices own ALL blocks: empty ones before the first / after the last chunk too)
             const uint32_t b0 = (pipe && pipe->n_slices == 0) ? 0u : h_chunks[c0].block;
             const uint32_t b1 = c1 < E.n_chunks ? h_chunks[c1].block : (pipe ? E.n_blocks : h_chunks[c1 - 1].block + 1);
-            if (b1 > b0) { k_huff_build<<<b1 - b0, 32, 0, aux[g]>>>(E, b0, 0u); B2F_LAUNCH_CHECK(); }
+            if (b1 > b0) { k_huff_build<<<b1 - b0, 32, 0, aux[g % kAuxStreams]>>>(E, b0, 0u); B2F_LAUNCH_CHECK(); }
             const uint32_t t0 = h_tile0[c0], t1 = h_tile0[c1];
-            if (t1 > t0) { k_tile_bits<<<(t1 - t0 + 7) / 8, 256, 0, aux[g]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
+            if (t1 > t0) { k_tile_bits<<<(t1 - t0 + 7) / 8, 256, 0, aux[g % kAuxStreams]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
             if (sliced) *sliced = true;
             if (pipe && b1 > b0) {
                 // The whole entropy stage of the slice's blocks runs here as well, under the other slices' LZ77 kernels: only the bit
                 // position of the slice's first block depends on the previous slice (event chain), and the packed bytes of a slice
                 // can leave for the host while the next slices are still being matched (pipe->h_pos = that position, for the copy).
                 const uint32_t k = pipe->n_slices;                       // (a slice without chunks does not take part)
-                k_scan_tiles<<<b1 - b0, 256, 0, aux[g]>>>(E, b0); B2F_LAUNCH_CHECK();
-                if (k > 0) { e = cudaStreamWaitEvent(aux[g], pipe->ev_scan[k - 1], 0); if (e != cudaSuccess) return e; }
-                k_scan_blocks<<<(E.n_streams + 63) / 64, 64, 0, aux[g]>>>(E, b0, b1); B2F_LAUNCH_CHECK();
-                if (pipe->h_pos) { e = cudaMemcpyAsync(pipe->h_pos + k, E.stream_end_bits, 8, cudaMemcpyDeviceToHost, aux[g]); if (e != cudaSuccess) return e; }
-                e = cudaEventRecord(pipe->ev_scan[k], aux[g]); if (e != cudaSuccess) return e;
-                k_write_headers<<<(b1 - b0 + 3) / 4, 128, 0, aux[g]>>>(E, b0, b1); B2F_LAUNCH_CHECK();
-                if (t1 > t0) { k_bitpack<<<(t1 - t0 + 7) / 8, 256, 8 * kPackWords * 4, aux[g]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
-                e = cudaEventRecord(pipe->ev_pack[k], aux[g]); if (e != cudaSuccess) return e;
+                k_scan_tiles<<<b1 - b0, 256, 0, aux[g % kAuxStreams]>>>(E, b0); B2F_LAUNCH_CHECK();
+                if (k > 0) { e = cudaStreamWaitEvent(aux[g % kAuxStreams], pipe->ev_scan[k - 1], 0); if (e != cudaSuccess) return e; }
+                k_scan_blocks<<<(E.n_streams + 63) / 64, 64, 0, aux[g % kAuxStreams]>>>(E, b0, b1); B2F_LAUNCH_CHECK();
+                if (pipe->h_pos) { e = cudaMemcpyAsync(pipe->h_pos + k, E.stream_end_bits, 8, cudaMemcpyDeviceToHost, aux[g % kAuxStreams]); if (e != cudaSuccess) return e; }
+                e = cudaEventRecord(pipe->ev_scan[k], aux[g % kAuxStreams]); if (e != cudaSuccess) return e;
+                k_write_headers<<<(b1 - b0 + 3) / 4, 128, 0, aux[g % kAuxStreams]>>>(E, b0, b1); B2F_LAUNCH_CHECK();
+                if (t1 > t0) { k_bitpack<<<(t1 - t0 + 7) / 8, 256, 8 * kPackWords * 4, aux[g % kAuxStreams]>>>(E, t0, t1); B2F_LAUNCH_CHECK(); }
+                e = cudaEventRecord(pipe->ev_pack[k], aux[g % kAuxStreams]); if (e != cudaSuccess) return e;
                 pipe->n_slices = k + 1;
             }
         }
-        e = cudaEventRecord(ev[1 + g], aux[g]); if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ev[1 + g], aux[g % kAuxStreams]); if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st, ev[1 + g], 0); if (e != cudaSuccess) return e;
         c0 = c1;
     }

@@ -129,6 +129,11 @@ struct b2f_ctx {
     bool last_is_decode = false;
     uint64_t n_spec_members = 0, n_inorder_members = 0;
     cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
+    // decode: a page-locked input arrives in pieces on copy_st; the block finder follows piece by piece (inflate_round)
+    static constexpr uint32_t kFeedMax = 8;
+    cudaEvent_t feed_ev[kFeedMax] = {};
+    uint64_t feed_end[kFeedMax] = {};   // device offset up to which the input has arrived with piece k
+    uint32_t feed_n = 0;
     cudaStream_t copy_st = nullptr;   // early D2H of an encode's finished slices (the aux streams are busy with the slices themselves)
     cudaEvent_t aux_ev[kMaxSlices + 1] = {};
     uint32_t enc_slices = 4;       // slices of the encode pipeline (B2F_ENC_SLICES, 2..kMaxSlices)
@@ -232,6 +237,7 @@ extern "C" int b2f_ctx_create(int device, b2f_ctx **out) {
     ctx->tm.create();
     for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking);
+    for (auto &ev : ctx->feed_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : ctx->aux_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : ctx->part_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (uint32_t i = 0; i < kMaxSlices; i++) { cudaEventCreateWithFlags(&ctx->pipe.ev_scan[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->pipe.ev_pack[i], cudaEventDisableTiming); }
@@ -257,6 +263,7 @@ extern "C" void b2f_ctx_destroy(b2f_ctx *ctx) {
     ctx->tm.destroy();
     for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+    for (auto &ev : ctx->feed_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->aux_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->part_ev) if (ev) cudaEventDestroy(ev);
     for (uint32_t i = 0; i < kMaxSlices; i++) { if (ctx->pipe.ev_scan[i]) cudaEventDestroy(ctx->pipe.ev_scan[i]); if (ctx->pipe.ev_pack[i]) cudaEventDestroy(ctx->pipe.ev_pack[i]); }
@@ -1112,16 +1119,41 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
     const size_t a_qm = PA.reserve((size_t)q_cap * 4), a_qb = PA.reserve((size_t)q_cap * 8);
     CK(PA.commit(ctx->stream));
     std::vector<uint32_t> c_member; std::vector<uint64_t> c_bit;
+    if (ctx->feed_n && big.empty()) { CK(cudaStreamWaitEvent(ctx->stream, ctx->feed_ev[ctx->feed_n - 1], 0)); ctx->feed_n = 0; }
     if (!big.empty()) {
         FindDev F;
         F.in = d_in; F.in_off = PA.ptr<uint64_t>(a_io); F.in_len = PA.ptr<uint64_t>(a_il);
         F.members = PA.ptr<uint32_t>(a_sel); F.seg0 = PA.ptr<uint32_t>(a_seg); F.n_sel = (uint32_t)big.size(); F.n_segs = seg0.back();
         F.cand_member = PA.ptr<uint32_t>(a_cm); F.cand_bit = PA.ptr<uint64_t>(a_cb); F.cand_count = PA.ptr<uint32_t>(a_cc); F.cand_cap = cand_cap;
         F.q_member = PA.ptr<uint32_t>(a_qm); F.q_bit = PA.ptr<uint64_t>(a_qb); F.q_count = PA.ptr<uint32_t>(a_cc) + 1; F.q_cap = q_cap;
-        CK(cudaMemsetAsync(F.cand_count, 0, 8, ctx->stream));
+        F.q_done = PA.ptr<uint32_t>(a_cc) + 2;
+        CK(cudaMemsetAsync(F.cand_count, 0, 16, ctx->stream));
         ctx->tm.mark(ctx->stream, "find_blocks");
-        CK(dec_launch_find(F, ctx->stream));
-        ctx->stats.kernel_launches += 2;
+        if (ctx->feed_n) {
+            // the input is still arriving (b2f_decode_batch): scan what each piece completes.  A segment is ready when its 1 KiB, the
+            // look-ahead of the cheap tests and the longest dynamic header behind its last offset (< 1 KiB) are there.
+            uint32_t s_lo = 0;
+            for (uint32_t k = 0; k < ctx->feed_n; k++) {
+                uint32_t s_hi = F.n_segs;
+                if (k + 1 < ctx->feed_n) {
+                    s_hi = 0;
+                    for (size_t j = 0; j < big.size(); j++) {
+                        const uint64_t o = in_off[big[j]], l = in_len[big[j]], have = ctx->feed_end[k];
+                        const uint32_t ns = seg0[j + 1] - seg0[j];
+                        if (o + l <= have) { s_hi = seg0[j + 1]; continue; }
+                        if (have > o + 2048) s_hi = seg0[j] + (uint32_t)std::min<uint64_t>(ns, (have - o - 2048) / 1024 + 1);
+                        else s_hi = seg0[j];
+                        break;
+                    }
+                }
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->feed_ev[k], 0));
+                if (s_hi > s_lo) { CK(dec_launch_find(F, s_lo, s_hi, ctx->stream)); ctx->stats.kernel_launches += 3; s_lo = s_hi; }
+            }
+            ctx->feed_n = 0;
+        } else {
+            CK(dec_launch_find(F, 0, F.n_segs, ctx->stream));
+            ctx->stats.kernel_launches += 3;
+        }
         ctx->tm.mark(ctx->stream, "sync");
         CK(ctx->pin_res.ensure(64));
         uint32_t *h_cnt = ctx->pin_res.as<uint32_t>();
@@ -1578,14 +1610,38 @@ extern "C" int b2f_decode_batch(b2f_ctx *ctx, int fmt, size_t n_streams, const u
     CK(ctx->buf[NB_DEC_OUT].ensure(tout + 512));
     uint8_t *d_in = ctx->buf[NB_IN].as<uint8_t>(), *d_out = ctx->buf[NB_DEC_OUT].as<uint8_t>();
     ctx->tm.mark(ctx->stream, "h2d");
-    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(h2d_copy(ctx, d_in + in_off[s], in[s], in_len[s], ctx->stream, is_pinned_host(in[s])));
+    bool all_pinned = true; uint64_t in_bytes = 0;
+    for (size_t s = 0; s < n_streams; s++) if (in_len[s]) { in_bytes += in_len[s]; all_pinned = all_pinned && is_pinned_host(in[s]); }
+    ctx->feed_n = 0;
+    if (ctx->overlap && all_pinned && in_bytes >= (8u << 20)) {
+        // page-locked input: the copy runs in pieces on its own stream and the block finder follows it piece by piece
+        const uint64_t piece = std::max<uint64_t>(4u << 20, (in_bytes + b2f_ctx::kFeedMax - 2) / (b2f_ctx::kFeedMax - 1));
+        uint64_t acc = 0;
+        for (size_t s = 0; s < n_streams; s++) {
+            for (uint64_t a = 0; a < in_len[s]; ) {
+                const uint64_t len = std::min<uint64_t>(in_len[s] - a, piece - acc);
+                CK(cudaMemcpyAsync(d_in + in_off[s] + a, in[s] + a, len, cudaMemcpyHostToDevice, ctx->copy_st));
+                a += len; acc += len;
+                if (acc >= piece && ctx->feed_n + 1 < b2f_ctx::kFeedMax) {
+                    ctx->feed_end[ctx->feed_n] = in_off[s] + a;
+                    CK(cudaEventRecord(ctx->feed_ev[ctx->feed_n++], ctx->copy_st));
+                    acc = 0;
+                }
+            }
+        }
+        ctx->feed_end[ctx->feed_n] = tin;
+        CK(cudaEventRecord(ctx->feed_ev[ctx->feed_n++], ctx->copy_st));
+    } else {
+        for (size_t s = 0; s < n_streams; s++) if (in_len[s]) CK(h2d_copy(ctx, d_in + in_off[s], in[s], in_len[s], ctx->stream, is_pinned_host(in[s])));
+    }
     InputAccess IA = { ctx, in, d_in, in_off.data(), in_len };
     // finished parts of the output are copied out while the rest is still being resolved (inflate_round)
     std::vector<uint8_t *> h_out(n_streams, nullptr); std::vector<char> h_pinned(n_streams, 0);
     for (size_t s = 0; s < n_streams; s++) { h_out[s] = out[s]; h_pinned[s] = is_pinned_host(out[s]) ? 1 : 0; }
     std::vector<uint64_t> h_copied(n_streams, 0);
     int rc = decode_core(ctx, fmt, n_streams, IA, d_in, in_off.data(), in_len, d_out, out_off.data(), out_cap, out_len, in_consumed, status, h_out.data(), &h_copied, &h_pinned);
-    if (rc) return rc;
+    if (ctx->feed_n) { ctx->feed_n = 0; cudaStreamSynchronize(ctx->copy_st); }      // nothing on the device consumed the input (early error)
+    if (rc) { cudaStreamSynchronize(ctx->copy_st); return rc; }
     ctx->tm.finish(ctx->stream);
     CK(cudaStreamSynchronize(ctx->stream));
     collect_stats(ctx, true);

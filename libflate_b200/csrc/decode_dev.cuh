@@ -25,9 +25,10 @@ struct FindDev {
     const uint32_t *seg0;                // [n_sel + 1] prefix of 1 KiB scan segments
     uint32_t n_sel, n_segs;
     uint32_t *q_member; uint64_t *q_bit; uint32_t *q_count; uint32_t q_cap;            // offsets that passed the cheap tests
+    uint32_t *q_done;                                                                  // queue entries already validated
     uint32_t *cand_member; uint64_t *cand_bit; uint32_t *cand_count; uint32_t cand_cap;   // fully validated candidates
 };
 cudaError_t dec_init_attributes();
 cudaError_t dec_launch_serial(const DecDev &D, cudaStream_t st);
-cudaError_t dec_launch_find(const FindDev &F, cudaStream_t st);
+cudaError_t dec_launch_find(const FindDev &F, uint32_t seg_lo, uint32_t seg_hi, cudaStream_t st);   // segments [seg_lo, seg_hi) of F.seg0
 }

@@ -189,16 +189,17 @@ __device__ __forceinline__ uint32_t find_owner_u32(const uint32_t *__restrict__ 
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= idx) lo = mid; else hi = mid; }
     return lo;
 }
-__global__ void __launch_bounds__(256) k_find_blocks(FindDev F) {
+__global__ void __launch_bounds__(256) k_find_blocks(FindDev F, uint32_t seg_off) {
     __shared__ __align__(16) uint32_t sw[(kFindBytes + 64) / 4];
     __shared__ uint16_t qa[kFindBytes * 8], qb[kFindBytes * 8];
     __shared__ uint32_t na, nb;
     const uint32_t tid = threadIdx.x;
-    const uint32_t sel = find_owner_u32(F.seg0, F.n_sel, blockIdx.x);
+    const uint32_t seg = blockIdx.x + seg_off;
+    const uint32_t sel = find_owner_u32(F.seg0, F.n_sel, seg);
     const uint32_t m = F.members[sel];
     const uint64_t len = F.in_len[m];
     const uint8_t *__restrict__ p = F.in + F.in_off[m];
-    const uint64_t b0 = (uint64_t)(blockIdx.x - F.seg0[sel]) * kFindBytes;
+    const uint64_t b0 = (uint64_t)(seg - F.seg0[sel]) * kFindBytes;
     if (tid == 0) { na = 0; nb = 0; }
     for (uint32_t i = tid; i < (kFindBytes + 64) / 4; i += 256) {
         uint32_t v = 0;
@@ -234,17 +235,19 @@ __global__ void __launch_bounds__(256) k_find_blocks(FindDev F) {
         if (slot < F.q_cap) { F.q_member[slot] = m; F.q_bit[slot] = b0 * 8 + qb[i]; }
     }
 }
+// Validates the queue entries [*q_done, *q_count): the finder may run piece by piece while the input is still arriving.
 __global__ void __launch_bounds__(128) k_validate_candidates(FindDev F) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     const uint32_t nq = min(*F.q_count, F.q_cap);
-    if (i >= nq) return;
-    const uint32_t m = F.q_member[i];
-    const uint64_t q = F.q_bit[i];
-    if (validate_dynamic_header(F.in + F.in_off[m], F.in_len[m], q)) {
-        const uint32_t slot = atomicAdd(F.cand_count, 1u);
-        if (slot < F.cand_cap) { F.cand_member[slot] = m; F.cand_bit[slot] = q; }
+    for (uint32_t i = *F.q_done + blockIdx.x * 128 + threadIdx.x; i < nq; i += gridDim.x * 128) {
+        const uint32_t m = F.q_member[i];
+        const uint64_t q = F.q_bit[i];
+        if (validate_dynamic_header(F.in + F.in_off[m], F.in_len[m], q)) {
+            const uint32_t slot = atomicAdd(F.cand_count, 1u);
+            if (slot < F.cand_cap) { F.cand_member[slot] = m; F.cand_bit[slot] = q; }
+        }
     }
 }
+__global__ void k_find_advance(FindDev F) { *F.q_done = min(*F.q_count, F.q_cap); }
 
 cudaError_t dec_init_attributes() {
     return cudaFuncSetAttribute(k_inflate_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);
@@ -254,11 +257,15 @@ cudaError_t dec_launch_serial(const DecDev &D, cudaStream_t st) {
     k_inflate_streams<<<D.n, 32, kWinSmem, st>>>(D);
     return cudaGetLastError();
 }
-cudaError_t dec_launch_find(const FindDev &F, cudaStream_t st) {
-    if (F.n_segs == 0) return cudaSuccess;
-    k_find_blocks<<<F.n_segs, 256, 0, st>>>(F);
+cudaError_t dec_launch_find(const FindDev &F, uint32_t seg_lo, uint32_t seg_hi, cudaStream_t st) {
+    if (seg_hi <= seg_lo) return cudaSuccess;
+    k_find_blocks<<<seg_hi - seg_lo, 256, 0, st>>>(F, seg_lo);
     cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
-    k_validate_candidates<<<(F.q_cap + 127) / 128, 128, 0, st>>>(F);      // grid sized for the queue capacity; idle threads exit at once
+    // grid sized for the usual share of survivors of this range (the kernel strides over whatever was queued)
+    const uint64_t want = (uint64_t)(seg_hi - seg_lo) * kFindBytes / 32 + 8192;
+    k_validate_candidates<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(F);
+    e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    k_find_advance<<<1, 1, 0, st>>>(F);
     return cudaGetLastError();
 }
 }  // namespace b2f

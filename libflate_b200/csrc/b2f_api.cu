@@ -1193,7 +1193,7 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
             bm[i] = cands[i].first; bb[i] = cands[i].second;
             // A candidate's extent runs to the candidate AFTER the next one: the finder's rare false positives (about one per 300 Mbit)
             // lie inside a true block, and with the doubled extent that block's parse simply runs across it to its EndOfBlock -- no second
-            // parse of the whole stream.  The parse is latency bound (one thread per 4096-bit subsegment), so the extra threads are nearly
+            // parse of the whole stream.  The parse is latency bound (one thread per subsegment), so the extra threads are nearly
             // free; two false positives in a row still take the drop-and-retry path below.
             be[i] = (i + 2 < ncand && cands[i + 2].first == bm[i]) ? cands[i + 2].second : in_len[bm[i]] * 8;
             const uint64_t bits = be[i] - bb[i];
@@ -1226,15 +1226,31 @@ int inflate_round(b2f_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const std::
             S.changed = carve<uint32_t>(sp, 64);
             CK(cudaMemsetAsync(S.changed, 0, 256, ctx->stream));
             ctx->tm.mark(ctx->stream, "spec_parse");
-            CK(spec_launch_parse(S, 5, ctx->stream));
+            uint32_t rounds = 5;
+            CK(spec_launch_parse(S, 0, rounds, ctx->stream));
             ctx->stats.kernel_launches += 7;
             ctx->tm.mark(ctx->stream, "sync");
             const size_t res_bytes = r_end - r_dr;
-            CK(ctx->pin_res.ensure(res_bytes + 64));
+            CK(ctx->pin_res.ensure(res_bytes + 256 + 64));
             uint8_t *hr = ctx->pin_res.as<uint8_t>();
-            CK(cudaMemcpyAsync(hr, PB.ptr<uint8_t>(r_dr), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            const uint32_t *h_changed = (const uint32_t *)(hr + align_up(res_bytes, 16));
             const uint32_t *h_fl = (const uint32_t *)(hr + (r_fl - r_dr)), *h_st = (const uint32_t *)(hr + (r_st - r_dr)), *h_ee = (const uint32_t *)(hr + (r_ee - r_dr));
+            for (;;) {
+                CK(cudaMemcpyAsync(hr, PB.ptr<uint8_t>(r_dr), res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(hr + align_up(res_bytes, 16), S.changed, 256, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                // Five rounds settle ordinary data.  Where codes do not self-synchronise (long runs: one- and two-bit codes) a wrong
+                // start moves on by one subsegment per round; as long as the last round still changed something and a block fails
+                // verification, iterate further (cheap: only the changed subsegments are decoded again) instead of giving the
+                // member to the in-order kernel.
+                bool any_bad = false;
+                for (size_t i = 0; i < ncand && !any_bad; i++) any_bad = h_st[i] == 1;
+                if (!any_bad || h_changed[rounds - 1] == 0 || rounds + 8 > 61) break;
+                ctx->tm.mark(ctx->stream, "spec_parse");
+                CK(spec_launch_parse(S, rounds, rounds + 8, ctx->stream));
+                rounds += 8; ctx->stats.kernel_launches += 9;
+                ctx->tm.mark(ctx->stream, "sync");
+            }
             const uint64_t *h_no = (const uint64_t *)(hr + (r_no - r_dr)), *h_nt = (const uint64_t *)(hr + (r_nt - r_dr));
             // ---- phase C: chain walk from bit 0 of every big member
             std::vector<uint32_t> blk_sel(ncand, 0); std::vector<uint64_t> blk_out0(ncand, 0), blk_tok0(ncand, 0);

@@ -3,8 +3,14 @@
 #include <stdint.h>
 #include "inflate_core.cuh"
 namespace b2f {
-constexpr uint32_t kSpecBits = 4096;      // bits per speculative subsegment (one thread each)
-constexpr uint32_t kSpecCta = 128;        // subsegments per CTA (all of one block)
+#ifndef B2F_SPEC_BITS
+#define B2F_SPEC_BITS 2048
+#endif
+#ifndef B2F_SPEC_CTA
+#define B2F_SPEC_CTA 128
+#endif
+constexpr uint32_t kSpecBits = B2F_SPEC_BITS;      // bits per speculative subsegment (one thread each)
+constexpr uint32_t kSpecCta = B2F_SPEC_CTA;        // subsegments per CTA (all of one block)
 // LZ77 resolution works on SEGMENTS: runs of subsegments of one block whose output starts inside the same kSegBytes-aligned
 // window of the block's output.  One warp resolves a segment on its own; bytes copied from before the segment's first byte
 // become 16-bit MARKERS (0x8000 | distance before the segment start - 1) that a second pass substitutes in stream order.
@@ -57,7 +63,7 @@ struct SpecDev {
     uint32_t *mem_err;                                              // per member: 1 inconsistent size, 2 match reaches before the member's first byte
 };
 cudaError_t spec_init_attributes();
-cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st);
+cudaError_t spec_launch_parse(const SpecDev &S, uint32_t r0, uint32_t r1, cudaStream_t st);   // rounds [r0, r1) + verification
 cudaError_t spec_launch_tokens(const SpecDev &S, uint32_t cta_lo, uint32_t cta_hi, cudaStream_t st);   // CTAs (128 subsegments each) [cta_lo, cta_hi)
 cudaError_t spec_launch_segments(const SpecDev &S, uint32_t part, cudaStream_t st);   // k_seg_plan + k_seg_resolve + k_seg_cuts over the part's slots
 cudaError_t spec_launch_subst(const SpecDev &S, uint32_t part, cudaStream_t st);      // k_seg_subst over the chains that start in the part

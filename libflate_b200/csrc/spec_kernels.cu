@@ -2,7 +2,7 @@
 //
 // A DEFLATE block is one serial bit stream, but Huffman parses self-synchronise: a decoder started at an arbitrary bit
 // falls into step with the true parse after a few symbols.  Each candidate block (from the boundary finder) is cut into
-// 4096-bit subsegments, one THREAD each:
+// kSpecBits-bit (2048) subsegments, one THREAD each:
 //   k_spec_headers   warp per block : parse the dynamic header, build the decode tables (kept in HBM, 12 KiB per block)
 //   k_spec_round     thread per subsegment, Jacobi iteration: round 0 decodes from the subsegment's first bit (the first
 //                    subsegment from the true first symbol); round r restarts from the exit of the left neighbour of
@@ -910,18 +910,23 @@ cudaError_t spec_init_attributes() {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_seg_subst<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSubSmem);
 }
-cudaError_t spec_launch_parse(const SpecDev &S, uint32_t rounds, cudaStream_t st) {
-    if (!S.n_blocks) return cudaSuccess;
-    k_spec_headers<<<(S.n_blocks + 3) / 4, 128, 4 * sizeof(InflateTables), st>>>(S);
-    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+// Rounds [r0, r1) of the Jacobi iteration, then the verification.  r0 = 0 also parses the block headers; a later call continues
+// an iteration that had not converged (regions whose codes do not self-synchronise settle one subsegment per round).
+cudaError_t spec_launch_parse(const SpecDev &S, uint32_t r0, uint32_t r1, cudaStream_t st) {
+    if (!S.n_blocks || r1 <= r0) return cudaSuccess;
+    cudaError_t e;
+    if (r0 == 0) {
+        k_spec_headers<<<(S.n_blocks + 3) / 4, 128, 4 * sizeof(InflateTables), st>>>(S);
+        e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    }
     SpecDev R = S;
-    for (uint32_t r = 0; r < rounds; r++) {
-        // Jacobi iteration: round r reads the exits of round r-1 (s_exit_prev) and writes s_exit
+    for (uint32_t r = r0; r < r1; r++) {
+        // round r reads the exits of round r-1 (s_exit_prev) and writes s_exit
         if (r & 1) { R.s_exit = S.s_exit_prev; R.s_exit_prev = S.s_exit; } else { R.s_exit = S.s_exit; R.s_exit_prev = S.s_exit_prev; }
         k_spec_round<<<S.n_ctas, kSpecCta, 0, st>>>(R, r);
         e = cudaGetLastError(); if (e != cudaSuccess) return e;
     }
-    if (((rounds - 1) & 1)) { R.s_exit = S.s_exit_prev; R.s_exit_prev = S.s_exit; } else { R.s_exit = S.s_exit; R.s_exit_prev = S.s_exit_prev; }
+    if (((r1 - 1) & 1)) { R.s_exit = S.s_exit_prev; R.s_exit_prev = S.s_exit; } else { R.s_exit = S.s_exit; R.s_exit_prev = S.s_exit_prev; }
     k_spec_verify<<<S.n_blocks, 256, 0, st>>>(R);
     return cudaGetLastError();
 }

@@ -394,6 +394,45 @@ def test_pageable_and_page_locked_callers_get_the_same_bytes(ctx):
             native.host_free(a)
 
 
+def test_page_locked_input_arrives_in_pieces(ctx):
+    """b2f_decode_batch with page-locked inputs of >= 8 MiB in all: the H2D copy runs in pieces on its own stream and the block
+    finder follows it piece by piece (pieces cross stream boundaries; a small and an incompressible stream ride along)"""
+    import ctypes as C
+    from libflate_b200 import native, titles
+    rng = random.Random(77)
+    plains = [titles.generate(30 << 20, seed=21).tobytes(), titles.generate(12 << 20, seed=22).tobytes(), _text(rng, 1000),
+              bytes(rng.getrandbits(8) for _ in range(1 << 20)) * 2]
+    encs = [orc.encode(orc.FMT_GZIP, p, [8192] * (len(p) // 8192 + 1), mtime=0) for p in plains]
+    assert sum(map(len, encs)) >= (8 << 20)
+    n = len(encs)
+    h_in = [native.host_alloc(len(e)) for e in encs]
+    h_out = [native.host_alloc(len(p) + 64) for p in plains]
+    try:
+        for a, e in zip(h_in, encs):
+            a[:] = np.frombuffer(e, dtype=np.uint8)
+        in_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in h_in]); in_len = (C.c_size_t * n)(*[len(e) for e in encs])
+        out_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in h_out]); out_cap = (C.c_size_t * n)(*[a.size for a in h_out])
+        out_len, used, status = (C.c_size_t * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        for rep in range(2):                       # the second call reuses the context's feed events
+            for a in h_out:
+                a[:] = 0
+            rc = native.lib().b2f_decode_batch(ctx._h, native.FMT_GZIP, n, in_ptrs, in_len, out_ptrs, out_cap, out_len, used, status)
+            assert rc == 0
+            for i in range(n):
+                assert status[i] == 0 and out_len[i] == len(plains[i]) and used[i] == len(encs[i]), (rep, i, status[i], out_len[i])
+                assert h_out[i][:out_len[i]].tobytes() == plains[i], (rep, i)
+        # a truncated big stream in page-locked memory: same answer as the oracle (the pieces must not hide the error path)
+        cut = len(encs[0]) - 3000
+        in_len[0] = cut
+        rc = native.lib().b2f_decode_batch(ctx._h, native.FMT_GZIP, n, in_ptrs, in_len, out_ptrs, out_cap, out_len, used, status)
+        assert rc == 0
+        orc_rc, orc_out, _, _ = orc.decode(orc.FMT_GZIP, encs[0][:cut], cap=len(plains[0]) + 64)
+        assert status[0] == orc_rc != 0 and status[1] == 0 and h_out[1][:out_len[1]].tobytes() == plains[1]
+    finally:
+        for a in h_in + h_out:
+            native.host_free(a)
+
+
 def test_decode_output_too_small(ctx):
     d = b"abcabcabc" * 5000
     enc = orc.encode(orc.FMT_ZLIB, d)

@@ -738,18 +738,42 @@ int encode_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_s
     return B2F_OK;
 }
 
-// Stored mode (EncodeOptions::no_compression, RawBuf encode.rs:354-383): framing + memcpy only, plus the device checksum.
-void stored_stream(int fmt, const b2f_encode_opts &o, const uint8_t *in, size_t n, const int64_t *sched, size_t n_sched,
-                   uint32_t crc, uint32_t adler, std::vector<uint8_t> &out) {
-    make_header(fmt, o, out);
+// host arrays packed into one pinned staging block and one device block (one H2D copy)
+struct Packer {
+    PinBuf &pin; DevBuf &dev; size_t off = 0; std::vector<std::pair<const void *, size_t>> items; std::vector<size_t> offs;
+    Packer(PinBuf &p, DevBuf &d) : pin(p), dev(d) {}
+    size_t add(const void *src, size_t bytes) { size_t o = off; items.push_back({ src, bytes }); offs.push_back(o); off += align_up(bytes ? bytes : 1, 256); return o; }
+    size_t reserve(size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1, 256); return o; }     // device-only region
+    cudaError_t commit(cudaStream_t st) {
+        cudaError_t e = dev.ensure(off + 256); if (e != cudaSuccess) return e;
+        e = pin.ensure(off + 256); if (e != cudaSuccess) return e;
+        size_t hi = 0;
+        for (size_t i = 0; i < items.size(); i++) { if (items[i].second) memcpy(pin.as<uint8_t>() + offs[i], items[i].first, items[i].second); hi = std::max(hi, offs[i] + items[i].second); }
+        if (hi) e = cudaMemcpyAsync(dev.p, pin.p, hi, cudaMemcpyHostToDevice, st);
+        return e;
+    }
+    template <class T> T *ptr(size_t o) const { return reinterpret_cast<T *>(dev.as<uint8_t>() + o); }
+};
+
+// Stored mode (EncodeOptions::no_compression, RawBuf encode.rs:354-383): no compute besides the checksum, but the stream is still
+// assembled on the device -- the host only lays it out.  A stream is a list of copy records: literal bytes (container header, the
+// five header bytes of every stored block, sync markers, trailer; gathered in `blob`) and payload ranges of the input.
+struct CopyRec { uint64_t src; uint64_t dst; uint64_t n; };     // src: offset into the blob (bit 63 set) or into the input buffer
+constexpr uint64_t kRecBlob = 1ull << 63;
+uint64_t stored_layout(int fmt, const b2f_encode_opts &o, uint64_t in_base, size_t n, const int64_t *sched, size_t n_sched,
+                       uint32_t crc, uint32_t adler, uint64_t out_base, std::vector<uint8_t> &blob, std::vector<CopyRec> &recs) {
+    uint64_t out = 0;                                  // stream-relative output position
+    auto lit = [&](const uint8_t *b, size_t k) { recs.push_back({ kRecBlob | blob.size(), out_base + out, k }); blob.insert(blob.end(), b, b + k); out += k; };
+    std::vector<uint8_t> hdr; make_header(fmt, o, hdr);
+    if (!hdr.empty()) lit(hdr.data(), hdr.size());
     size_t bs = (size_t)o.block_size; if (bs > 0xFFFF) bs = 0xFFFF;
     size_t buf_start = 0, pos = 0;                     // RawBuf holds in[buf_start, pos)
     auto flush = [&](bool fin) {
-        size_t size = std::min<size_t>(pos - buf_start, 0xFFFF);
-        out.push_back(fin ? 1 : 0);                    // BFINAL + BTYPE=00, then BitWriter::flush pads the byte
-        out.push_back((uint8_t)size); out.push_back((uint8_t)(size >> 8));
-        uint16_t ns = (uint16_t)~size; out.push_back((uint8_t)ns); out.push_back((uint8_t)(ns >> 8));
-        out.insert(out.end(), in + buf_start, in + buf_start + size);
+        const size_t size = std::min<size_t>(pos - buf_start, 0xFFFF);
+        const uint16_t ns = (uint16_t)~size;
+        const uint8_t h[5] = { (uint8_t)(fin ? 1 : 0), (uint8_t)size, (uint8_t)(size >> 8), (uint8_t)ns, (uint8_t)(ns >> 8) };   // BFINAL + BTYPE=00, byte-aligned
+        lit(h, 5);
+        if (size) { recs.push_back({ in_base + buf_start, out_base + out, size }); out += size; }
         buf_start += size;
     };
     int64_t one = (int64_t)n;
@@ -757,7 +781,7 @@ void stored_stream(int fmt, const b2f_encode_opts &o, const uint8_t *in, size_t 
     for (size_t k = 0; k < n_sched; k++) {
         if (sched[k] < 0) {
             flush(false);
-            if (fmt == B2F_FMT_ZLIB && o.zlib_flush_sync) { const uint8_t m[5] = { 0, 0, 0, 255, 255 }; out.insert(out.end(), m, m + 5); }
+            if (fmt == B2F_FMT_ZLIB && o.zlib_flush_sync) { const uint8_t m[5] = { 0, 0, 0, 255, 255 }; lit(m, 5); }
             continue;
         }
         size_t w = (size_t)sched[k]; if (pos + w > n) w = n - pos;
@@ -765,8 +789,42 @@ void stored_stream(int fmt, const b2f_encode_opts &o, const uint8_t *in, size_t 
         while (pos - buf_start >= bs) flush(false);
     }
     flush(true);
-    if (fmt == B2F_FMT_GZIP) { for (int k = 0; k < 4; k++) out.push_back((uint8_t)(crc >> (8 * k))); uint32_t z = (uint32_t)n; for (int k = 0; k < 4; k++) out.push_back((uint8_t)(z >> (8 * k))); }
-    else if (fmt == B2F_FMT_ZLIB) { for (int k = 3; k >= 0; k--) out.push_back((uint8_t)(adler >> (8 * k))); }
+    if (fmt == B2F_FMT_GZIP) { uint8_t t[8]; for (int k = 0; k < 4; k++) { t[k] = (uint8_t)(crc >> (8 * k)); t[4 + k] = (uint8_t)((uint32_t)n >> (8 * k)); } lit(t, 8); }
+    else if (fmt == B2F_FMT_ZLIB) { uint8_t t[4]; for (int k = 0; k < 4; k++) t[k] = (uint8_t)(adler >> (8 * (3 - k))); lit(t, 4); }
+    return out;
+}
+__global__ void __launch_bounds__(256) k_copy_records(const CopyRec *__restrict__ recs, const uint8_t *__restrict__ in, const uint8_t *__restrict__ blob,
+                                                     uint8_t *__restrict__ out) {
+    const CopyRec r = recs[blockIdx.x];
+    const uint8_t *__restrict__ src = (r.src & kRecBlob) ? blob + (r.src & ~kRecBlob) : in + r.src;
+    uint8_t *__restrict__ dst = out + r.dst;
+    for (uint64_t i = threadIdx.x; i < r.n; i += 256) dst[i] = src[i];
+}
+// Stored-mode encode of a batch whose inputs are in d_in: checksums, layout, one copy kernel.  d_dst = where stream s goes
+// (dst_off[s]); streams whose output does not fit get OUTPUT_TOO_SMALL and are not written.
+int stored_on_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts &o, size_t n_streams, const uint8_t *d_in, const std::vector<uint64_t> &in_off,
+                     const std::vector<uint64_t> &in_len, const int64_t *const *sched, const size_t *n_sched,
+                     uint8_t *d_dst, const std::vector<uint64_t> &dst_off, const size_t *out_cap, size_t *out_len, int *status) {
+    std::vector<uint32_t> crc, adler;
+    int rc = run_checksums(ctx, d_in, in_off, in_len, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
+    if (rc) return rc;
+    std::vector<uint8_t> blob; std::vector<CopyRec> recs;
+    for (size_t s = 0; s < n_streams; s++) {
+        const size_t r0 = recs.size(), b0 = blob.size();
+        out_len[s] = (size_t)stored_layout(fmt, o, in_off[s], (size_t)in_len[s], sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0,
+                                           crc[s], adler[s], dst_off[s], blob, recs);
+        if (out_len[s] > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; recs.resize(r0); blob.resize(b0); } else status[s] = B2F_OK;
+    }
+    if (!recs.empty()) {
+        Packer P(ctx->pin_meta, ctx->buf[NB_DEC_META]);
+        const size_t a_r = P.add(recs.data(), recs.size() * sizeof(CopyRec)), a_b = P.add(blob.data(), blob.size());
+        CK(P.commit(ctx->stream));
+        ctx->tm.mark(ctx->stream, "stored_copy");
+        k_copy_records<<<(unsigned)recs.size(), 256, 0, ctx->stream>>>(P.ptr<CopyRec>(a_r), d_in, P.ptr<uint8_t>(a_b), d_dst);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+    }
+    return B2F_OK;
 }
 }  // namespace
 
@@ -794,9 +852,18 @@ extern "C" int b2f_encode_device(b2f_ctx *ctx, int fmt, const b2f_encode_opts *o
     if (n_streams && (!d_in || !in_off || !in_len || !d_out || !out_off || !out_cap || !out_len || !status)) { ctx->err = "NULL argument"; return B2F_ERR_INVALID_ARG; }
     b2f_encode_opts d; if (!opts) { b2f_encode_opts_default(&d); opts = &d; }
     int rc = validate_opts(ctx, fmt, *opts); if (rc) return rc;
-    if (opts->mode == B2F_MODE_STORED) { ctx->err = "stored mode has no device-resident variant (framing only)"; return B2F_ERR_INVALID_ARG; }
     CK(cudaSetDevice(ctx->device));
     ctx->tm.reset();
+    if (opts->mode == B2F_MODE_STORED) {
+        std::vector<uint64_t> io(in_off, in_off + n_streams), il(n_streams), oo(out_off, out_off + n_streams);
+        for (size_t s = 0; s < n_streams; s++) il[s] = effective_len(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s]);
+        rc = stored_on_device(ctx, fmt, *opts, n_streams, d_in, io, il, sched, n_sched, d_out, oo, out_cap, out_len, status);
+        if (rc) return rc;
+        ctx->tm.finish(ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
+        collect_stats(ctx, false);
+        return B2F_OK;
+    }
     EncodeJob job; job.d_in = d_in;
     job.in_off.assign(in_off, in_off + n_streams); job.in_len.resize(n_streams);
     for (size_t s = 0; s < n_streams; s++) job.in_len[s] = effective_len(sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, in_len[s]);
@@ -837,18 +904,17 @@ extern "C" int b2f_encode_batch(b2f_ctx *ctx, int fmt, const b2f_encode_opts *op
     if (opts->mode == B2F_MODE_STORED) {
         ctx->tm.mark(ctx->stream, "h2d");
         for (size_t s = 0; s < n_streams; s++) if (job.in_len[s]) CK(h2d_copy(ctx, d_in + job.in_off[s], in[s], job.in_len[s], ctx->stream, is_pinned_host(in[s])));
-        std::vector<uint32_t> crc, adler;
-        rc = run_checksums(ctx, d_in, job.in_off, job.in_len, fmt == B2F_FMT_GZIP, fmt == B2F_FMT_ZLIB, nullptr, crc, adler);
+        // the streams are assembled in the device output buffer (bound: 5 bytes per 65535 + container) and copied out
+        std::vector<uint64_t> dst_off(n_streams); uint64_t tout = 0;
+        for (size_t s = 0; s < n_streams; s++) { dst_off[s] = tout; tout += align_up(b2f_encode_bound((size_t)job.in_len[s], (sched && n_sched) ? n_sched[s] : 0, opts) + 16, 256); }
+        CK(ctx->buf[NB_OUT].ensure(tout + 512));
+        std::vector<size_t> cap(out_cap, out_cap + n_streams);
+        rc = stored_on_device(ctx, fmt, *opts, n_streams, d_in, job.in_off, job.in_len, sched, n_sched, ctx->buf[NB_OUT].as<uint8_t>(), dst_off, cap.data(), out_len, status);
         if (rc) return rc;
         ctx->tm.finish(ctx->stream);
+        for (size_t s = 0; s < n_streams; s++)
+            if (status[s] == B2F_OK) CK(d2h_copy(ctx, out[s], ctx->buf[NB_OUT].as<uint8_t>() + dst_off[s], out_len[s], ctx->stream, is_pinned_host(out[s])));
         CK(cudaStreamSynchronize(ctx->stream));
-        for (size_t s = 0; s < n_streams; s++) {
-            std::vector<uint8_t> o;
-            stored_stream(fmt, *opts, in[s], (size_t)job.in_len[s], sched ? sched[s] : nullptr, (sched && n_sched) ? n_sched[s] : 0, crc[s], adler[s], o);
-            out_len[s] = o.size();
-            if (o.size() > out_cap[s]) { status[s] = B2F_ERR_OUTPUT_TOO_SMALL; continue; }
-            memcpy(out[s], o.data(), o.size()); status[s] = B2F_OK;
-        }
         collect_stats(ctx, false);
         return B2F_OK;
     }
@@ -1069,21 +1135,6 @@ struct Member { size_t stream; uint64_t def_off; uint64_t def_len; uint64_t out_
                 uint64_t scan_len; };   // bytes of def_len the block finder / speculative parse may look at (0: in-order kernel)
 
 // Packs several host arrays into one pinned staging area + one H2D copy; returns device pointers.
-struct Packer {
-    PinBuf &pin; DevBuf &dev; size_t off = 0; std::vector<std::pair<const void *, size_t>> items; std::vector<size_t> offs;
-    Packer(PinBuf &p, DevBuf &d) : pin(p), dev(d) {}
-    size_t add(const void *src, size_t bytes) { size_t o = off; items.push_back({ src, bytes }); offs.push_back(o); off += align_up(bytes ? bytes : 1, 256); return o; }
-    size_t reserve(size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1, 256); return o; }     // device-only region
-    cudaError_t commit(cudaStream_t st) {
-        cudaError_t e = dev.ensure(off + 256); if (e != cudaSuccess) return e;
-        e = pin.ensure(off + 256); if (e != cudaSuccess) return e;
-        size_t hi = 0;
-        for (size_t i = 0; i < items.size(); i++) { if (items[i].second) memcpy(pin.as<uint8_t>() + offs[i], items[i].first, items[i].second); hi = std::max(hi, offs[i] + items[i].second); }
-        if (hi) e = cudaMemcpyAsync(dev.p, pin.p, hi, cudaMemcpyHostToDevice, st);
-        return e;
-    }
-    template <class T> T *ptr(size_t o) const { return reinterpret_cast<T *>(dev.as<uint8_t>() + o); }
-};
 
 constexpr uint64_t kParallelMinBytes = 128 * 1024;    // smaller streams are decoded in order by one warp each
 

@@ -555,6 +555,36 @@ def test_cli_mirror_of_examples_flate(tmp_path):
 
 
 @pytest.mark.gpu
+def test_stored_mode_is_assembled_on_the_device(ctx):
+    """EncodeOptions::no_compression (encode.rs:354-383): block headers, payload, sync markers and trailers are laid out by the
+    host and copied by one kernel -- host API and device API, all three containers, schedules with flushes, too-small output"""
+    import torch
+    from libflate_b200 import native, titles
+    d = titles.generate(700_001, seed=9).tobytes()
+    sched = [100_000, 65_535, -1, 1, 200_000, -1, -1, 334_465]
+    for fmt, kw in ((orc.FMT_DEFLATE, {}), (orc.FMT_ZLIB, dict(zlib_flush_sync=1)), (orc.FMT_GZIP, dict(mtime=7)), (orc.FMT_ZLIB, dict(block_size=1000))):
+        want = orc.encode(fmt, d, sched, mode=orc.MODE_STORED, **kw)
+        assert ctx.encode(fmt, d, sched, mode=native.MODE_STORED, **kw) == want, (fmt, kw)
+        rc, out, used, _ = orc.decode(fmt, want)
+        assert rc == 0 and out == d
+    # device API: two streams at odd offsets, the second one with too little room
+    datas = [d, d[:70_000]]
+    want = [orc.encode(orc.FMT_GZIP, x, mode=orc.MODE_STORED, mtime=0) for x in datas]
+    in_off = [1, len(d) + 6]
+    d_in = torch.zeros(in_off[1] + len(datas[1]) + 64, dtype=torch.uint8, device="cuda")
+    for o, x in zip(in_off, datas):
+        d_in[o:o + len(x)] = torch.frombuffer(bytearray(x), dtype=torch.uint8).cuda()
+    caps = [len(want[0]) + 10, len(want[1]) - 1]
+    e_off = [3, 3 + caps[0] + 5]
+    d_enc = torch.full((e_off[1] + caps[1] + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    ol, st = ctx.encode_device(native.FMT_GZIP, d_in.data_ptr(), in_off, [len(x) for x in datas], d_enc.data_ptr(), e_off, caps, None, mode=native.MODE_STORED, mtime=0)
+    assert st == [0, -3] and ol == [len(want[0]), len(want[1])]
+    host = d_enc.cpu().numpy()
+    assert bytes(host[e_off[0]:e_off[0] + ol[0]]) == want[0] and host[e_off[0] - 1] == 0xEE and host[e_off[0] + ol[0]] == 0xEE
+    assert (host[e_off[1]:e_off[1] + caps[1]] == 0xEE).all()                  # the stream that does not fit is not written at all
+
+
+@pytest.mark.gpu
 def test_device_api_unaligned_offsets(ctx):
     """b2f_encode_device / b2f_decode_device with odd byte offsets on both sides (the resolve kernel writes aligned words only
     where a word is wholly owned by one unit)."""

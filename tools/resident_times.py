@@ -8,7 +8,7 @@ size = 277303937
 ctx = native.Context(0)
 L = native.lib()
 data = titles.generate(size, seed=42)
-sched = [8192] * (size // 8192) + ([size % 8192] if size % 8192 else [])
+sched = np.asarray([8192] * (size // 8192) + ([size % 8192] if size % 8192 else []), dtype=np.int64)   # an array: no per-call list conversion in the binding
 bound = L.b2f_encode_bound(size, len(sched), None)
 d_in = torch.from_numpy(data).cuda()
 d_enc = torch.empty(bound + 256, dtype=torch.uint8, device="cuda")

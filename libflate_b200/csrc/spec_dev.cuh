@@ -15,11 +15,21 @@ constexpr uint32_t kSpecCta = B2F_SPEC_CTA;        // subsegments per CTA (all o
 // window of the block's output.  One warp resolves a segment on its own; bytes copied from before the segment's first byte
 // become 16-bit MARKERS (0x8000 | distance before the segment start - 1) that a second pass substitutes in stream order.
 #ifndef B2F_SEG_BYTES
-#define B2F_SEG_BYTES 6144
+#define B2F_SEG_BYTES 4096
 #endif
 constexpr uint32_t kSegBytes = B2F_SEG_BYTES;   // output bytes per segment slot (a segment can be longer: its last subsegment is never split)
-constexpr uint32_t kSegRing = 8192;       // symbols of a segment kept in shared memory by k_seg_resolve
-constexpr uint32_t kSegStepMax = 4096;    // output symbols of one 32-token step (a step with more output is cut short)
+#ifndef B2F_SEG_RING
+#define B2F_SEG_RING 4096
+#endif
+#ifndef B2F_SEG_STEPMAX
+#define B2F_SEG_STEPMAX (B2F_SEG_RING / 2)
+#endif
+#ifndef B2F_SEG_LAZY
+#define B2F_SEG_LAZY (B2F_SEG_RING / 4)
+#endif
+constexpr uint32_t kSegRing = B2F_SEG_RING;          // symbols of a segment kept in shared memory by k_seg_resolve
+constexpr uint32_t kSegStepMax = B2F_SEG_STEPMAX;    // output symbols of one 32-token step (a step with more output is cut short)
+constexpr uint32_t kSegLazy = B2F_SEG_LAZY;          // symbols that may wait in the ring before they are written to sym16
 constexpr uint32_t kMarker = 0x8000u;
 constexpr uint32_t kChainCounters = 8;
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;

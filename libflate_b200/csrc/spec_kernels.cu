@@ -10,7 +10,7 @@
 //   k_spec_verify    CTA per block  : checks that every start equals its left neighbour's exit (=> by induction the true
 //                    parse), finds EndOfBlock, exclusive scans of symbol/byte counts
 //   k_spec_tokens    thread per subsegment: final decode from the true start, writes one token per symbol
-//   k_seg_plan/resolve/cuts/subst : LZ77 resolution of the token stream by ~6 KiB segments, one warp each, with 16-bit
+//   k_seg_plan/resolve/cuts/subst : LZ77 resolution of the token stream by ~4 KiB segments, one warp each, with 16-bit
 //                    markers for bytes copied from before the segment; one substitution pass per chain of dependent segments
 // Nothing here is trusted blindly: the host accepts a block only if its verified EndOfBlock lands exactly on the next
 // block of the chain; otherwise the stream goes to the exact in-order kernel (decode_kernels.cu).
@@ -355,7 +355,6 @@ __global__ void __launch_bounds__(128) k_seg_plan(SpecDev S, uint32_t slot_lo, u
 }
 
 constexpr uint32_t kSegMask = kSegRing - 1;
-constexpr uint32_t kSegLazy = 2048;                               // symbols that may wait in the ring before they are written to sym16
 constexpr uint32_t kSegFreeQ = 2 * kSegRing;                     // byte offset of the queue of order-free copies (<= 64 entries + 4 read-ahead)
 constexpr uint32_t kSegOrdQ = kSegFreeQ + 68 * 8;                // byte offset of the queue of in-order copies (<= 32 entries + 2 read-ahead)
 constexpr uint32_t kSegSmem = kSegOrdQ + 34 * 8;

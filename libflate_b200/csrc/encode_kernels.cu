@@ -725,7 +725,10 @@ __global__ void __launch_bounds__(256) k_lz_fixup2(EncDev E, uint32_t slice) {
 // The DP's ring of the last 260 exits lives in shared memory as [index][lane]; when the DP is done it holds the exits of positions
 // 0..259, i.e. the tile's exit table, which is written out tile by tile with contiguous stores.
 constexpr uint32_t kRing = 260;
-constexpr uint32_t kPxWarps = 4;
+#ifndef B2F_PX_WARPS
+#define B2F_PX_WARPS 1
+#endif
+constexpr uint32_t kPxWarps = B2F_PX_WARPS;
 constexpr uint32_t kPxWarpSmem = 32 * 33 * 4 + kRing * 32 * 2 + 32 * 8 + 32 * 4;      // md chunk | ring | row pointers | row lengths
 constexpr uint32_t kPxSmem = kPxWarps * kPxWarpSmem;
 __global__ void __launch_bounds__(kPxWarps * 32) k_parse_exits(EncDev E, uint32_t off, uint32_t lim) {
